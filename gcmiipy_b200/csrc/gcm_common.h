@@ -1,0 +1,92 @@
+// gcm_common.h -- shared declarations of the sm_100a kernels behind include/gcm_b200.h
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gcm_b200.h"
+
+#ifdef GCM_EMU
+#include "cuda_emu.h"  // tests/emu: CPU execution of these sources for the no-GPU test-suite only
+#define GCM_LAUNCH(kern, grid, block, smem, stream, ...) \
+  gcm_emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#define GCM_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(gcm_emu::dyn_smem())
+#else
+#include <cuda_runtime.h>
+#define GCM_LAUNCH(kern, grid, block, smem, stream, ...) \
+  kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define GCM_DYN_SMEM(type, name)                                 \
+  extern __shared__ __align__(16) unsigned char gcm_dyn_smem_[]; \
+  type* name = reinterpret_cast<type*>(gcm_dyn_smem_)
+#endif
+
+#define GCM_CHECK_LAUNCH()                        \
+  do {                                            \
+    cudaError_t e_ = cudaGetLastError();          \
+    if (e_ != cudaSuccess) return (int)e_;        \
+  } while (0)
+#define GCM_CUDA(call)                            \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) return (int)e_;        \
+  } while (0)
+#define GCM_REQUIRE(cond, code) \
+  do {                          \
+    if (!(cond)) return (code); \
+  } while (0)
+
+// physical constants, SI (reference constants.py:16-48)
+#define GCM_RD 287.0
+#define GCM_CP 1004.0
+#define GCM_KAPPA (287.0 / 1004.0)
+#define GCM_P0 100000.0
+#define GCM_G 9.8
+
+#define GCM_MAX_RADIX_PASSES 24
+
+// Stockham mixed-radix plan for one row of length n (see fft_rows.h)
+struct GcmFftPlan {
+  int n;
+  int npass;
+  int radix[GCM_MAX_RADIX_PASSES];
+};
+
+// device-resident geometry tables, passed to kernels by value
+struct GcmGeomDev {
+  int H, W, L;
+  int wrap_j;
+  int row_lo, row_hi;
+  int zero_v_row;
+  double dy, ptop;
+  const double* sig;
+  const double* dsig;
+  const double* sigb;
+  const double* sigt;
+  const double* dx_j;
+  const double* dx_h;
+  const double* hmap;
+  const double* smmz;   // [H][W/2+1]
+  const double2* tw;    // [W]  exp(-2 pi i m / W)
+  GcmFftPlan plan;
+};
+
+struct gcm_geom {
+  GcmGeomDev d;
+  void* d_block;  // one device allocation holding every table
+};
+
+static inline bool gcm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// neighbour row in j: periodic like np.roll when the geometry stores the whole grid, plain offset
+// when it stores a band with halo rows
+__host__ __device__ __forceinline__ int gcm_row(int j, int d, int H, int wrap) {
+  int r = j + d;
+  if (wrap) {
+    if (r < 0) r += H;
+    if (r >= H) r -= H;
+  }
+  return r;
+}
+__host__ __device__ __forceinline__ int gcm_ip(int i, int W) { return i + 1 == W ? 0 : i + 1; }
+__host__ __device__ __forceinline__ int gcm_im(int i, int W) { return i == 0 ? W - 1 : i - 1; }
+
+int gcm_fft_make_plan(int n, GcmFftPlan* plan);

@@ -1,0 +1,118 @@
+// geom.cu -- device-resident metric / sigma / filter tables (reference geometry.py:9-182, low_pass.py:61-72)
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "gcm_common.h"
+
+extern "C" int gcm_version(void) { return 100; }
+
+extern "C" const char* gcm_status_string(int s) {
+  switch (s) {
+    case GCM_OK: return "ok";
+    case GCM_ENULL: return "required pointer is NULL";
+    case GCM_ESHAPE: return "bad extent or row range";
+    case GCM_EALIGN: return "device pointer not 16-byte aligned";
+    case GCM_EUNSUP: return "unsupported combination";
+    case GCM_EWORK: return "workspace too small";
+    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+  }
+}
+
+// radices 4,2,3,5 get unrolled butterflies; any other prime factor takes the generic O(R^2) pass
+int gcm_fft_make_plan(int n, GcmFftPlan* plan) {
+  plan->n = n;
+  plan->npass = 0;
+  int m = n;
+  const int pref[4] = {4, 2, 3, 5};
+  for (int f = 0; f < 4; ++f)
+    while (m % pref[f] == 0) {
+      if (plan->npass >= GCM_MAX_RADIX_PASSES) return GCM_EUNSUP;
+      plan->radix[plan->npass++] = pref[f];
+      m /= pref[f];
+    }
+  for (int p = 7; m > 1; p += 2)
+    while (m % p == 0) {
+      if (plan->npass >= GCM_MAX_RADIX_PASSES) return GCM_EUNSUP;
+      plan->radix[plan->npass++] = p;
+      m /= p;
+    }
+  return GCM_OK;
+}
+
+static size_t up256(size_t b) { return (b + 255) / 256 * 256; }
+
+extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
+  GCM_REQUIRE(d && out, GCM_ENULL);
+  GCM_REQUIRE(d->h_sig && d->h_dsig && d->h_sigb && d->h_sigt && d->h_dx_j && d->h_dx_h, GCM_ENULL);
+  const int H = d->H, W = d->W, L = d->L;
+  GCM_REQUIRE(H > 0 && W > 0 && L > 0, GCM_ESHAPE);
+  GCM_REQUIRE(W == 1 || W % 2 == 0, GCM_ESHAPE);  // the reference filter breaks on odd W (low_pass.py:57)
+  GCM_REQUIRE(W == 1 || d->h_smmz, GCM_ENULL);
+  GCM_REQUIRE(d->row_lo >= 0 && d->row_lo < d->row_hi && d->row_hi <= H, GCM_ESHAPE);
+  if (d->wrap_j) GCM_REQUIRE(d->row_lo == 0 && d->row_hi == H, GCM_ESHAPE);
+  // a band needs 1 halo row to the north and 2 to the south of its owned rows
+  if (!d->wrap_j) GCM_REQUIRE(d->row_lo >= 1 && d->row_hi + 2 <= H, GCM_ESHAPE);
+  GCM_REQUIRE(d->zero_v_row >= -1 && d->zero_v_row < H, GCM_ESHAPE);
+
+  gcm_geom* g = (gcm_geom*)calloc(1, sizeof(gcm_geom));
+  GCM_REQUIRE(g, (int)cudaErrorMemoryAllocation);
+  int st = gcm_fft_make_plan(W, &g->d.plan);
+  if (st != GCM_OK) { free(g); return st; }
+
+  const size_t nw = (size_t)W / 2 + 1;
+  const size_t o_sig = 0, o_dsig = o_sig + up256(L * 8), o_sigb = o_dsig + up256(L * 8), o_sigt = o_sigb + up256(L * 8);
+  const size_t o_dxj = o_sigt + up256(L * 8), o_dxh = o_dxj + up256(H * 8), o_hmap = o_dxh + up256(H * 8);
+  const size_t o_smmz = o_hmap + up256((size_t)H * W * 8), o_tw = o_smmz + up256((size_t)H * nw * 8);
+  const size_t total = o_tw + up256((size_t)W * 16);
+
+  std::vector<unsigned char> host(total, 0);
+  memcpy(&host[o_sig], d->h_sig, L * 8);
+  memcpy(&host[o_dsig], d->h_dsig, L * 8);
+  memcpy(&host[o_sigb], d->h_sigb, L * 8);
+  memcpy(&host[o_sigt], d->h_sigt, L * 8);
+  memcpy(&host[o_dxj], d->h_dx_j, H * 8);
+  memcpy(&host[o_dxh], d->h_dx_h, H * 8);
+  if (d->h_heightmap) memcpy(&host[o_hmap], d->h_heightmap, (size_t)H * W * 8);
+  if (d->h_smmz) memcpy(&host[o_smmz], d->h_smmz, (size_t)H * nw * 8);
+  double* tw = reinterpret_cast<double*>(&host[o_tw]);
+  for (int m = 0; m < W; ++m) {  // exp(-2 pi i m / W), evaluated in long double
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)W;
+    tw[2 * m] = (double)cosl(a);
+    tw[2 * m + 1] = (double)(-sinl(a));
+  }
+
+  void* blk = nullptr;
+  cudaError_t e = cudaMalloc(&blk, total);
+  if (e != cudaSuccess) { free(g); return (int)e; }
+  e = cudaMemcpy(blk, host.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(blk); free(g); return (int)e; }
+
+  unsigned char* b = (unsigned char*)blk;
+  g->d_block = blk;
+  g->d.H = H; g->d.W = W; g->d.L = L;
+  g->d.wrap_j = d->wrap_j ? 1 : 0;
+  g->d.row_lo = d->row_lo; g->d.row_hi = d->row_hi;
+  g->d.zero_v_row = d->zero_v_row;
+  g->d.dy = d->dy; g->d.ptop = d->ptop;
+  g->d.sig = (const double*)(b + o_sig);
+  g->d.dsig = (const double*)(b + o_dsig);
+  g->d.sigb = (const double*)(b + o_sigb);
+  g->d.sigt = (const double*)(b + o_sigt);
+  g->d.dx_j = (const double*)(b + o_dxj);
+  g->d.dx_h = (const double*)(b + o_dxh);
+  g->d.hmap = (const double*)(b + o_hmap);
+  g->d.smmz = (const double*)(b + o_smmz);
+  g->d.tw = (const double2*)(b + o_tw);
+  *out = g;
+  return GCM_OK;
+}
+
+extern "C" int gcm_geom_destroy(gcm_geom* g) {
+  if (!g) return GCM_OK;
+  cudaFree(g->d_block);
+  free(g);
+  return GCM_OK;
+}

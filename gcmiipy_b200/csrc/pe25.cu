@@ -1,0 +1,653 @@
+// pe25.cu -- 2.5-D sigma-layer primitive-equation Matsuno step (reference dynamics.py:15-237)
+//
+// One half step = 4 kernels, split at the dependency barriers of dynamics.half_timestep:
+//   A  pe25_spu_filter_kernel   rows x layer pairs   spu = arakawa_1977(su * iph(sp))           (:187-189)
+//   B  pe25_column_kernel       one thread / column  rho, phi (hydrostatic scan), conv, pit, sd, p_n (:193-194, :111-142)
+//   C  pe25_pgf_filter_kernel   rows x layer pairs   pgf_f = arakawa_1977(pgfu + phiu)            (:198, :202)
+//   D  pe25_update_kernel       one thread / cell    momentum, tracer update, un_pu/un_pv        (:197-222)
+// Rows are periodic in j (np.roll) when the geometry stores the whole grid and plain neighbours when it
+// stores a latitude band with halo rows; kernels B (and A) also run on the first halo row south of the
+// band because row j of the update needs pit, sd, phi, rho and filtered spu at row j + 1.
+#include "fft_rows.h"
+#include "gcm_common.h"
+
+#define IDX3(k, j, i) (((size_t)(k) * H + (size_t)(j)) * W + (size_t)(i))
+#define IDX2(j, i) ((size_t)(j) * W + (size_t)(i))
+
+// ---------------------------------------------------------------------------------------------------
+// accessors: a mass flux either comes from an array or is formed on the fly from velocity and pressure
+// ---------------------------------------------------------------------------------------------------
+struct GcmArr3 {
+  const double* a;
+  int H, W;
+  __device__ __forceinline__ double operator()(int k, int j, int i) const { return a[IDX3(k, j, i)]; }
+};
+// calc_pv (dynamics.py:20): pv = v * jph(p)
+struct GcmPvInline {
+  const double* v;
+  const double* p;
+  int H, W, wrap;
+  __device__ __forceinline__ double operator()(int k, int j, int i) const {
+    const int jp = gcm_row(j, 1, H, wrap);
+    return v[IDX3(k, j, i)] * ((p[IDX2(j, i)] + p[IDX2(jp, i)]) / 2);
+  }
+};
+
+static int gcm_fft_threads(int W) {
+  int t = (W / 4 + 31) / 32 * 32;
+  return t < 32 ? 32 : (t > 256 ? 256 : t);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column device functions
+// ---------------------------------------------------------------------------------------------------
+// dynamics.compute_geopotential (dynamics.py:111-142) for one column; also rho of pgf (:150-152).
+// t, phi, rho point at layer 0 of the column; ks = layer stride.  T = theta * (p/P0)^kappa reuses the
+// Exner factor of the scan (the reference evaluates theta / (P0/p)^kappa: same value to rounding).
+__device__ __forceinline__ void gcm_col_geopotential(const GcmGeomDev& g, double spc, double hm, const double* t,
+                                                     size_t ks, double* phi, double* rho) {
+  const int L = g.L;
+  const double ptop = g.ptop;
+  double sum = 0.0;
+  double tp = spc * g.sig[0] + ptop;
+  double pk = pow((g.sig[0] * spc + ptop) / GCM_P0, GCM_KAPPA);
+  double tk = t[0];
+  const double pk0 = pk, t0 = tk;
+  for (int k = 0; k < L; ++k) {
+    double tp_n = tp, pk_n = pk0, t_n = t0;  // k + 1 wraps to layer 0 (coordinates_3d.py:55); sigt[L-1] = 0 kills it
+    if (k + 1 < L) {
+      const double sg = g.sig[k + 1];
+      tp_n = spc * sg + ptop;
+      pk_n = pow((sg * spc + ptop) / GCM_P0, GCM_KAPPA);
+      t_n = t[(size_t)(k + 1) * ks];
+    }
+    const double tt = tk * pk;                    // temperature.to_true_temp
+    const double r = tp / (GCM_RD * tt);
+    const double spa = (g.sig[k] * spc) / r;
+    const double s1 = spa * g.dsig[k];
+    const double stp = GCM_CP * ((tk + t_n) / 2) * (pk - pk_n);
+    const double s2 = g.sigt[k] * stp;
+    sum += (s1 - s2);
+    if (k + 1 < L) phi[(size_t)(k + 1) * ks] = stp;  // stp_n = km(stp); stp_n[0] is overwritten below
+    if (rho) rho[(size_t)k * ks] = r;
+    tp = tp_n; pk = pk_n; tk = t_n;
+  }
+  double run = sum + hm * GCM_G;
+  phi[0] = run;
+  for (int k = 1; k < L; ++k) {
+    run = run + phi[(size_t)k * ks];
+    phi[(size_t)k * ks] = run;
+  }
+}
+
+// dynamics.aflux (dynamics.py:35-46) for one column (j, i); sd points at layer 0 of the column
+template <class FPU, class FPV>
+__device__ __forceinline__ double gcm_col_aflux(const GcmGeomDev& g, const FPU& pu, const FPV& pv, int j, int jm, int i,
+                                                int im, double* sd, size_t ks) {
+  const int L = g.L;
+  const double dxj = g.dx_j[j], dy = g.dy;
+  double pit = 0.0;
+  for (int k = 0; k < L; ++k) {
+    const double conv = ((pu(k, j, i) - pu(k, j, im)) / dxj + (pv(k, j, i) - pv(k, jm, i)) / dy) * g.dsig[k];
+    pit += conv;  // np.sum(conv, 0): k ascending
+    sd[(size_t)k * ks] = conv;
+  }
+  double acc = 0.0;  // np.cumsum(conv[::-1], 0)[::-1]: k descending
+  for (int k = L - 1; k >= 0; --k) {
+    acc += sd[(size_t)k * ks];
+    sd[(size_t)k * ks] = acc - pit * g.sigb[k];
+  }
+  sd[0] = 0.0;  // dynamics.py:44
+  return pit;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cell device functions
+// ---------------------------------------------------------------------------------------------------
+// dynamics.advec_m_pu (dynamics.py:55-108); Coriolis is hard-disabled in the reference (:82) and adds 0
+template <class FPU, class FPV>
+__device__ __forceinline__ void gcm_cell_advec_m(const GcmGeomDev& g, const double* u, const double* v, const FPU& pu,
+                                                 const FPV& pv, int k, int j, int jm, int jp, int i, int im, int ip,
+                                                 double* dut, double* dvt) {
+  const int H = g.H, W = g.W;
+  const double u_c = u[IDX3(k, j, i)], u_im = u[IDX3(k, j, im)], u_ip = u[IDX3(k, j, ip)];
+  const double u_jp = u[IDX3(k, jp, i)], u_jm = u[IDX3(k, jm, i)];
+  const double v_c = v[IDX3(k, j, i)], v_im = v[IDX3(k, j, im)], v_ip = v[IDX3(k, j, ip)];
+  const double v_jp = v[IDX3(k, jp, i)], v_jm = v[IDX3(k, jm, i)];
+  const double pu_c = pu(k, j, i), pu_im = pu(k, j, im), pu_ip = pu(k, j, ip);
+  const double pu_jp = pu(k, jp, i), pu_jp_im = pu(k, jp, im);
+  const double pv_c = pv(k, j, i), pv_ip = pv(k, j, ip), pv_jm = pv(k, jm, i), pv_jm_ip = pv(k, jm, ip);
+  const double pv_jp = pv(k, jp, i);
+  const double puum = ((u_c + u_im) / 2) * ((pu_c + pu_im) / 2);
+  const double puup = ((u_ip + u_c) / 2) * ((pu_ip + pu_c) / 2);
+  const double puvp = ((pv_c + pv_ip) / 2) * ((u_c + u_jp) / 2);
+  const double puvm = ((pv_jm + pv_jm_ip) / 2) * ((u_jm + u_c) / 2);
+  const double pvvm = ((v_c + v_jm) / 2) * ((pv_c + pv_jm) / 2);
+  const double pvvp = ((v_jp + v_c) / 2) * ((pv_jp + pv_c) / 2);
+  const double pvup = ((v_c + v_ip) / 2) * ((pu_c + pu_jp) / 2);
+  const double pvum = ((v_im + v_c) / 2) * ((pu_im + pu_jp_im) / 2);
+  *dut = (puum - puup) / g.dx_j[j] + (puvm - puvp) / g.dy + 0.0;
+  *dvt = (pvvm - pvvp) / g.dy + (pvum - pvup) / g.dx_h[j] + 0.0;
+}
+
+// dynamics.advec_sig (dynamics.py:49-52) with the sigma-dot of layers k and k+1 given
+__device__ __forceinline__ double gcm_cell_advec_sig(const GcmGeomDev& g, const double* q, double sd_k, double sd_kp,
+                                                     int k, int km, int kp, int j, int i) {
+  const int H = g.H, W = g.W;
+  const double q_k = q[IDX3(k, j, i)], q_km = q[IDX3(km, j, i)], q_kp = q[IDX3(kp, j, i)];
+  const double flux = ((q_k + q_km) / 2) * sd_k;
+  const double flux_p = ((q_kp + q_k) / 2) * sd_kp;
+  return -((flux - flux_p) / g.dsig[k]);
+}
+
+// dynamics.advec_t (dynamics.py:174-181)
+template <class FPU, class FPV>
+__device__ __forceinline__ double gcm_cell_advec_t(const GcmGeomDev& g, const double* t, const FPU& pu, const FPV& pv,
+                                                   int k, int j, int jm, int jp, int i, int im, int ip) {
+  const int H = g.H, W = g.W;
+  const double t_c = t[IDX3(k, j, i)];
+  const double tpu = pu(k, j, i) * ((t_c + t[IDX3(k, j, ip)]) / 2);
+  const double tpu_m = pu(k, j, im) * ((t[IDX3(k, j, im)] + t_c) / 2);
+  const double tpv = pv(k, j, i) * ((t_c + t[IDX3(k, jp, i)]) / 2);
+  const double tpv_m = pv(k, jm, i) * ((t[IDX3(k, jm, i)] + t_c) / 2);
+  return (tpu - tpu_m) / g.dx_j[j] + (tpv - tpv_m) / g.dy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A: spu = arakawa_1977(su * iph(sp))  (dynamics.py:187-189).  Also the plain filter (mode 0).
+// grid = (ceil(layers/2), rows, batch)
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>  // 0: out = filter(in)   1: out = filter(in * iph(p))
+__global__ void pe25_filter_kernel(GcmGeomDev g, const double* __restrict__ in, const double* __restrict__ p,
+                                   double* __restrict__ out, const double* __restrict__ table, int nlayers, int ja,
+                                   size_t bstride2, size_t bstride3) {
+  GCM_DYN_SMEM(double2, smem);
+  const int H = g.H, W = g.W;
+  double2* a = smem;
+  double2* b = smem + W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int j = ja + blockIdx.y;
+  const int k0 = 2 * blockIdx.x, k1 = k0 + 1;
+  const bool has1 = k1 < nlayers;
+  in += blockIdx.z * bstride3;
+  out += blockIdx.z * bstride3;
+  const double* prow = MODE == 1 ? p + blockIdx.z * bstride2 + IDX2(j, 0) : nullptr;
+  const double* r0 = in + IDX3(k0, j, 0);
+  const double* r1 = in + IDX3(has1 ? k1 : k0, j, 0);
+  for (int i = tid; i < W; i += nthr) {
+    double x0 = r0[i], x1 = has1 ? r1[i] : 0.0;
+    if (MODE == 1) {
+      const double ph = (prow[i] + prow[gcm_ip(i, W)]) / 2;
+      x0 = x0 * ph;
+      x1 = x1 * ph;
+    }
+    a[i] = make_double2(x0, x1);
+  }
+  __syncthreads();
+  const double2* r = gcm_filter_pair(a, b, g.plan, g.tw, table + (size_t)j * (W / 2 + 1), tid, nthr);
+  const double inv = 1.0 / W;
+  double* o0 = out + IDX3(k0, j, 0);
+  double* o1 = out + IDX3(has1 ? k1 : k0, j, 0);
+  for (int i = tid; i < W; i += nthr) {
+    const double2 v = r[i];
+    o0[i] = W == 1 ? v.x : v.x * inv;
+    if (has1) o1[i] = W == 1 ? v.y : v.y * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// B: per column: rho, phi (dynamics.py:111-142,150-152), conv/pit/sd (:35-46), p_n = p - pit dt (:194)
+// grid = (ceil(W/T), rows, batch)
+// ---------------------------------------------------------------------------------------------------
+__global__ void pe25_column_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ sp,
+                                   const double* __restrict__ sv, const double* __restrict__ st,
+                                   const double* __restrict__ spu, double* __restrict__ phi, double* __restrict__ rho,
+                                   double* __restrict__ sd, double* __restrict__ pit, double* __restrict__ pn,
+                                   double dt, int ja, size_t bstride2, size_t bstride3) {
+  const int H = g.H, W = g.W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y;
+  const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
+  p += o2; sp += o2; pit += o2; pn += o2;
+  sv += o3; st += o3; spu += o3; phi += o3; rho += o3; sd += o3;
+  const size_t ks = (size_t)H * W;
+  const size_t c = IDX2(j, i);
+  gcm_col_geopotential(g, sp[c], g.hmap[c], st + c, ks, phi + c, rho + c);
+  const int jm = gcm_row(j, -1, H, g.wrap_j), im = gcm_im(i, W);
+  GcmArr3 fpu{spu, H, W};
+  GcmPvInline fpv{sv, sp, H, W, g.wrap_j};
+  const double pt = gcm_col_aflux(g, fpu, fpv, j, jm, i, im, sd + c, ks);
+  pit[c] = pt;
+  pn[c] = p[c] - pt * dt;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C: pgf_f = arakawa_1977(pgfu + phiu)  (dynamics.py:159,162-165,202)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gcm_pgu_plus_phiu(const GcmGeomDev& g, const double* sprow, const double* phirow,
+                                                    const double* rhorow, double sg, double dxj, int i, int ip) {
+  const double p_c = sprow[i], p_ip = sprow[ip];
+  const double gradp = (p_ip - p_c) / dxj;
+  const double pgu = (((sg * p_c) + (sg * p_ip)) / 2) / ((rhorow[i] + rhorow[ip]) / 2) * gradp;
+  const double phiu = ((p_c + p_ip) / 2) * ((phirow[ip] - phirow[i]) / dxj);
+  return pgu + phiu;
+}
+
+__global__ void pe25_pgf_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* __restrict__ phi,
+                                       const double* __restrict__ rho, double* __restrict__ out, int ja,
+                                       size_t bstride2, size_t bstride3) {
+  GCM_DYN_SMEM(double2, smem);
+  const int H = g.H, W = g.W, L = g.L;
+  double2* a = smem;
+  double2* b = smem + W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int j = ja + blockIdx.y;
+  const int k0 = 2 * blockIdx.x, k1 = k0 + 1;
+  const bool has1 = k1 < L;
+  const int k1s = has1 ? k1 : k0;
+  sp += blockIdx.z * bstride2;
+  phi += blockIdx.z * bstride3; rho += blockIdx.z * bstride3; out += blockIdx.z * bstride3;
+  const double* sprow = sp + IDX2(j, 0);
+  const double dxj = g.dx_j[j];
+  const double sg0 = g.sig[k0], sg1 = g.sig[k1s];
+  for (int i = tid; i < W; i += nthr) {
+    const int ip = gcm_ip(i, W);
+    const double x0 = gcm_pgu_plus_phiu(g, sprow, phi + IDX3(k0, j, 0), rho + IDX3(k0, j, 0), sg0, dxj, i, ip);
+    const double x1 = has1 ? gcm_pgu_plus_phiu(g, sprow, phi + IDX3(k1, j, 0), rho + IDX3(k1, j, 0), sg1, dxj, i, ip) : 0.0;
+    a[i] = make_double2(x0, x1);
+  }
+  __syncthreads();
+  const double2* r = gcm_filter_pair(a, b, g.plan, g.tw, g.smmz + (size_t)j * (W / 2 + 1), tid, nthr);
+  const double inv = 1.0 / W;
+  double* o0 = out + IDX3(k0, j, 0);
+  double* o1 = out + IDX3(k1s, j, 0);
+  for (int i = tid; i < W; i += nthr) {
+    const double2 v = r[i];
+    o0[i] = W == 1 ? v.x : v.x * inv;
+    if (has1) o1[i] = W == 1 ? v.y : v.y * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D: everything else of half_timestep for one cell (dynamics.py:186,190,197-222)
+// grid = (ceil(W/T), rows, L * batch)
+// ---------------------------------------------------------------------------------------------------
+struct GcmStateC {
+  const double *p, *u, *v, *t, *q;
+};
+struct GcmStateM {
+  double *p, *u, *v, *t, *q;
+};
+
+__global__ void pe25_update_kernel(GcmGeomDev g, GcmStateC base, GcmStateC star, GcmStateM out,
+                                   const double* __restrict__ spu, const double* __restrict__ sd,
+                                   const double* __restrict__ phi, const double* __restrict__ rho,
+                                   const double* __restrict__ pgf, const double* __restrict__ pn, double dt, int ja,
+                                   size_t bstride2, size_t bstride3) {
+  const int H = g.H, W = g.W, L = g.L;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y;
+  const int k = blockIdx.z % L;
+  const size_t o2 = (blockIdx.z / L) * bstride2, o3 = (blockIdx.z / L) * bstride3;
+  const double* p = base.p + o2; const double* u = base.u + o3; const double* v = base.v + o3;
+  const double* t = base.t + o3; const double* q = base.q + o3;
+  const double* sp = star.p + o2; const double* su = star.u + o3; const double* sv = star.v + o3;
+  const double* st = star.t + o3; const double* sq = star.q + o3;
+  spu += o3; sd += o3; phi += o3; rho += o3; pgf += o3; pn += o2;
+
+  const int wrap = g.wrap_j;
+  const int jm = gcm_row(j, -1, H, wrap), jp = gcm_row(j, 1, H, wrap);
+  const int im = gcm_im(i, W), ip = gcm_ip(i, W);
+  const int km = k == 0 ? L - 1 : k - 1, kp = k == L - 1 ? 0 : k + 1;
+  const double dy = g.dy;
+
+  GcmArr3 fpu{spu, H, W};
+  GcmPvInline fpv{sv, sp, H, W, wrap};
+
+  double dut, dvt;
+  gcm_cell_advec_m(g, su, sv, fpu, fpv, k, j, jm, jp, i, im, ip, &dut, &dvt);
+
+  // pgf, v direction (dynamics.py:160,167-169); the u direction comes filtered from kernel C
+  const double sp_c = sp[IDX2(j, i)], sp_jp = sp[IDX2(jp, i)];
+  const double sg = g.sig[k];
+  const double phiv = ((sp_c + sp_jp) / 2) * ((phi[IDX3(k, jp, i)] - phi[IDX3(k, j, i)]) / dy);
+  const double pgv = (((sg * sp_c) + (sg * sp_jp)) / 2) / ((rho[IDX3(k, j, i)] + rho[IDX3(k, jp, i)]) / 2) *
+                     ((sp_jp - sp_c) / dy);
+
+  // vertical advection of momentum (dynamics.py:199-200): sigma-dot averaged to the u and v points
+  const double sd_k = sd[IDX3(k, j, i)], sd_kp = sd[IDX3(kp, j, i)];
+  const double sdu_k = (sd_k + sd[IDX3(k, j, ip)]) / 2, sdu_kp = (sd_kp + sd[IDX3(kp, j, ip)]) / 2;
+  const double sdv_k = (sd_k + sd[IDX3(k, jp, i)]) / 2, sdv_kp = (sd_kp + sd[IDX3(kp, jp, i)]) / 2;
+  const double dus = gcm_cell_advec_sig(g, su, sdu_k, sdu_kp, k, km, kp, j, i);
+  const double dvs = gcm_cell_advec_sig(g, sv, sdv_k, sdv_kp, k, km, kp, j, i);
+
+  const double p_c = p[IDX2(j, i)], p_ip = p[IDX2(j, ip)], p_jp = p[IDX2(jp, i)];
+  const double pn_c = pn[IDX2(j, i)], pn_ip = pn[IDX2(j, ip)], pn_jp = pn[IDX2(jp, i)];
+  const size_t c = IDX3(k, j, i);
+  const double pu = u[c] * ((p_c + p_ip) / 2);
+  const double pv = v[c] * ((p_c + p_jp) / 2);
+  const double pu_n = pu - (dut + dus + pgf[c]) * dt;
+  const double pv_n = pv - (dvt + dvs + phiv + pgv) * dt;
+  out.u[o3 + c] = pu_n / ((pn_c + pn_ip) / 2);
+  double v_n = pv_n / ((pn_c + pn_jp) / 2);
+  if (j == g.zero_v_row) v_n *= 0.0;  // dynamics.py:222
+  out.v[o3 + c] = v_n;
+
+  const double adv_t = gcm_cell_advec_t(g, st, fpu, fpv, k, j, jm, jp, i, im, ip);
+  const double ads_t = gcm_cell_advec_sig(g, st, sd_k, sd_kp, k, km, kp, j, i);
+  out.t[o3 + c] = (t[c] * p_c - (adv_t + ads_t) * dt) / pn_c;
+  const double adv_q = gcm_cell_advec_t(g, sq, fpu, fpv, k, j, jm, jp, i, im, ip);
+  const double ads_q = gcm_cell_advec_sig(g, sq, sd_k, sd_kp, k, km, kp, j, i);
+  out.q[o3 + c] = (q[c] * p_c - (adv_q + ads_q) * dt) / pn_c;
+  if (k == 0) out.p[o2 + IDX2(j, i)] = pn_c;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// half step / Matsuno step drivers
+// ---------------------------------------------------------------------------------------------------
+struct Pe25Work {
+  double *spu, *sd, *phi, *rho, *pgf, *pit, *pn;
+  gcm_state star, tmp;
+};
+
+static size_t pe25_n2(const gcm_geom* g) { return ((size_t)g->d.H * g->d.W + 1) / 2 * 2; }  // keep 16-byte alignment
+static size_t pe25_n3(const gcm_geom* g) { return (size_t)g->d.L * g->d.H * g->d.W; }
+
+extern "C" size_t gcm_pe25_workspace_bytes(const gcm_geom* g, int nbatch) {
+  if (!g || nbatch <= 0) return 0;
+  const size_t n3 = (pe25_n3(g) + 1) / 2 * 2, n2 = pe25_n2(g);
+  return (13 * n3 + 4 * n2) * sizeof(double) * (size_t)nbatch;
+}
+
+static void pe25_carve(const gcm_geom* g, int nbatch, void* ws, Pe25Work* w) {
+  const size_t n3 = (pe25_n3(g) + 1) / 2 * 2 * (size_t)nbatch, n2 = pe25_n2(g) * (size_t)nbatch;
+  double* d = (double*)ws;
+  w->spu = d; d += n3;
+  w->sd = d; d += n3;
+  w->phi = d; d += n3;
+  w->rho = d; d += n3;
+  w->pgf = d; d += n3;
+  w->star.u = d; d += n3;
+  w->star.v = d; d += n3;
+  w->star.t = d; d += n3;
+  w->star.q = d; d += n3;
+  w->tmp.u = d; d += n3;
+  w->tmp.v = d; d += n3;
+  w->tmp.t = d; d += n3;
+  w->tmp.q = d; d += n3;
+  w->pit = d; d += n2;
+  w->pn = d; d += n2;
+  w->star.p = d; d += n2;
+  w->tmp.p = d; d += n2;
+}
+
+static int pe25_check_state(const gcm_state* s) {
+  GCM_REQUIRE(s && s->p && s->u && s->v && s->t && s->q, GCM_ENULL);
+  GCM_REQUIRE(gcm_aligned16(s->p) && gcm_aligned16(s->u) && gcm_aligned16(s->v) && gcm_aligned16(s->t) &&
+                  gcm_aligned16(s->q), GCM_EALIGN);
+  return GCM_OK;
+}
+
+static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                               double dt, int nbatch, const Pe25Work& w, void* stream) {
+  const GcmGeomDev& d = g->d;
+  const int H = d.H, W = d.W, L = d.L;
+  const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;  // member strides of the caller's arrays
+  const int ja = d.row_lo, nrows = d.row_hi - d.row_lo;
+  const int nrows_ext = d.wrap_j ? nrows : nrows + 1;  // band: also the first halo row to the south
+  const int npairs = (L + 1) / 2;
+  const int tf = gcm_fft_threads(W);
+  const size_t smem = 2 * (size_t)W * sizeof(double2);
+  const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
+  const unsigned gx = (unsigned)((W + tc - 1) / tc);
+
+  GCM_LAUNCH((pe25_filter_kernel<1>), dim3(npairs, nrows_ext, nbatch), dim3(tf), smem, stream, d, star->u, star->p,
+             w.spu, d.smmz, L, ja, b2, b3);
+  GCM_CHECK_LAUNCH();
+  GCM_LAUNCH(pe25_column_kernel, dim3(gx, nrows_ext, nbatch), dim3(tc), 0, stream, d, base->p, star->p, star->v,
+             star->t, w.spu, w.phi, w.rho, w.sd, w.pit, w.pn, dt, ja, b2, b3);
+  GCM_CHECK_LAUNCH();
+  GCM_LAUNCH(pe25_pgf_filter_kernel, dim3(npairs, nrows, nbatch), dim3(tf), smem, stream, d, star->p, w.phi, w.rho,
+             w.pgf, ja, b2, b3);
+  GCM_CHECK_LAUNCH();
+  GcmStateC cb{base->p, base->u, base->v, base->t, base->q};
+  GcmStateC cs{star->p, star->u, star->v, star->t, star->q};
+  GcmStateM mo{out->p, out->u, out->v, out->t, out->q};
+  GCM_LAUNCH(pe25_update_kernel, dim3(gx, nrows, L * nbatch), dim3(tc), 0, stream, d, cb, cs, mo, w.spu, w.sd, w.phi,
+             w.rho, w.pgf, w.pn, dt, ja, b2, b3);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+
+static int pe25_check_smem(const gcm_geom* g) {
+#ifndef GCM_EMU
+  const size_t smem = 2 * (size_t)g->d.W * sizeof(double2);
+  if (smem > 48 * 1024) {
+    GCM_REQUIRE(smem <= 227 * 1024, GCM_EUNSUP);
+    GCM_CUDA(cudaFuncSetAttribute(pe25_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCM_CUDA(cudaFuncSetAttribute(pe25_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCM_CUDA(cudaFuncSetAttribute(pe25_pgf_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+#else
+  (void)g;
+#endif
+  return GCM_OK;
+}
+
+extern "C" int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star,
+                                  const gcm_state* out, double dt, int nbatch, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  GCM_REQUIRE(g && ws, GCM_ENULL);
+  GCM_REQUIRE(nbatch > 0, GCM_ESHAPE);
+  int st;
+  if ((st = pe25_check_state(base)) || (st = pe25_check_state(star)) || (st = pe25_check_state(out))) return st;
+  GCM_REQUIRE(gcm_aligned16(ws), GCM_EALIGN);
+  GCM_REQUIRE(ws_bytes >= gcm_pe25_workspace_bytes(g, nbatch), GCM_EWORK);
+  if ((st = pe25_check_smem(g))) return st;
+  Pe25Work w;
+  pe25_carve(g, nbatch, ws, &w);
+  return pe25_half_step_impl(g, base, star, out, dt, nbatch, w, stream);
+}
+
+extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt,
+                                     int nsteps, int nbatch, void* ws, size_t ws_bytes, void* stream) {
+  GCM_REQUIRE(g && ws, GCM_ENULL);
+  GCM_REQUIRE(nbatch > 0 && nsteps > 0, GCM_ESHAPE);
+  GCM_REQUIRE(g->d.wrap_j, GCM_EUNSUP);  // bands are stepped half step by half step around the halo exchange
+  int st;
+  if ((st = pe25_check_state(in)) || (st = pe25_check_state(out))) return st;
+  GCM_REQUIRE(gcm_aligned16(ws), GCM_EALIGN);
+  GCM_REQUIRE(ws_bytes >= gcm_pe25_workspace_bytes(g, nbatch), GCM_EWORK);
+  if ((st = pe25_check_smem(g))) return st;
+  Pe25Work w;
+  pe25_carve(g, nbatch, ws, &w);
+  const gcm_state* cur = in;
+  for (int s = 0; s < nsteps; ++s) {
+    const gcm_state* dst = ((nsteps - 1 - s) % 2 == 0) ? out : &w.tmp;
+    // dynamics.py:231: predictor with star = base; :234: corrector with the predicted star state
+    if ((st = pe25_half_step_impl(g, cur, cur, &w.star, dt, nbatch, w, stream))) return st;
+    if ((st = pe25_half_step_impl(g, cur, &w.star, dst, dt, nbatch, w, stream))) return st;
+    cur = dst;
+  }
+  return GCM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone operators (one member, owned rows)
+// ---------------------------------------------------------------------------------------------------
+// op: 0 calc_pu  1 calc_pv  2 un_pu  3 un_pv  (a = velocity or mass flux, out likewise)
+__global__ void pe25_flux_convert_kernel(GcmGeomDev g, int op, const double* __restrict__ p,
+                                         const double* __restrict__ a, double* __restrict__ out, int ja) {
+  const int H = g.H, W = g.W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y, k = blockIdx.z;
+  const double pc = p[IDX2(j, i)];
+  const double ph = (op == 0 || op == 2) ? (pc + p[IDX2(j, gcm_ip(i, W))]) / 2
+                                         : (pc + p[IDX2(gcm_row(j, 1, H, g.wrap_j), i)]) / 2;
+  const size_t c = IDX3(k, j, i);
+  out[c] = op < 2 ? a[c] * ph : a[c] / ph;
+}
+
+static int pe25_flux_convert(const gcm_geom* g, int op, const double* p, const double* a, double* out, void* stream) {
+  GCM_REQUIRE(g && p && a && out, GCM_ENULL);
+  const GcmGeomDev& d = g->d;
+  const int tc = d.W >= 128 ? 128 : (d.W + 31) / 32 * 32;
+  GCM_LAUNCH(pe25_flux_convert_kernel, dim3((d.W + tc - 1) / tc, d.row_hi - d.row_lo, d.L), dim3(tc), 0, stream, d, op,
+             p, a, out, d.row_lo);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+extern "C" int gcm_pe25_calc_pu(const gcm_geom* g, const double* p, const double* u, double* pu, void* s) { return pe25_flux_convert(g, 0, p, u, pu, s); }
+extern "C" int gcm_pe25_calc_pv(const gcm_geom* g, const double* p, const double* v, double* pv, void* s) { return pe25_flux_convert(g, 1, p, v, pv, s); }
+extern "C" int gcm_pe25_un_pu(const gcm_geom* g, const double* pu, const double* p, double* u, void* s) { return pe25_flux_convert(g, 2, p, pu, u, s); }
+extern "C" int gcm_pe25_un_pv(const gcm_geom* g, const double* pv, const double* p, double* v, void* s) { return pe25_flux_convert(g, 3, p, pv, v, s); }
+
+__global__ void pe25_aflux_kernel(GcmGeomDev g, const double* __restrict__ pu, const double* __restrict__ pv,
+                                  double* __restrict__ pit, double* __restrict__ sd, int ja) {
+  const int H = g.H, W = g.W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y;
+  GcmArr3 fpu{pu, H, W}, fpv{pv, H, W};
+  const size_t c = IDX2(j, i);
+  pit[c] = gcm_col_aflux(g, fpu, fpv, j, gcm_row(j, -1, H, g.wrap_j), i, gcm_im(i, W), sd + c, (size_t)H * W);
+}
+
+extern "C" int gcm_pe25_aflux(const gcm_geom* g, const double* pu, const double* pv, double* pit, double* sd,
+                              void* stream) {
+  GCM_REQUIRE(g && pu && pv && pit && sd, GCM_ENULL);
+  const GcmGeomDev& d = g->d;
+  const int tc = d.W >= 128 ? 128 : (d.W + 31) / 32 * 32;
+  GCM_LAUNCH(pe25_aflux_kernel, dim3((d.W + tc - 1) / tc, d.row_hi - d.row_lo, 1), dim3(tc), 0, stream, d, pu, pv, pit,
+             sd, d.row_lo);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+
+// op: 0 advec_sig(sd, q)   1 advec_t(pu, pv, t)   2 advec_m_pu -> (dut, dvt)
+__global__ void pe25_cell_op_kernel(GcmGeomDev g, int op, const double* __restrict__ a0, const double* __restrict__ a1,
+                                    const double* __restrict__ a2, const double* __restrict__ a3,
+                                    double* __restrict__ out0, double* __restrict__ out1, int ja) {
+  const int H = g.H, W = g.W, L = g.L;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y, k = blockIdx.z;
+  const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+  const int im = gcm_im(i, W), ip = gcm_ip(i, W);
+  const int km = k == 0 ? L - 1 : k - 1, kp = k == L - 1 ? 0 : k + 1;
+  const size_t c = IDX3(k, j, i);
+  if (op == 0) {
+    out0[c] = gcm_cell_advec_sig(g, a1, a0[c], a0[IDX3(kp, j, i)], k, km, kp, j, i);
+  } else if (op == 1) {
+    GcmArr3 fpu{a0, H, W}, fpv{a1, H, W};
+    out0[c] = gcm_cell_advec_t(g, a2, fpu, fpv, k, j, jm, jp, i, im, ip);
+  } else {
+    GcmArr3 fpu{a2, H, W}, fpv{a3, H, W};
+    double dut, dvt;
+    gcm_cell_advec_m(g, a0, a1, fpu, fpv, k, j, jm, jp, i, im, ip, &dut, &dvt);
+    out0[c] = dut;
+    out1[c] = dvt;
+  }
+}
+
+static int pe25_cell_op(const gcm_geom* g, int op, const double* a0, const double* a1, const double* a2,
+                        const double* a3, double* o0, double* o1, void* stream) {
+  GCM_REQUIRE(g, GCM_ENULL);
+  const GcmGeomDev& d = g->d;
+  const int tc = d.W >= 128 ? 128 : (d.W + 31) / 32 * 32;
+  GCM_LAUNCH(pe25_cell_op_kernel, dim3((d.W + tc - 1) / tc, d.row_hi - d.row_lo, d.L), dim3(tc), 0, stream, d, op, a0,
+             a1, a2, a3, o0, o1, d.row_lo);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+extern "C" int gcm_pe25_advec_sig(const gcm_geom* g, const double* sd, const double* q, double* out, void* s) {
+  GCM_REQUIRE(sd && q && out, GCM_ENULL);
+  return pe25_cell_op(g, 0, sd, q, nullptr, nullptr, out, nullptr, s);
+}
+extern "C" int gcm_pe25_advec_t(const gcm_geom* g, const double* pu, const double* pv, const double* t, double* out, void* s) {
+  GCM_REQUIRE(pu && pv && t && out, GCM_ENULL);
+  return pe25_cell_op(g, 1, pu, pv, t, nullptr, out, nullptr, s);
+}
+extern "C" int gcm_pe25_advec_m_pu(const gcm_geom* g, const double* p, const double* u, const double* v, const double* pu,
+                                   const double* pv, double* dut, double* dvt, void* s) {
+  (void)p;  // the reference signature carries p but advec_m_pu never reads it (dynamics.py:55-108)
+  GCM_REQUIRE(u && v && pu && pv && dut && dvt, GCM_ENULL);
+  return pe25_cell_op(g, 2, u, v, pu, pv, dut, dvt, s);
+}
+
+__global__ void pe25_geopotential_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ t,
+                                         double* __restrict__ phi, double* __restrict__ rho, int ja) {
+  const int H = g.H, W = g.W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y;
+  const size_t c = IDX2(j, i);
+  gcm_col_geopotential(g, p[c], g.hmap[c], t + c, (size_t)H * W, phi + c, rho ? rho + c : nullptr);
+}
+
+extern "C" int gcm_pe25_geopotential(const gcm_geom* g, const double* p, const double* t, double* phi, void* stream) {
+  GCM_REQUIRE(g && p && t && phi, GCM_ENULL);
+  const GcmGeomDev& d = g->d;
+  const int tc = d.W >= 128 ? 128 : (d.W + 31) / 32 * 32;
+  GCM_LAUNCH(pe25_geopotential_kernel, dim3((d.W + tc - 1) / tc, d.row_hi - d.row_lo, 1), dim3(tc), 0, stream, d, p, t,
+             phi, (double*)nullptr, d.row_lo);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+
+// dynamics.pgf (dynamics.py:147-171): the four unfiltered pressure-gradient terms
+__global__ void pe25_pgf_terms_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ phi,
+                                      const double* __restrict__ rho, double* __restrict__ pgfu,
+                                      double* __restrict__ pgfv, double* __restrict__ phiu, double* __restrict__ phiv,
+                                      int ja) {
+  const int H = g.H, W = g.W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const int j = ja + blockIdx.y, k = blockIdx.z;
+  const int jp = gcm_row(j, 1, H, g.wrap_j), ip = gcm_ip(i, W);
+  const double p_c = p[IDX2(j, i)], p_ip = p[IDX2(j, ip)], p_jp = p[IDX2(jp, i)];
+  const double sg = g.sig[k];
+  const size_t c = IDX3(k, j, i);
+  const double r_c = rho[c], ph_c = phi[c];
+  phiu[c] = ((p_c + p_ip) / 2) * ((phi[IDX3(k, j, ip)] - ph_c) / g.dx_j[j]);
+  phiv[c] = ((p_c + p_jp) / 2) * ((phi[IDX3(k, jp, i)] - ph_c) / g.dy);
+  pgfu[c] = (((sg * p_c) + (sg * p_ip)) / 2) / ((r_c + rho[IDX3(k, j, ip)]) / 2) * ((p_ip - p_c) / g.dx_j[j]);
+  pgfv[c] = (((sg * p_c) + (sg * p_jp)) / 2) / ((r_c + rho[IDX3(k, jp, i)]) / 2) * ((p_jp - p_c) / g.dy);
+}
+
+extern "C" int gcm_pe25_pgf(const gcm_geom* g, const double* p, const double* t, double* pgfu, double* pgfv,
+                            double* phiu, double* phiv, void* ws, size_t ws_bytes, void* stream) {
+  GCM_REQUIRE(g && p && t && pgfu && pgfv && phiu && phiv && ws, GCM_ENULL);
+  GCM_REQUIRE(g->d.wrap_j, GCM_EUNSUP);
+  const GcmGeomDev& d = g->d;
+  const size_t n3 = pe25_n3(g);
+  GCM_REQUIRE(ws_bytes >= 2 * n3 * sizeof(double), GCM_EWORK);
+  double* phi = (double*)ws;
+  double* rho = phi + n3;
+  const int tc = d.W >= 128 ? 128 : (d.W + 31) / 32 * 32;
+  const unsigned gx = (unsigned)((d.W + tc - 1) / tc);
+  GCM_LAUNCH(pe25_geopotential_kernel, dim3(gx, d.H, 1), dim3(tc), 0, stream, d, p, t, phi, rho, 0);
+  GCM_CHECK_LAUNCH();
+  GCM_LAUNCH(pe25_pgf_terms_kernel, dim3(gx, d.H, d.L), dim3(tc), 0, stream, d, p, (const double*)phi,
+             (const double*)rho, pgfu, pgfv, phiu, phiv, 0);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+
+extern "C" int gcm_polar_filter(const gcm_geom* g, const double* in, double* out, int nlayers, const double* table,
+                                void* stream) {
+  GCM_REQUIRE(g && in && out, GCM_ENULL);
+  GCM_REQUIRE(nlayers > 0, GCM_ESHAPE);
+  int st;
+  if ((st = pe25_check_smem(g))) return st;
+  const GcmGeomDev& d = g->d;
+  const size_t b3 = (size_t)nlayers * d.H * d.W;
+  GCM_LAUNCH((pe25_filter_kernel<0>), dim3((nlayers + 1) / 2, d.row_hi - d.row_lo, 1), dim3(gcm_fft_threads(d.W)),
+             2 * (size_t)d.W * sizeof(double2), stream, d, in, (const double*)nullptr, out, table ? table : d.smmz,
+             nlayers, d.row_lo, (size_t)0, b3);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}

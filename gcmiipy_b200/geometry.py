@@ -1,0 +1,175 @@
+"""Grid + metric terms, mirror of the reference `geometry` module (geometry.py:9-182).
+
+Host side: plain float64 numpy in SI base units with the reference's broadcast shapes
+(`sig*`: (L,1,1); `dx_j`, `dx_h`: (1,H,1); `dy` scalar; `lat`: (H,1) rad; `long`: (W,) rad; `area`: (H,);
+`ptop` Pa; `heightmap`: (H,W) m).  Row 0 is the north-most row, k = 0 the surface layer.
+Device side: `device_geom(geom)` uploads the tables once (sigma tables, dx_j, dx_h, heightmap, the
+polar-filter multipliers of low_pass.py:61-72 and the FFT twiddles) and keeps them resident; kernels
+receive the handle.  A geometry object may be mutated by the caller (e.g. `geom.heightmap[0, 8] = 1000`,
+test_geography.py:13); the device copy is refreshed when a fingerprint of the host tables changes.
+"""
+import ctypes
+import hashlib
+import math
+
+import numpy as np
+
+from . import _abi, _host, _lib
+from .constants import radius
+
+__all__ = ["Geom", "manabe_sig", "equal_sig", "gen_geometry", "gen_square_geometry", "device_geom", "polar_filter_table"]
+
+
+class Geom:
+    """geometry.py:9-26."""
+
+    def __init__(self, height, width, layers):
+        self.height = height
+        self.width = width
+        self.layers = layers
+        self.sige = self.dsig = self.sigb = self.sigt = self.sig = self.dsigv = None
+        self.dy = 0.0
+        self.lat = 0.0
+        self.long = 0.0
+        self.dx_j = self.dx_h = None
+        self.area = None
+        self.ptop = 0.0
+        self.heightmap = None
+        self._dev = {}
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_dev"] = {}
+        return d
+
+
+def manabe_sig(s):
+    """geometry.py:30."""
+    return s ** 2 * (3 - 2 * s)
+
+
+def equal_sig(s):
+    """geometry.py:34."""
+    return s
+
+
+def _sigma_tables(geom, layers, sig_func):
+    """geometry.py:73-85 / :158-172: sige[k] = sig_func(1 - k/L), k = 0..L."""
+    edges = np.asarray([sig_func(1 - k / layers) for k in range(layers + 1)], dtype=np.float64)
+    col = lambda a: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 1, 1)
+    geom.sige = col(edges)
+    geom.sigt = col(edges[1:])
+    geom.sigb = col(edges[:-1])
+    geom.dsig = geom.sigb - geom.sigt
+    geom.sig = (geom.sigb + geom.sigt) / 2
+    geom.dsigv = np.roll(geom.sig, -1, 0) - geom.sig
+
+
+def gen_geometry(height, width, layers, sig_func=equal_sig,
+                 north_edge=90, south_edge=-90, west_edge=-180, east_edge=180):
+    """geometry.py:38-151 (the reference's prints are dropped)."""
+    geom = Geom(height, width, layers)
+    _sigma_tables(geom, layers, sig_func)
+    circumference = 2 * radius * math.pi
+    dlat = (north_edge - south_edge) / height
+    dlong = (east_edge - west_edge) / width
+    rows = np.arange(height, dtype=np.float64)
+    lat_j = north_edge - (rows + 0.5) * dlat          # cell centres (u, p points)
+    lat_h = north_edge - (rows + 1) * dlat            # southern cell edges (v points)
+    long_k = west_edge + (np.arange(width, dtype=np.float64) + 0.5) * dlong
+    geom.lat = lat_j.reshape(height, -1) * (math.pi / 180.0)
+    geom.long = long_k * (math.pi / 180.0)
+    geom.dx_j = (np.cos(lat_j * np.pi / 180) * circumference / width).reshape(1, height, 1)
+    dx_h = np.cos(lat_h * np.pi / 180) * circumference / width
+    geom.dx_h = dx_h.reshape(1, height, 1)
+    geom.dy = circumference / 2 / height
+    geom.area = (np.roll(dx_h, 1, axis=0) + dx_h) * geom.dy * 0.5   # trapezoids, geometry.py:141
+    geom.ptop = 0.0
+    geom.heightmap = np.zeros((height, width))
+    return geom
+
+
+def gen_square_geometry(height, width, layers, dx, dy, sig_func=equal_sig):
+    """geometry.py:154-182: uniform Cartesian metric."""
+    geom = Geom(height, width, layers)
+    _sigma_tables(geom, layers, sig_func)
+    geom.dx_j = np.full((1, height, 1), _host.scalar(dx))
+    geom.dx_h = np.full((1, height, 1), _host.scalar(dx))
+    geom.dy = _host.scalar(dy)
+    geom.heightmap = np.zeros((height, width))
+    return geom
+
+
+def polar_filter_table(geom, im=None):
+    """Multipliers smmz[j, n] of low_pass.arakawa_1977 (low_pass.py:61-72), shape (H, im/2+1):
+    1 for n = 0, min(1, (dx_j/dy) / sin(pi n / im)) for 1 <= n <= im/2."""
+    im = geom.width if im is None else im
+    drat = _host.scalar(geom.dy) / np.asarray(_host.magnitude(geom.dx_j), dtype=np.float64).reshape(-1, 1)
+    bysn = 1 / np.sin(np.pi / im * np.arange(1, im / 2 + 1))
+    sm = 1 - bysn / drat
+    smmz = 1 - np.maximum(sm, np.zeros_like(sm))
+    return np.ascontiguousarray(np.insert(smmz, 0, 1, -1))
+
+
+class DeviceGeom:
+    """Owner of one `gcm_geom*` (include/gcm_b200.h)."""
+
+    def __init__(self, handle, H, W, L, row_lo, row_hi, wrap_j):
+        self.handle, self.H, self.W, self.L = handle, H, W, L
+        self.row_lo, self.row_hi, self.wrap_j = row_lo, row_hi, wrap_j
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().gcm_geom_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _vec(a, n):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(_host.magnitude(a), dtype=np.float64).reshape(-1), (n,)))
+
+
+def _fingerprint(geom, band):
+    h = hashlib.blake2b(digest_size=16)
+    for a in (geom.sige, geom.dx_j, geom.dx_h, geom.heightmap):
+        h.update(np.ascontiguousarray(_host.magnitude(a), dtype=np.float64).tobytes())
+    h.update(np.asarray([_host.scalar(geom.dy), _host.scalar(geom.ptop)]).tobytes())
+    h.update(repr(band).encode())
+    return h.hexdigest()
+
+
+def device_geom(geom, band=None):
+    """Device-resident tables for `geom`.  band = None: the whole grid, rows periodic in j like np.roll
+    (coordinates_3d.py:43-48).  band = (j0, j1, halo_n, halo_s): a latitude band holding global rows
+    [j0 - halo_n, j1 + halo_s) (mod H) of which [j0, j1) are owned."""
+    key = _fingerprint(geom, band)
+    if key in geom._dev:
+        return geom._dev[key]
+    H, W, L = geom.height, geom.width, geom.layers
+    sig, dsig = _vec(geom.sig, L), _vec(geom.dsig, L)
+    sigb, sigt = _vec(geom.sigb, L), _vec(geom.sigt, L)
+    dx_j, dx_h = _vec(geom.dx_j, H), _vec(geom.dx_h, H)
+    hmap = np.ascontiguousarray(_host.magnitude(geom.heightmap), dtype=np.float64).reshape(H, W)
+    smmz = polar_filter_table(geom, W) if W > 1 else None
+    if band is None:
+        Hs, row_lo, row_hi, wrap, zero_v = H, 0, H, 1, H - 1
+    else:
+        j0, j1, hn, hs = band
+        rows = np.arange(j0 - hn, j1 + hs) % H
+        Hs, row_lo, row_hi, wrap = len(rows), hn, hn + (j1 - j0), 0
+        dx_j, dx_h, hmap = dx_j[rows].copy(), dx_h[rows].copy(), np.ascontiguousarray(hmap[rows])
+        smmz = np.ascontiguousarray(smmz[rows]) if smmz is not None else None
+        own = np.nonzero(rows[row_lo:row_hi] == H - 1)[0]
+        zero_v = int(row_lo + own[0]) if len(own) else -1
+    desc = _abi.GeomDesc(Hs, W, L, wrap, row_lo, row_hi, zero_v, _host.scalar(geom.dy), _host.scalar(geom.ptop),
+                         _host.hptr(sig), _host.hptr(dsig), _host.hptr(sigb), _host.hptr(sigt), _host.hptr(dx_j),
+                         _host.hptr(dx_h), _host.hptr(hmap), _host.hptr(smmz))
+    handle = ctypes.c_void_p()
+    _lib.check(_lib.lib().gcm_geom_create(ctypes.byref(desc), ctypes.byref(handle)), "gcm_geom_create")
+    obj = DeviceGeom(handle, Hs, W, L, row_lo, row_hi, wrap)
+    if len(geom._dev) >= 8:       # a caller that keeps editing the heightmap: drop the stale tables
+        geom._dev.clear()
+    geom._dev[key] = obj
+    return obj

@@ -1,0 +1,119 @@
+"""Driver of the 2.5-D model, mirror of the reference `no_limits_2_5d` module
+(no_limits_2_5d.py:35-60 calc_energy, :79-94 full_timestep, :146-168 gen_initial_conditions,
+:220-236 run_model).  The column physics after the dynamics step is unreachable in the reference
+(`return` at :94) and is out of scope here too.
+"""
+from collections import defaultdict, namedtuple
+
+import numpy as np
+import torch
+
+from . import _host, _lib, geometry
+from .constants import P0, kappa
+from .dynamics import *  # noqa: F401,F403  (the reference re-exports dynamics the same way, :29)
+from .dynamics import Stepper, _struct, matsuno_timestep
+from .geometry import device_geom, gen_geometry
+from .humidity import manabe_rh, rh_to_mmr
+
+GroundVars = namedtuple("GroundVars", ("gt", "gw", "snow", "ice"))
+STATS = defaultdict(list)
+
+height = 24
+width = 36
+layers = 9
+
+
+def gen_initial_conditions(geom):
+    """no_limits_2_5d.py:146-168 (host side, once): p = 1e5 Pa - ptop, u = 1, v = 0, T = 360 K -> theta,
+    q = max(3e-6, Manabe RH mixing ratio); ground variables ride along untouched."""
+    full = (geom.layers, geom.height, geom.width)
+    surface = (geom.height, geom.width)
+    ptop = _host.scalar(geom.ptop)
+    p = np.full(surface, 1) * 100000.0 - ptop
+    u = np.full(full, 1) * 1.0
+    v = np.full(full, 1) * .0
+    tt = np.full(full, 1) * 360.0
+    tp = p * geom.sig + ptop
+    t = tt * ((P0 / tp) ** kappa)
+    q = np.maximum(np.full(full, 1) * 0.000003, rh_to_mmr(manabe_rh(geom), tp, tt))
+    g = GroundVars(np.full(surface, 1) * 360.0, np.zeros(surface), np.zeros(surface), np.zeros(surface))
+    return p, u, v, t, q, g
+
+
+def _area_by_i(geom):
+    """The reference multiplies an (L, H, W) array by geom.area of shape (H,) (no_limits_2_5d.py:49), which
+    numpy broadcasts along i: valid only when H == W or H == 1."""
+    area = np.asarray(_host.magnitude(geom.area), dtype=np.float64).reshape(-1)
+    if area.shape[0] not in (1, geom.width):
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d,%d) (%d,)"
+                         % (geom.layers, geom.height, geom.width, area.shape[0]))
+    return np.ascontiguousarray(np.broadcast_to(area, (geom.width,)))
+
+
+def calc_energy(p, u, v, t, q, g, geom):
+    """no_limits_2_5d.py:35-60 -> (ke, cpT, geopotential, total) in J, one fused reduction kernel."""
+    import ctypes
+    dg = device_geom(geom)
+    ts = [_host.dev(x) for x in (p, u, v, t, q)]
+    area = _host.dev(_area_by_i(geom))
+    out = _host.empty((3,))
+    s = _struct(ts)
+    _lib.check(_lib.lib().gcm_pe25_energy(dg.handle, ctypes.byref(s), _host.ptr(area), _host.ptr(out), _lib.stream()),
+               "gcm_pe25_energy")
+    ke, ate, geo = (float(x) for x in out.cpu())
+    return ke, ate, geo, ke + ate + geo
+
+
+def _minmax(t):
+    out = _host.empty((3,))
+    _lib.check(_lib.lib().gcm_diag_minmax(_host.ptr(t), t.numel(), _host.ptr(out), _lib.stream()), "gcm_diag_minmax")
+    mn, mx, bad = (float(x) for x in out.cpu())
+    return mn, mx, int(bad)
+
+
+def full_timestep(p, u, v, t, q, g, dt, utc, geom):
+    """no_limits_2_5d.py:79-94: dynamics step + the STATS diagnostics (the reference's print is dropped)."""
+    p, u, v, t, q = matsuno_timestep(p, u, v, t, q, dt, geom)
+    umin, umax, _ = _minmax(_host.dev(u))
+    vmin, vmax, _ = _minmax(_host.dev(v))
+    STATS["u_max"].append(umax)
+    STATS["u_min"].append(umin)
+    STATS["v_max"].append(vmax)
+    STATS["v_min"].append(vmin)
+    STATS["ke"].append(calc_energy(p, u, v, t, q, g, geom))
+    return p, u, v, t, q, g
+
+
+def run_model(height, width, layers, dt, timesteps, callback, stats=True):
+    """no_limits_2_5d.py:220-236.  The state stays resident on the device for the whole run; it is
+    downloaded only for `callback` and at the end.  stats=False skips the per-step diagnostics."""
+    geom = gen_geometry(height, width, layers, sig_func=geometry.manabe_sig)
+    p, u, v, t, q, g = gen_initial_conditions(geom)
+    v[0, 0, 0] = 0.1
+    u *= 0
+    st = Stepper(geom, p, u, v, t, q)
+    for _ in range(timesteps):
+        st.step(dt, 1)
+        if stats:
+            dp, du, dv, dtt, dq = st.tensors()
+            umin, umax, _ = _minmax(du)
+            vmin, vmax, _ = _minmax(dv)
+            STATS["u_max"].append(umax)
+            STATS["u_min"].append(umin)
+            STATS["v_max"].append(vmax)
+            STATS["v_min"].append(vmin)
+            STATS["ke"].append(calc_energy(dp, du, dv, dtt, dq, g, geom))
+        if callback:
+            callback(*st.download())
+    p, u, v, t, q = st.download()
+    return p, u, v, t, q, g, geom
+
+
+def main():
+    """no_limits_2_5d.py:256-270 at a stable time step (the reference's 1800 s diverges)."""
+    p, u, v, t, q, g, geom = run_model(8, 8, 3, 450.0, 200, None)
+    print("pressures:", p * geom.sig + geom.ptop)
+
+
+if __name__ == "__main__":
+    main()

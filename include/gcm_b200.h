@@ -1,0 +1,204 @@
+/* gcm_b200.h -- C ABI of the B200-native Matsuno C-grid dynamical-core stepper.
+ *
+ * Drop-in boundary for ONE path of marthinwurer/gcmiipy: the Matsuno forward-backward step on the
+ * Arakawa C-grid and the operators it is built from.  The reference has no FFI layer: its boundary
+ * is plain Python module functions.  Each entry point below names the
+ * reference function (file:line under the reference checkout) whose result it reproduces; the Python
+ * package `gcmiipy_b200` binds them with ctypes under the reference's own module/function names
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer to C-contiguous float64; h_* is a host pointer;
+ *   - 2-D fields are [j][i] (H rows x W columns, i fastest, row 0 = north); 3-D fields are
+ *     [k][j][i] (L layers, k = 0 = surface); a leading ensemble dimension [b] is allowed where a
+ *     function takes `nbatch`;
+ *   - out-of-place: inputs are never written, outputs never alias inputs (the reference functions
+ *     are pure);
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*; NULL =
+ *     default stream); no hidden synchronisation unless stated;
+ *   - every function returns int: 0 = ok, < 0 = argument error (GCM_E*), > 0 = cudaError_t.
+ *     Nothing throws or aborts.  There is no CPU fallback: without a CUDA device every compute entry
+ *     point returns the CUDA error.
+ */
+#ifndef GCM_B200_H
+#define GCM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCM_OK 0
+#define GCM_ENULL (-1)      /* required pointer is NULL */
+#define GCM_ESHAPE (-2)     /* bad extent (<= 0, odd W for the polar filter, row range outside the band ...) */
+#define GCM_EALIGN (-3)     /* device pointer not 16-byte aligned */
+#define GCM_EUNSUP (-4)     /* unsupported combination */
+#define GCM_EWORK (-5)      /* workspace too small */
+
+int gcm_version(void);
+const char* gcm_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry: metric + sigma tables kept resident on the device (geometry.py:9-182, Geom).
+ * A geometry describes the rows STORED by one process: either the whole grid (wrap_j = 1, rows are
+ * periodic in j exactly like np.roll in coordinates_3d.py:43-48) or one latitude band with halo rows
+ * (wrap_j = 0; stored row r holds global row (band_j0 - halo_n + r) mod H_global; the caller fills
+ * halo rows, see gcm_halo_*).  A step writes only the owned rows [row_lo, row_hi).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gcm_geom gcm_geom;
+
+typedef struct {
+  int H;            /* stored rows */
+  int W;            /* columns; must be even or 1 (low_pass.py:57-59) */
+  int L;            /* layers */
+  int wrap_j;       /* 1 = rows periodic in j; 0 = band with halo rows */
+  int row_lo;       /* owned rows [row_lo, row_hi) */
+  int row_hi;
+  int zero_v_row;   /* stored row of the global last row: v_n[:, -1, :] *= 0 (dynamics.py:222); -1 if absent */
+  double dy;        /* geometry.py:138 */
+  double ptop;      /* geometry.py:147 (Pa) */
+  const double* h_sig;      /* [L]  geometry.py:84 */
+  const double* h_dsig;     /* [L]  geometry.py:83 */
+  const double* h_sigb;     /* [L]  geometry.py:81 */
+  const double* h_sigt;     /* [L]  geometry.py:80 */
+  const double* h_dx_j;     /* [H]  geometry.py:136 */
+  const double* h_dx_h;     /* [H]  geometry.py:137 */
+  const double* h_heightmap;/* [H*W] geometry.py:149 (m); NULL = zeros */
+  const double* h_smmz;     /* [H*(W/2+1)] polar-filter multipliers, low_pass.py:61-72; NULL iff W == 1 */
+} gcm_geom_desc;
+
+int gcm_geom_create(const gcm_geom_desc* desc, gcm_geom** out);
+int gcm_geom_destroy(gcm_geom* g);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2.5-D sigma-layer primitive equations (dynamics.py).  State = surface pressure p[H][W] and
+ * u, v, t, q [L][H][W], with an optional leading ensemble dimension of `nbatch` members.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double* p;
+  double* u;
+  double* v;
+  double* t;
+  double* q;
+} gcm_state;
+
+/* bytes of device scratch a half step / Matsuno step needs for `nbatch` members */
+size_t gcm_pe25_workspace_bytes(const gcm_geom* g, int nbatch);
+
+/* dynamics.half_timestep (dynamics.py:183-227): out = base + dt * F(star).  Rows of `star` within
+ * [-1, +2] of an owned row (and row +1 of base.p) must be valid (halo rows in band mode). */
+int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                       double dt, int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* dynamics.matsuno_timestep (dynamics.py:230-237), `nsteps` times, whole-grid geometry (wrap_j = 1).
+ * `in` is not modified; the result of the last step lands in `out`. */
+int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt, int nsteps,
+                          int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* the operators half_timestep is built from, each on the owned rows of one member */
+int gcm_pe25_calc_pu(const gcm_geom* g, const double* d_p, const double* d_u, double* d_pu, void* stream);   /* dynamics.py:15 */
+int gcm_pe25_calc_pv(const gcm_geom* g, const double* d_p, const double* d_v, double* d_pv, void* stream);   /* dynamics.py:20 */
+int gcm_pe25_un_pu(const gcm_geom* g, const double* d_pu, const double* d_p, double* d_u, void* stream);     /* dynamics.py:25 */
+int gcm_pe25_un_pv(const gcm_geom* g, const double* d_pv, const double* d_p, double* d_v, void* stream);     /* dynamics.py:30 */
+int gcm_pe25_aflux(const gcm_geom* g, const double* d_pu, const double* d_pv, double* d_pit, double* d_sd,
+                   void* stream);                                                                          /* dynamics.py:35 */
+int gcm_pe25_advec_sig(const gcm_geom* g, const double* d_sd, const double* d_q, double* d_out, void* stream); /* dynamics.py:49 */
+int gcm_pe25_advec_m_pu(const gcm_geom* g, const double* d_p, const double* d_u, const double* d_v,
+                        const double* d_pu, const double* d_pv, double* d_dut, double* d_dvt, void* stream);  /* dynamics.py:55 */
+int gcm_pe25_geopotential(const gcm_geom* g, const double* d_p, const double* d_t, double* d_phi,
+                          void* stream);                                                                   /* dynamics.py:111 */
+int gcm_pe25_pgf(const gcm_geom* g, const double* d_p, const double* d_t, double* d_pgfu, double* d_pgfv,
+                 double* d_phiu, double* d_phiv, void* d_workspace, size_t workspace_bytes, void* stream);   /* dynamics.py:147 */
+int gcm_pe25_advec_t(const gcm_geom* g, const double* d_pu, const double* d_pv, const double* d_t,
+                     double* d_out, void* stream);                                                         /* dynamics.py:174 */
+
+/* low_pass.arakawa_1977 (low_pass.py:41-78): per-row rFFT x smmz[j][n] x irFFT on `nlayers` layers of
+ * the geometry's owned rows.  low_pass.avrx (low_pass.py:14-38) is the same kernel with a 0/1 table:
+ * pass its table through `d_table` ([H][W/2+1], device) or NULL for the geometry's smmz. */
+int gcm_polar_filter(const gcm_geom* g, const double* d_in, double* d_out, int nlayers, const double* d_table,
+                     void* stream);
+
+/* diagnostics of no_limits_2_5d.full_timestep (no_limits_2_5d.py:85-91): min and max of a field
+ * -> d_out[0], d_out[1]; number of non-finite values -> d_out[2] (as a double). */
+int gcm_diag_minmax(const double* d_x, size_t n, double* d_out3, void* stream);
+/* no_limits_2_5d.calc_energy (no_limits_2_5d.py:35-60): ke, cpT, geopotential sums -> d_out[0..2];
+ * h_area_by_i is the reference's broadcast of geom.area along i (valid when H == W or H == 1). */
+int gcm_pe25_energy(const gcm_geom* g, const gcm_state* s, const double* d_area_by_i, double* d_out3, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latitude-band halo rows (emulates np.roll over j across ranks, coordinates_3d.py:43-48).
+ * pack: copy `nrows` stored rows starting at `row0` of each of the 5 state fields (p: 1 layer,
+ * u,v,t,q: L layers) into one contiguous buffer; unpack is the inverse.  Buffer layout:
+ * [p rows][u rows][v rows][t rows][q rows], each [layer][row][i].
+ * ---------------------------------------------------------------------------------------------- */
+size_t gcm_halo_buffer_doubles(const gcm_geom* g, int nrows);
+int gcm_halo_pack(const gcm_geom* g, const gcm_state* s, int row0, int nrows, double* d_buf, void* stream);
+int gcm_halo_unpack(const gcm_geom* g, const gcm_state* s, int row0, int nrows, const double* d_buf, void* stream);
+/* same, but copies straight between two states (used for the periodic self-wrap and for peer-mapped
+ * neighbour memory over NVLink): dst rows [dst_row0, +nrows) <- src rows [src_row0, +nrows) */
+int gcm_halo_copy_rows(const gcm_geom* g, const gcm_state* src, int src_row0, const gcm_state* dst, int dst_row0,
+                       int nrows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2-D schemes on a uniform doubly periodic grid.
+ * ---------------------------------------------------------------------------------------------- */
+/* matsuno_c_grid.matsumo_scheme (matsuno_c_grid.py:125-142), nsteps times; both sub-steps fused in
+ * one launch (radius-2 halo tile).  Bit-identical to the reference arithmetic (no FMA contraction). */
+int gcm_sw2d_matsuno_step(const double* d_u, const double* d_v, const double* d_p, double* d_u_out,
+                          double* d_v_out, double* d_p_out, int H, int W, double dx, double dt, int nsteps,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+size_t gcm_sw2d_workspace_bytes(int H, int W);
+/* op: 0 advection_of_velocity_u (:15)  1 advection_of_velocity_v (:54)  2 geopotential_gradient_u (:97)
+ *     3 geopotential_gradient_v (:103) 4 advection_of_geopotential (:109); unused inputs may be NULL */
+int gcm_sw2d_operator(int op, const double* d_u, const double* d_v, const double* d_p, double* d_out, int H, int W,
+                      double dx, void* stream);
+
+/* no_limits_2d.half_timestep / matsuno_timestep (no_limits_2d.py:104-131); q passes through */
+int gcm_pe2d_half_step(const gcm_state* base, const gcm_state* star, const gcm_state* out, int H, int W, double dt,
+                       double dx, void* stream);
+int gcm_pe2d_matsuno_step(const gcm_state* in, const gcm_state* out, int H, int W, double dt, double dx, int nsteps,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+size_t gcm_pe2d_workspace_bytes(int H, int W);
+/* op: 0 advec_m -> (dut, dvt) (:47)   1 pgf -> (pgfu, pgfv) (:76) */
+int gcm_pe2d_operator(int op, const double* d_p, const double* d_u, const double* d_v, const double* d_t,
+                      double* d_out0, double* d_out1, int H, int W, double dx, void* stream);
+
+/* matsumo_temp.matsumo_scheme (matsumo_temp.py:66-99): shallow water + temperature + viscosity */
+int gcm_swt2d_matsuno_step(const double* d_u, const double* d_v, const double* d_p, const double* d_t,
+                           double* d_u_out, double* d_v_out, double* d_p_out, double* d_t_out, int H, int W,
+                           double dx, double dt, double mu, int nsteps, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
+size_t gcm_swt2d_workspace_bytes(int H, int W);
+
+/* viscosity.finite_laplacian_2d (viscosity.py:12): out = (q[j+1]+q[j-1]+q[i+1]+q[i-1]-4q)/(dx*dx) * scale;
+ * scale = 1 for the Laplacian, mu for incompressible_viscosity_2d (viscosity.py:22: mu * lap) */
+int gcm_laplacian5(const double* d_q, double* d_out, int H, int W, double dx, double mu, int apply_mu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators
+ * ---------------------------------------------------------------------------------------------- */
+/* phi_port.PGF (phi_port.py:5-113) on [k][j][i] inputs (the transposes of the reference's T[W][H][L],
+ * P[W][H]); only column i = 0 of every row is computed (IMAX = 1, :50-54), the rest of phi is zero */
+int gcm_phi_port_pgf(const gcm_geom* g, const double* d_p, const double* d_t, double* d_phi, void* stream);
+
+/* flux_limiter.py:10-32 on `nrows` independent periodic rows of length n */
+int gcm_fl_van_leer(const double* d_r, double* d_out, size_t n, void* stream);                               /* :10 */
+int gcm_fl_calc_r(const double* d_q, double* d_out, int nrows, int n, void* stream);                         /* :14 */
+int gcm_fl_donor_cell_flux(const double* d_q, const double* d_u, double* d_out, int nrows, int n, void* stream); /* :23 */
+int gcm_fl_donor_cell_advection(const double* d_q, const double* d_u, double* d_out, int nrows, int n, double dx,
+                                double dt, int nsteps, double* d_tmp, void* stream);                         /* :30 */
+
+/* coordinates*.py shift / half-average / gradient helpers on an [n2][n1][n0] array (n0 fastest).
+ * axis: 0 = i (fastest), 1 = j, 2 = k.  op: 0 roll by `shift` (np.roll semantics, constants.py:85)
+ * 1 (q + roll(q, shift))/2   2 (roll(q,-1) - q)/d */
+int gcm_shift_op(int op, const double* d_q, double* d_out, int n2, int n1, int n0, int axis, int shift, double d,
+                 void* stream);
+
+/* temperature.py:7-19: dir 0: T = theta / (P0/p)^kappa ; dir 1: theta = T * (P0/p)^kappa */
+int gcm_temperature_convert(int dir, const double* d_t, const double* d_p, double* d_out, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCM_B200_H */
