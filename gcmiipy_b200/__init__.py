@@ -15,5 +15,5 @@ from . import _lib  # noqa: F401
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into gcmiipy_b200/_lib/libgcm_b200.so (in-tree)."""
-    from .build import build as _build
+    from ._build import build as _build
     return _build(force=force, verbose=verbose)

@@ -63,6 +63,10 @@ SIGNATURES = {
     "gcm_fl_donor_cell_flux": (_i, [c_dp, c_dp, c_dp, _i, _i, c_stream]),
     "gcm_fl_donor_cell_advection": (_i, [c_dp, c_dp, c_dp, _i, _i, _d, _d, _i, c_dp, c_stream]),
     "gcm_shift_op": (_i, [_i, c_dp, c_dp, _i, _i, _i, _i, _i, _d, c_stream]),
+    "gcm_prof_enable": (_i, [_i]),
+    "gcm_prof_kinds": (_i, []),
+    "gcm_prof_kind_name": (C.c_char_p, [_i]),
+    "gcm_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "gcm_temperature_convert": (_i, [_i, c_dp, c_dp, c_dp, _z, c_stream]),
 }
 

@@ -1,6 +1,6 @@
 """Build the C-ABI library `gcmiipy_b200/_lib/libgcm_b200.so` (hand-written sm_100a CUDA) in-tree.
 
-    python -m gcmiipy_b200.build [--force] [--verbose]
+    python -m gcmiipy_b200._build [--force] [--verbose]
 
 nvcc cross-compiles for sm_100a without a GPU.  Objects are rebuilt only when a source or header
 is newer.  Per-file flags: the `+ - * /`-only schemes (sw2d, pe2d, ops) and the exact 2.5-D
@@ -23,6 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 # source -> extra flags
 SOURCES = {
     "geom.cu": [],
+    "prof.cu": [],
     "pe25.cu": ["-fmad=false"],
     "pe25_fast.cu": [],
     "sw2d.cu": ["-fmad=false"],

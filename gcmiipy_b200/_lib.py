@@ -25,11 +25,11 @@ class GcmError(RuntimeError):
 
 
 def lib():
-    """The bound CDLL; built in-tree by `python -m gcmiipy_b200.build` (or __graft_entry__.build())."""
+    """The bound CDLL; built in-tree by `python -m gcmiipy_b200._build` (or __graft_entry__.build())."""
     global _LIB
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError("gcmiipy_b200: %s is missing -- run `python -m gcmiipy_b200.build` "
+            raise RuntimeError("gcmiipy_b200: %s is missing -- run `python -m gcmiipy_b200._build` "
                                "(there is no CPU fallback)" % LIB_PATH)
         _LIB = _abi.bind(ctypes.CDLL(LIB_PATH))
     return _LIB

@@ -10,6 +10,7 @@
 // band because row j of the update needs pit, sd, phi, rho and filtered spu at row j + 1.
 #include "fft_rows.h"
 #include "gcm_common.h"
+#include "prof.h"
 
 #define IDX3(k, j, i) (((size_t)(k) * H + (size_t)(j)) * W + (size_t)(i))
 #define IDX2(j, i) ((size_t)(j) * W + (size_t)(i))
@@ -403,20 +404,32 @@ static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const g
   const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
   const unsigned gx = (unsigned)((W + tc - 1) / tc);
 
-  GCM_LAUNCH((pe25_filter_kernel<1>), dim3(npairs, nrows_ext, nbatch), dim3(tf), smem, stream, d, star->u, star->p,
-             w.spu, d.smmz, L, ja, b2, b3);
+  {
+    GcmProfScope ps(GCM_K_FILTER_SPU, stream);
+    GCM_LAUNCH((pe25_filter_kernel<1>), dim3(npairs, nrows_ext, nbatch), dim3(tf), smem, stream, d, star->u, star->p,
+               w.spu, d.smmz, L, ja, b2, b3);
+  }
   GCM_CHECK_LAUNCH();
-  GCM_LAUNCH(pe25_column_kernel, dim3(gx, nrows_ext, nbatch), dim3(tc), 0, stream, d, base->p, star->p, star->v,
-             star->t, w.spu, w.phi, w.rho, w.sd, w.pit, w.pn, dt, ja, b2, b3);
+  {
+    GcmProfScope ps(GCM_K_COLUMN, stream);
+    GCM_LAUNCH(pe25_column_kernel, dim3(gx, nrows_ext, nbatch), dim3(tc), 0, stream, d, base->p, star->p, star->v,
+               star->t, w.spu, w.phi, w.rho, w.sd, w.pit, w.pn, dt, ja, b2, b3);
+  }
   GCM_CHECK_LAUNCH();
-  GCM_LAUNCH(pe25_pgf_filter_kernel, dim3(npairs, nrows, nbatch), dim3(tf), smem, stream, d, star->p, w.phi, w.rho,
-             w.pgf, ja, b2, b3);
+  {
+    GcmProfScope ps(GCM_K_FILTER_PGF, stream);
+    GCM_LAUNCH(pe25_pgf_filter_kernel, dim3(npairs, nrows, nbatch), dim3(tf), smem, stream, d, star->p, w.phi, w.rho,
+               w.pgf, ja, b2, b3);
+  }
   GCM_CHECK_LAUNCH();
   GcmStateC cb{base->p, base->u, base->v, base->t, base->q};
   GcmStateC cs{star->p, star->u, star->v, star->t, star->q};
   GcmStateM mo{out->p, out->u, out->v, out->t, out->q};
-  GCM_LAUNCH(pe25_update_kernel, dim3(gx, nrows, L * nbatch), dim3(tc), 0, stream, d, cb, cs, mo, w.spu, w.sd, w.phi,
-             w.rho, w.pgf, w.pn, dt, ja, b2, b3);
+  {
+    GcmProfScope ps(GCM_K_UPDATE, stream);
+    GCM_LAUNCH(pe25_update_kernel, dim3(gx, nrows, L * nbatch), dim3(tc), 0, stream, d, cb, cs, mo, w.spu, w.sd, w.phi,
+               w.rho, w.pgf, w.pn, dt, ja, b2, b3);
+  }
   GCM_CHECK_LAUNCH();
   return GCM_OK;
 }

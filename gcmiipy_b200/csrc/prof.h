@@ -1,0 +1,32 @@
+// prof.h -- optional per-kernel timing with CUDA events on the launching stream (used by bench.py for the
+// live roofline of the dominant kernel; off by default, no cost when off).
+#pragma once
+#include "gcm_common.h"
+
+enum GcmProfKind {
+  GCM_K_FILTER_SPU = 0,   // pe25_filter_kernel<1>
+  GCM_K_COLUMN = 1,       // pe25_column_kernel
+  GCM_K_FILTER_PGF = 2,   // pe25_pgf_filter_kernel
+  GCM_K_UPDATE = 3,       // pe25_update_kernel
+  GCM_K_COUNT = 4
+};
+
+#ifdef GCM_EMU
+struct GcmProfScope {
+  GcmProfScope(int, void*) {}
+};
+#else
+void gcm_prof_begin(int kind, void* stream);
+void gcm_prof_end(int kind, void* stream);
+extern int g_gcm_prof_on;
+struct GcmProfScope {
+  int kind;
+  void* stream;
+  GcmProfScope(int k, void* s) : kind(k), stream(s) {
+    if (g_gcm_prof_on) gcm_prof_begin(kind, stream);
+  }
+  ~GcmProfScope() {
+    if (g_gcm_prof_on) gcm_prof_end(kind, stream);
+  }
+};
+#endif

@@ -76,6 +76,15 @@ class Stepper:
         self.cur, self.nxt = self.nxt, self.cur
         self.nsteps_done += int(nsteps)
 
+    def step_host(self, host_in, host_out, dt, nsteps=1):
+        """Host-resident caller: copy the five (pinned) host tensors `host_in` to the device, advance, copy the
+        new state into the five (pinned) host tensors `host_out`.  All asynchronous on the current stream."""
+        for dst, src in zip(self.cur, host_in):
+            dst.copy_(src, non_blocking=True)
+        self.step(dt, nsteps)
+        for dst, src in zip(host_out, self.cur):
+            dst.copy_(src, non_blocking=True)
+
     def tensors(self):
         """The current state as device tensors (p, u, v, t, q); valid until the next step()."""
         return tuple(self.cur)

@@ -198,6 +198,17 @@ int gcm_shift_op(int op, const double* d_q, double* d_out, int n2, int n1, int n
 /* temperature.py:7-19: dir 0: T = theta / (P0/p)^kappa ; dir 1: theta = T * (P0/p)^kappa */
 int gcm_temperature_convert(int dir, const double* d_t, const double* d_p, double* d_out, size_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optional per-kernel timing (CUDA events on the launching stream), used by bench.py for the live
+ * roofline of the dominant kernel.  Off by default.  gcm_prof_collect synchronises the device, writes the
+ * summed milliseconds and launch counts per kernel kind ([gcm_prof_kinds()] entries) and clears them.
+ * The reference has no counterpart (its only instrumentation is tqdm, no_limits_2_5d.py:230).
+ * ---------------------------------------------------------------------------------------------- */
+int gcm_prof_enable(int on);
+int gcm_prof_kinds(void);
+const char* gcm_prof_kind_name(int kind);
+int gcm_prof_collect(double* h_ms, long long* h_launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,67 @@
+"""The C-ABI library builds, loads and exports every symbol include/gcm_b200.h declares (no compute calls:
+this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gcm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for must in ("gcm_geom_create", "gcm_pe25_half_step", "gcm_pe25_matsuno_step", "gcm_sw2d_matsuno_step",
+                 "gcm_pe2d_matsuno_step", "gcm_polar_filter", "gcm_phi_port_pgf", "gcm_laplacian5",
+                 "gcm_fl_donor_cell_advection", "gcm_halo_pack"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import gcmiipy_b200
+    from gcmiipy_b200 import _abi
+    lib = gcmiipy_b200.build()
+    cdll = ctypes.CDLL(lib)
+    syms = declared_symbols()
+    missing = [s for s in syms if not hasattr(cdll, s)]
+    assert not missing, missing
+    assert sorted(_abi.SIGNATURES) == syms, set(_abi.SIGNATURES) ^ set(syms)
+    _abi.bind(cdll)
+    assert cdll.gcm_version() >= 100
+    assert cdll.gcm_status_string(-2) == b"bad extent or row range"
+
+
+def test_product_has_no_cpu_fallback():
+    """Without a CUDA device the product refuses to compute; it never imports the oracle."""
+    import torch
+    from gcmiipy_b200 import _lib
+    _lib._override_for_tests(None, None)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            _lib.device()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gcmiipy_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "np_oracle" not in text and "import oracle" not in text, f
+
+
+def test_argument_errors_are_status_codes():
+    """Bad arguments come back as negative status codes before any CUDA call (error convention of the ABI)."""
+    import gcmiipy_b200
+    from gcmiipy_b200 import _abi
+    cdll = _abi.bind(ctypes.CDLL(gcmiipy_b200.build()))
+    assert cdll.gcm_geom_create(None, None) == -1
+    assert cdll.gcm_sw2d_operator(9, None, None, None, ctypes.c_void_p(16), 4, 4, 1.0, None) == -4
+    assert cdll.gcm_sw2d_matsuno_step(None, None, None, None, None, None, 4, 4, 1.0, 1.0, 1, None, 0, None) == -1
+    assert cdll.gcm_fl_calc_r(ctypes.c_void_p(16), ctypes.c_void_p(16), 0, 4, None) == -2
+    assert cdll.gcm_pe25_workspace_bytes(None, 1) == 0
+    desc = _abi.GeomDesc(H=4, W=3, L=2)
+    h = ctypes.c_void_p()
+    assert cdll.gcm_geom_create(ctypes.byref(desc), ctypes.byref(h)) == -1     # tables missing

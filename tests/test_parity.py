@@ -1,0 +1,321 @@
+"""Parity of the kernel path with the reference: (1) the golden vectors produced by the UNMODIFIED reference
+(tests/golden, oracle/make_golden.py) and (2) the pinned numpy oracle on seeded inputs.
+
+Every case runs on two builds of the same kernel sources (conftest.backend): "gpu" = the sm_100a library on a
+B200 through the C ABI (-m gpu, the parity tests proper) and "emu" = the sources compiled for the CPU emulator
+(no GPU in the build container).
+
+Tolerances (fp64, relative to max|ref| of the field; u and v against max(|u|, |v|) because u starts at 0):
+  * + - * / only kernels (shallow water, Laplacian, flux limiter, shifts, aflux, advec_*): BIT-EXACT
+  * kernels with pow() or the FFT filter, single call: 1e-13
+  * phiu / phiv (differences of a geopotential of magnitude ~3e5 m2/s2): 1e-13 of p * max|phi| / dx
+  * N-step runs at the stable time steps of SURVEY.md section 4: 1e-11
+"""
+import numpy as np
+import pytest
+
+import np_oracle as O
+from conftest import load_golden
+from gcmiipy_b200 import (coordinates, coordinates_1d, coordinates_3d, dynamics, flux_limiter, geometry, low_pass,
+                          matsumo_temp, matsuno_c_grid, no_limits_2_5d, no_limits_2d, phi_port, temperature,
+                          viscosity)
+
+TOL_CALL = 1e-13
+TOL_RUN = 1e-11
+
+
+def rel(a, b, scale=None):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    s = np.max(np.abs(b)) if scale is None else scale
+    return np.max(np.abs(a - b)) / max(s, 1e-300)
+
+
+def exact(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a, b), "max |diff| = %g" % np.max(np.abs(a - b))
+
+
+def check_state(got, ref, tol):
+    suv = max(np.max(np.abs(ref[1])), np.max(np.abs(ref[2])))
+    for name, a, b in zip("puvtq", got, ref):
+        e = rel(a, b, suv if name in "uv" else None)
+        assert e <= tol, "field %s: rel err %.3g > %g" % (name, e, tol)
+
+
+# ---- 2-D shallow water: bit-exact ---------------------------------------------------------------------
+def test_sw2d_operators_golden(backend):
+    g = load_golden("sw2d_20x24")
+    u, v, p, dx = g["u_0"], g["v_0"], g["p_0"], float(g["dx"])
+    exact(matsuno_c_grid.advection_of_velocity_u(u, v, dx), g["adv_u"])
+    exact(matsuno_c_grid.advection_of_velocity_v(u, v, dx), g["adv_v"])
+    exact(matsuno_c_grid.geopotential_gradient_u(p, dx), g["grad_u"])
+    exact(matsuno_c_grid.geopotential_gradient_v(p, dx), g["grad_v"])
+    exact(matsuno_c_grid.advection_of_geopotential(u, v, p, dx), g["adv_p"])
+    assert matsuno_c_grid.courant_number(p, u, dx, float(g["dt"])) == float(g["courant"])
+
+
+def test_sw2d_matsuno_golden(backend):
+    g = load_golden("sw2d_20x24")
+    s = (g["u_0"], g["v_0"], g["p_0"])
+    for a, k in zip(matsuno_c_grid.matsumo_scheme(*s, float(g["dx"]), float(g["dt"])), "uvp"):
+        exact(a, g[k + "_1"])
+    for a, k in zip(matsuno_c_grid.matsumo_scheme(*s, float(g["dx"]), float(g["dt"]), nsteps=50), "uvp"):
+        exact(a, g[k + "_50"])
+
+
+def test_sw2d_reference_main_case(backend):
+    """matsuno_c_grid.py:146-157 at the stable bump: 64 x 64, dx = 300 km, dt = 300 s, 100 steps."""
+    g = load_golden("sw2d_64x64_main")
+    u = np.zeros((64, 64)); v = np.zeros((64, 64)); h = np.full((64, 64), 8000.0)
+    u[32, 32] = 1.0
+    for a, k in zip(matsuno_c_grid.matsumo_scheme(u, v, h, 300e3, 300.0, nsteps=100), "uvp"):
+        exact(a, g[k + "_100"])
+
+
+@pytest.mark.parametrize("H,W,n", [(80, 96, 3), (33, 70, 2), (1, 7, 2), (5, 1, 2)])
+def test_sw2d_tiled_and_ragged_vs_oracle(backend, H, W, n):
+    """Grids too large for the shared-memory-resident kernel take the tiled fused kernel; ragged and
+    degenerate extents exercise the periodic wrap of the halo tiles."""
+    rng = np.random.default_rng(H * 100 + W)
+    u, v = rng.standard_normal((2, H, W))
+    h = 8000.0 + 10 * rng.standard_normal((H, W))
+    ref = (u, v, h)
+    for _ in range(n):
+        ref = O.matsumo_scheme(*ref, 300e3, 300.0)
+    for a, b in zip(matsuno_c_grid.matsumo_scheme(u, v, h, 300e3, 300.0, nsteps=n), ref):
+        exact(a, b)
+
+
+# ---- coordinates: bit-exact shifts (reference KATs test_matsumo.py:9-21) ---------------------------------
+def test_shift_directions(backend):
+    p = np.full((3, 3), 1.0); p[1, 1] = 0
+    assert coordinates.ipj(p)[1, 0] == 0          # test_matsumo.py:9-14
+    assert coordinates.ijp(p)[0, 1] == 0          # test_matsumo.py:16-21
+    assert matsuno_c_grid.geopotential_gradient_v(p, 1.0)[1, 1] == O.G     # test_matsumo.py:24-29
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal((4, 5, 6))
+    for name in ("ipj", "imj", "ijp", "ijm", "imjp", "kp", "km", "kph", "kmh", "iph", "imh", "jph", "jmh"):
+        exact(getattr(coordinates_3d, name)(q), getattr(O, name)(q))
+    exact(coordinates_3d.gradi(q, 3.0), O.gradi(q, 3.0))
+    exact(coordinates_3d.gradj(q, 7.0), O.gradj(q, 7.0))
+    q2 = q[0]
+    for name in ("ipj", "imj", "ijp", "ijm", "imjp", "iph", "imh", "jph", "jmh"):
+        exact(getattr(coordinates, name)(q2), getattr(O, name)(q2))
+    q1 = q[0, 0]
+    exact(coordinates_1d.ip(q1), O.ip1(q1)); exact(coordinates_1d.im(q1), O.im1(q1))
+    exact(coordinates_1d.div(q1, 2.0), (q1 - O.im1(q1)) / 2.0)
+
+
+# ---- viscosity / flux limiter / temperature ------------------------------------------------------------
+def test_viscosity_golden(backend):
+    g = load_golden("viscosity")
+    exact(viscosity.finite_laplacian_2d(g["a"], 1.0), g["lap"])
+    exact(viscosity.incompressible_viscosity_2d(g["b"], float(g["mu"]), 300e3), g["vis"])
+    exact(viscosity.finite_laplacian_2d(g["c"], 3.5), g["lap2"])
+
+
+def test_flux_limiter_golden(backend):
+    g = load_golden("flux_limiter")
+    assert flux_limiter.van_leer(1.0) == 1 and flux_limiter.van_leer(0.0) == 0      # flux_limiter.py:46-48
+    exact(flux_limiter.van_leer(g["r"]), g["van_leer"])
+    for tag in ("pos", "neg", "mix"):
+        exact(flux_limiter.calc_r(g["q_" + tag]), g["r_" + tag])
+        exact(flux_limiter.donor_cell_flux(g["q_" + tag], g["u_" + tag]), g["flux_" + tag])
+    for tag in ("pos", "neg"):
+        exact(flux_limiter.donor_cell_advection(g["q_" + tag], g["u_" + tag], 100.0, 1.0, nsteps=100), g["adv100_" + tag])
+    exact(flux_limiter.donor_cell_advection(g["q_mix"], g["u_mix"], 100.0, 1.0), g["adv_mix"])
+
+
+def test_temperature_roundtrip(backend):
+    """temperature.py:31-41."""
+    g = load_golden("temperature")
+    th = temperature.to_potential_temp(np.array([O.standard_temperature]), np.array([O.standard_pressure]))
+    assert rel(th, np.array([float(g["theta"])])) < 1e-15
+    tt = temperature.to_true_temp(th, np.array([O.standard_pressure]))
+    assert abs(tt[0] - O.standard_temperature) < 1e-7
+
+
+# ---- 2-D primitive equations ---------------------------------------------------------------------------
+def test_pe2d_golden(backend):
+    g = load_golden("pe2d_24x36")
+    s = tuple(g[k + "_0"] for k in "puvtq")
+    dx, dt = float(g["dx"]), float(g["dt"])
+    dut, dvt = no_limits_2d.advec_m(s[0], s[1], s[2], dx)
+    exact(dut, g["dut"]); exact(dvt, g["dvt"])                                      # + - * / only
+    for a, k in zip(no_limits_2d.pgf(s[0], s[3], dx), ("pgu", "pgv")):
+        assert rel(a, g[k]) < TOL_CALL
+    for n in (1, 20):
+        out = no_limits_2d.matsuno_timestep(*s, dt, dx, nsteps=n)
+        for a, k in zip(out, "puvtq"):
+            assert rel(a, g["%s_%d" % (k, n)]) < TOL_RUN, k
+        exact(out[4], g["q_%d" % n])                                                # q passes through
+
+
+def test_pe2d_half_step_vs_oracle(backend):
+    rng = np.random.default_rng(5)
+    H, W = 10, 14
+    p = 101325.0 + 50 * rng.standard_normal((H, W))
+    u, v = rng.standard_normal((2, H, W))
+    t = 280.0 + rng.standard_normal((H, W))
+    q = rng.random((H, W))
+    sp, su, sv, st = p + rng.standard_normal((H, W)), u * 1.1, v * 0.9, t + 0.1
+    ref = O.pe2d_half_timestep(p, u, v, t, q, sp, su, sv, st, q, 0.1, 100.0)
+    got = no_limits_2d.half_timestep(p, u, v, t, q, sp, su, sv, st, q, 0.1, 100.0)
+    for a, b, k in zip(got, ref, "puvtq"):
+        assert rel(a, b) < TOL_CALL, k
+
+
+# ---- matsumo_temp --------------------------------------------------------------------------
+def test_matsumo_temp_golden(backend):
+    g = load_golden("matsumo_temp_12x12")
+    s = tuple(g[k + "_0"] for k in "uvpt")
+    for n in (1, 10):
+        out = matsumo_temp.matsumo_scheme(*s, float(g["dx"]), float(g["dt"]), nsteps=n)
+        suv = max(np.max(np.abs(g["u_%d" % n])), np.max(np.abs(g["v_%d" % n])))
+        for a, k in zip(out, "uvpt"):
+            assert rel(a, g["%s_%d" % (k, n)], suv if k in "uv" else None) < TOL_RUN, k
+
+
+# ---- phi_port -----------------------------------------------------------------------------------------------
+def test_phi_port_golden(backend):
+    g = load_golden("phi_port_24x36x9")
+    geom = geometry.gen_geometry(24, 36, 9)
+    phi = phi_port.PGF(np.transpose(g["t"]), np.transpose(g["p"]), geom)
+    assert phi.shape == (36, 24, 9)
+    assert rel(np.transpose(phi), g["phi"]) < TOL_CALL
+    geom.heightmap = g["heightmap2"]
+    phi = np.transpose(phi_port.PGF(np.transpose(g["t2"]), np.transpose(g["p2"]), geom))
+    assert rel(phi, g["phi2"]) < TOL_CALL
+    assert np.all(phi[:, :, 1:] == 0)                  # IMAX = 1 quirk: only column 0 is computed
+
+
+# ---- 2.5-D operators ---------------------------------------------------------------------------------------
+def test_ops25_golden(backend):
+    g = load_golden("ops25_24x36x9")
+    geom = geometry.gen_geometry(24, 36, 9, sig_func=geometry.manabe_sig)
+    p, u, v, t, q = (g[k] for k in "puvtq")
+    exact(dynamics.calc_pu(p, u), g["pu"]); exact(dynamics.calc_pv(p, v), g["pv"])
+    exact(dynamics.un_pu(g["pu"], p), g["un_pu"]); exact(dynamics.un_pv(g["pv"], p), g["un_pv"])
+    pit, sd = dynamics.aflux(g["pu"], g["pv"], geom)
+    exact(pit, g["pit"]); exact(sd, g["sd"])                                        # sums in the reference's k order
+    dut, dvt = dynamics.advec_m_pu(p, u, v, g["pu"], g["pv"], geom)
+    exact(dut, g["dut"]); exact(dvt, g["dvt"])
+    exact(dynamics.advec_t(g["pu"], g["pv"], t, geom), g["advec_t"])
+    exact(dynamics.advec_sig(g["sd"], t, geom), g["advec_sig"])
+    assert rel(dynamics.compute_geopotential(p, t, geom), g["phi"]) < TOL_CALL
+    pgu, pgv, phiu, phiv = dynamics.pgf(p, t, geom)
+    assert rel(pgu, g["pgu"]) < TOL_CALL and rel(pgv, g["pgv"]) < TOL_CALL
+    phimax, pmax = np.max(np.abs(g["phi"])), np.max(p)
+    assert rel(phiu, g["phiu"], pmax * phimax / np.min(geom.dx_j)) < TOL_CALL
+    assert rel(phiv, g["phiv"], pmax * phimax / geom.dy) < TOL_CALL
+    assert rel(temperature.to_true_temp(t, p * geom.sig + geom.ptop), g["true_temp"]) < TOL_CALL
+    assert rel(low_pass.arakawa_1977(g["pu"], geom), g["filt3d"]) < TOL_CALL
+    f2 = low_pass.arakawa_1977(p, geom)
+    assert f2.shape == (1, 24, 36) and rel(f2, g["filt2d"]) < TOL_CALL              # 2-D in -> (1, H, W) out
+    assert rel(low_pass.avrx(p, geom), g["avrx2d"]) < TOL_CALL
+    hs = dynamics.half_timestep(p, u, v, t, q, p, u, v, t, q, float(g["dt"]), geom)
+    check_state(hs, tuple(g["hs_" + k] for k in "puvtq"), 1e-12)
+
+
+@pytest.mark.parametrize("W", [8, 16, 36, 72, 98, 288, 1440])
+def test_polar_filter_sizes_vs_oracle(backend, W):
+    """Mixed-radix rows: 2^k, 2^2 3^2, 2^3 3^2, 2 7^2 (generic radix), 2^5 3^2, 2^5 3^2 5."""
+    H, L = 6, 3
+    geom = geometry.gen_geometry(H, W, L)
+    q = np.random.default_rng(W).standard_normal((L, H, W))
+    ref = O.arakawa_1977(q, O.gen_geometry(H, W, L))
+    assert rel(low_pass.arakawa_1977(q, geom), ref) < TOL_CALL
+
+
+def test_polar_filter_single_column_is_identity(backend):
+    geom = geometry.gen_geometry(4, 1, 2)
+    q = np.arange(8.0).reshape(2, 4, 1)
+    exact(low_pass.arakawa_1977(q, geom), q)            # low_pass.py:58-59
+
+
+# ---- 2.5-D N-step runs ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,H,W,L", [("run25_8x8x3", 8, 8, 3), ("run25_24x36x9", 24, 36, 9),
+                                        ("run25_24x36x9_refic", 24, 36, 9), ("run25_24x36x9_ptop", 24, 36, 9),
+                                        ("run25_1x16x17_mountain", 1, 16, 17), ("run25_46x72x9", 46, 72, 9)])
+def test_run25_golden(backend, name, H, W, L):
+    g = load_golden(name)
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    geom.ptop = float(g["ptop"]); geom.heightmap = g["heightmap"]
+    s = tuple(g[k + "_0"] for k in "puvtq")
+    n, dt = int(g["nsteps"]), float(g["dt"])
+    snaps = sorted(int(k[2:]) for k in g if k.startswith("p_") and k != "p_0")
+    st = dynamics.Stepper(geom, *s)
+    done = 0
+    for i in snaps:
+        st.step(dt, i - done)
+        done = i
+        check_state(st.download(), tuple(g["%s_%d" % (k, i)] for k in "puvtq"), TOL_RUN)
+    assert done == n
+    one = dynamics.matsuno_timestep(*s, dt, geom)              # the drop-in per-step call
+    check_state(one, tuple(g["%s_1" % k] for k in "puvtq") if "p_1" in g else O.matsuno_timestep(*s, dt, _ogeom(g, H, W, L)), 1e-12)
+
+
+def _ogeom(g, H, W, L):
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    og.ptop = float(g["ptop"]); og.heightmap = g["heightmap"]
+    return og
+
+
+def test_run_model_golden(backend):
+    """no_limits_2_5d.run_model(8, 8, 3, ...) through the STATS diagnostics (no_limits_2_5d.py:79-94, :220-236)."""
+    g = load_golden("run_model_8x8x3")
+    no_limits_2_5d.STATS.clear()
+    seen = []
+    p, u, v, t, q, ground, geom = no_limits_2_5d.run_model(8, 8, 3, 450.0, 5, lambda *s: seen.append(s[0].copy()))
+    check_state((p, u, v, t, q), tuple(g[k] for k in "puvtq"), TOL_RUN)
+    assert len(seen) == 5 and np.array_equal(seen[-1], p)
+    assert rel(np.array(no_limits_2_5d.STATS["ke"]), g["energy"]) < 1e-12
+    assert rel(np.array(no_limits_2_5d.STATS["u_max"]), g["u_max"]) < TOL_RUN
+    assert rel(np.array(no_limits_2_5d.STATS["v_min"]), g["v_min"]) < TOL_RUN
+    ke = no_limits_2_5d.calc_energy(p, u, v, t, q, ground, geom)
+    assert rel(np.array(ke), np.array(O.calc_energy(*(g[k] for k in "puvtq"), O.gen_geometry(8, 8, 3, sig_func=O.manabe_sig)))) < 1e-12
+
+
+def test_full_timestep_and_boundary_callback(backend):
+    geom = geometry.gen_geometry(8, 8, 3, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(8, 8, 3, sig_func=O.manabe_sig)
+    s = O.synthetic_state(og, seed=3)
+    bc = lambda p, u, v, t, q, dt, g: (p, u * 0.5, v, t, q)
+    ref = O.matsuno_timestep(*s, 450.0, og, boundary_conditions=bc)
+    got = dynamics.matsuno_timestep(*s, 450.0, geom, boundary_conditions=bc)
+    check_state(got, ref, 1e-12)
+    no_limits_2_5d.STATS.clear()
+    out = no_limits_2_5d.full_timestep(*s, None, 450.0, 0.0, geom)
+    check_state(out[:5], O.matsuno_timestep(*s, 450.0, og), 1e-12)
+    assert len(no_limits_2_5d.STATS["ke"]) == 1
+
+
+def test_ensemble_members_are_independent(backend):
+    """Batched ensemble (BASELINE configs[3]): member m of a batched step == the same member stepped alone."""
+    geom = geometry.gen_geometry(24, 36, 9, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(24, 36, 9, sig_func=O.manabe_sig)
+    members = [O.synthetic_state(og, seed=1234 + m) for m in range(3)]
+    batched = tuple(np.stack([m[f] for m in members]) for f in range(5))
+    st = dynamics.Stepper(geom, *batched)
+    st.step(450.0, 3)
+    out = st.download()
+    for m, s in enumerate(members):
+        single = dynamics.Stepper(geom, *s)
+        single.step(450.0, 3)
+        for a, b in zip(out, single.download()):
+            exact(a[m], b)
+        ref = s
+        for _ in range(3):
+            ref = O.matsuno_timestep(*ref, 450.0, og)
+        check_state(tuple(a[m] for a in out), ref, TOL_RUN)
+
+
+def test_nonfinite_input_propagates_like_numpy(backend):
+    """The reference has no error path: NaNs propagate and the caller polls (matsuno_c_grid.py:184-187)."""
+    geom = geometry.gen_geometry(8, 8, 3, sig_func=geometry.manabe_sig)
+    s = list(O.synthetic_state(O.gen_geometry(8, 8, 3, sig_func=O.manabe_sig)))
+    s[1] = s[1].copy(); s[1][0, 2, 2] = np.nan
+    out = dynamics.matsuno_timestep(*s, 450.0, geom)
+    assert np.isnan(out[1]).any()
