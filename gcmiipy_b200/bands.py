@@ -1,0 +1,135 @@
+"""Latitude-band domain decomposition of the 2.5-D Matsuno step across GPUs.
+
+The reference is a single process: every j-shift is np.roll over the whole array (coordinates_3d.py:43-48).
+Here rank r owns the contiguous rows [r H/R, (r+1) H/R) of every field, all i and all k, so the zonal FFT
+filter rows (low_pass.py:41-78) and the vertical column scans (dynamics.py:35-46, :111-142) stay rank-local.
+The j-stencil of a half step reaches rows j-1 .. j+2 (dynamics.py:183-227), so each rank stores one halo row
+to the north and two to the south; ranks form a ring (the reference's roll is periodic over the pole) and
+exchange halo rows twice per Matsuno step: before the predictor (base state) and before the corrector (star
+state).  The same kernels run on every band, so an R-rank run is bit-identical to the 1-rank run.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _host, _lib
+from .dynamics import _UNITS, _shape_check, _struct, _workspace
+from .geometry import device_geom
+
+HALO_N, HALO_S = 1, 2
+
+
+class BandStepper:
+    """One rank's latitude band of the model state, advanced by `gcm_pe25_half_step` around halo exchanges.
+
+    rank / world default to the initialised torch.distributed group (NCCL on GPUs).  world == 1 runs the same
+    band code against itself (the ring closes on the rank's own rows)."""
+
+    def __init__(self, geom, p, u, v, t, q, rank=None, world=None, group=None):
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        H, W, L = geom.height, geom.width, geom.layers
+        if H % world:
+            raise ValueError("%d rows do not split into %d equal latitude bands" % (H, world))
+        self.geom, self.rank, self.world = geom, rank, world
+        self.owned_rows = H // world
+        if self.owned_rows < HALO_S:
+            raise ValueError("a band needs at least %d rows" % HALO_S)
+        self.j0, self.j1 = rank * self.owned_rows, (rank + 1) * self.owned_rows
+        self.dg = device_geom(geom, band=(self.j0, self.j1, HALO_N, HALO_S))
+        self.family = _host.Family(p, u, v, t, q)
+        rows = torch.arange(self.j0 - HALO_N, self.j1 + HALO_S) % H
+        full = [_host.dev(x) for x in (p, u, v, t, q)]
+        rows = rows.to(full[0].device)
+        self.cur = [x.index_select(x.dim() - 2, rows).contiguous() for x in full]
+        _shape_check(self.dg, *self.cur)
+        self.star = [torch.empty_like(x) for x in self.cur]
+        self.nxt = [torch.empty_like(x) for x in self.cur]
+        lib = _lib.lib()
+        n_s = lib.gcm_halo_buffer_doubles(self.dg.handle, HALO_S)
+        n_n = lib.gcm_halo_buffer_doubles(self.dg.handle, HALO_N)
+        mk = lambda n: torch.empty(n, dtype=torch.float64, device=_lib.device())
+        self.send_north, self.recv_south = mk(n_s), mk(n_s)      # my first 2 owned rows -> north neighbour's south halo
+        self.send_south, self.recv_north = mk(n_n), mk(n_n)      # my last owned row     -> south neighbour's north halo
+        self.north, self.south = (rank - 1) % world, (rank + 1) % world
+        self.nsteps_done = 0
+
+    # ---- halo exchange ------------------------------------------------------------------------------
+    def exchange(self, state):
+        lib, dg, s = _lib.lib(), self.dg, _struct(state)
+        lo, hi = dg.row_lo, dg.row_hi
+        stream = _lib.stream()
+        if self.world == 1:
+            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), lo, ctypes.byref(s), hi, HALO_S, stream),
+                       "gcm_halo_copy_rows")
+            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), hi - HALO_N, ctypes.byref(s), lo - HALO_N,
+                                              HALO_N, stream), "gcm_halo_copy_rows")
+            return
+        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), lo, HALO_S, _host.ptr(self.send_north), stream),
+                   "gcm_halo_pack")
+        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), hi - HALO_N, HALO_N, _host.ptr(self.send_south), stream),
+                   "gcm_halo_pack")
+        ops = [dist.P2POp(dist.isend, self.send_north, self.north, self.group, tag=1),
+               dist.P2POp(dist.isend, self.send_south, self.south, self.group, tag=2),
+               dist.P2POp(dist.irecv, self.recv_south, self.south, self.group, tag=1),
+               dist.P2POp(dist.irecv, self.recv_north, self.north, self.group, tag=2)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), hi, HALO_S, _host.ptr(self.recv_south), stream),
+                   "gcm_halo_unpack")
+        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), lo - HALO_N, HALO_N, _host.ptr(self.recv_north),
+                                       stream), "gcm_halo_unpack")
+
+    # ---- stepping -------------------------------------------------------------------------------------
+    def _half(self, base, star, out, dt):
+        ws, need = _workspace(self.dg, 1)
+        sb, ss, so = _struct(base), _struct(star), _struct(out)
+        _lib.check(_lib.lib().gcm_pe25_half_step(self.dg.handle, ctypes.byref(sb), ctypes.byref(ss), ctypes.byref(so),
+                                                 float(dt), 1, _host.ptr(ws), need, _lib.stream()), "gcm_pe25_half_step")
+
+    def step(self, dt, nsteps=1):
+        dt = _host.scalar(dt)
+        for _ in range(int(nsteps)):
+            self.exchange(self.cur)
+            self._half(self.cur, self.cur, self.star, dt)        # dynamics.py:231
+            self.exchange(self.star)
+            self._half(self.cur, self.star, self.nxt, dt)        # dynamics.py:234
+            self.cur, self.nxt = self.nxt, self.cur
+        self.nsteps_done += int(nsteps)
+
+    def step_host(self, host_in, host_out, dt, nsteps=1):
+        """host_in / host_out: this rank's band (with halo rows) as five pinned host tensors."""
+        for dst, src in zip(self.cur, host_in):
+            dst.copy_(src, non_blocking=True)
+        self.step(dt, nsteps)
+        for dst, src in zip(host_out, self.cur):
+            dst.copy_(src, non_blocking=True)
+
+    def upload(self, p, u, v, t, q):
+        """Band-shaped tensors (as returned by tensors())."""
+        for dst, src in zip(self.cur, (p, u, v, t, q)):
+            dst.copy_(src, non_blocking=True)
+
+    def tensors(self):
+        return tuple(self.cur)
+
+    def owned(self):
+        lo, hi = self.dg.row_lo, self.dg.row_hi
+        return tuple(x.narrow(x.dim() - 2, lo, hi - lo) for x in self.cur)
+
+    def gather(self):
+        """The full fields on every rank (all_gather of the owned rows), in the caller's array family."""
+        parts = [x.contiguous() for x in self.owned()]
+        if self.world == 1:
+            full = parts
+        else:
+            full = []
+            for x in parts:
+                bufs = [torch.empty_like(x) for _ in range(self.world)]
+                dist.all_gather(bufs, x, group=self.group)
+                full.append(torch.cat(bufs, dim=x.dim() - 2))
+        return tuple(self.family.out(x, unit) for x, unit in zip(full, _UNITS))

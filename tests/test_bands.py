@@ -1,0 +1,103 @@
+"""Latitude-band decomposition: an R-rank run must be BIT-IDENTICAL to the 1-rank run
+(same kernels, decomposition-invariant arithmetic order).  World sizes 2 and 4 run here on the CPU with the
+`gloo` backend and the emulator build of the kernels; the `gpu` cases run the same band code on a B200."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import np_oracle as O
+from gcmiipy_b200 import bands, dynamics, geometry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(H=24, W=36, L=9, seed=1234):
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    geom.heightmap = 100.0 * np.random.default_rng(seed).random((H, W))       # rows differ: catches row mix-ups
+    s = O.synthetic_state(O.gen_geometry(H, W, L, sig_func=O.manabe_sig), seed=seed)
+    return geom, s
+
+
+def test_single_rank_band_is_bit_identical_to_whole_grid(backend):
+    geom, s = _case()
+    whole = dynamics.Stepper(geom, *s)
+    whole.step(450.0, 4)
+    band = bands.BandStepper(geom, *s, rank=0, world=1)
+    band.step(450.0, 4)
+    for a, b in zip(band.gather(), whole.download()):
+        assert np.array_equal(a, b)
+
+
+def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend):
+    """Bands stepped one by one in this process with halo rows taken from the whole-grid state."""
+    geom, s = _case(H=24)
+    whole = dynamics.Stepper(geom, *s)
+    whole.step(450.0, 1)
+    ref = whole.download()
+    star = dynamics.half_timestep(*s, *s, 450.0, geom)
+    for world in (2, 3, 4):
+        for rank in range(world):
+            b = bands.BandStepper(geom, *s, rank=rank, world=world)
+            rows = np.arange(b.j0 - 1, b.j1 + 2) % 24
+            b._half(b.cur, b.cur, b.star, 450.0)
+            for got, want in zip(b.star, star):
+                got = got.cpu().numpy()
+                assert np.array_equal(got[..., 1:-2, :], np.take(want, rows, axis=-2)[..., 1:-2, :])
+            for dst, src in zip(b.star, star):       # halo rows of the star state from the whole-grid predictor
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(np.take(src, rows, axis=-2))))
+            b._half(b.cur, b.star, b.nxt, 450.0)
+            for got, want in zip(b.nxt, ref):
+                assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, nsteps, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["GCM_EMU_THREADS"] = "2"
+    from emu import emu_lib
+    from gcmiipy_b200 import _lib
+    _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    geom, s = _case()
+    b = bands.BandStepper(geom, *s)
+    assert (b.rank, b.world) == (rank, world)
+    b.step(450.0, nsteps)
+    full = b.gather()
+    if rank == 0:
+        np.savez(out, *full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_ranks_bit_identical_to_single_process(world, tmp_path):
+    torch.set_num_threads(1)
+    out = str(tmp_path / "bands.npz")
+    mp.spawn(_worker, args=(world, _free_port(), 3, out), nprocs=world, join=True)
+    from emu import emu_lib
+    from gcmiipy_b200 import _lib
+    _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
+    try:
+        geom, s = _case()
+        whole = dynamics.Stepper(geom, *s)
+        whole.step(450.0, 3)
+        with np.load(out) as z:
+            for k, b in zip(sorted(z.files, key=lambda n: int(n.split("_")[1])), whole.download()):
+                assert np.array_equal(z[k], b), k
+    finally:
+        _lib._override_for_tests(None, None)
