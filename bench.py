@@ -172,6 +172,10 @@ def run_native(args):
 
     H, W, L, dt, members, desc = WORKLOADS[args.workload]
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    _lib.lib().gcm_pe25_select_path(args.path)
+    for kv in args.knob:
+        i, v = kv.split("=")
+        _lib.lib().gcm_tuning_knob(int(i), int(v))
     if members > 1:
         per = members // world
         states = [synthetic.synthetic_state(geom, seed=1234 + rank * per + m) for m in range(min(per, 8))]
@@ -319,6 +323,8 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="0 = fused kernels (default), 1 = general 4-kernel path")
+    ap.add_argument("--knob", action="append", default=[], help="tuning knob i=v (gcm_tuning_knob)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

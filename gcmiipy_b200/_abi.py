@@ -29,6 +29,8 @@ SIGNATURES = {
     "gcm_pe25_workspace_bytes": (_z, [_geom, _i]),
     "gcm_pe25_half_step": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, c_stream]),
     "gcm_pe25_matsuno_step": (_i, [_geom, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
+    "gcm_pe25_select_path": (_i, [_i]),
+    "gcm_tuning_knob": (_i, [_i, _i]),
     "gcm_pe25_calc_pu": (_i, [_geom, c_dp, c_dp, c_dp, c_stream]),
     "gcm_pe25_calc_pv": (_i, [_geom, c_dp, c_dp, c_dp, c_stream]),
     "gcm_pe25_un_pu": (_i, [_geom, c_dp, c_dp, c_dp, c_stream]),

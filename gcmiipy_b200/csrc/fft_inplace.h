@@ -1,0 +1,120 @@
+// fft_inplace.h -- in-place mixed-radix FFT filter over a batch of rows held in shared memory
+// (reference low_pass.py:41-78: rfft_i -> x smmz[j][n] -> irfft_i).
+//
+// Two real rows (two layers of one latitude) are packed as one complex row z = a + i b; the multiplier is
+// real and symmetric in the wavenumber, so one complex transform pair filters both (see fft_rows.h).
+//
+// No ping-pong buffer and no reordering pass:
+//   forward  = decimation in frequency: natural order in, digit-reversed order out.  Stage s (radix r,
+//              block length n = N / (r_0 .. r_{s-1})) combines the r elements q + t n/r of each block,
+//              multiplies output m by w_n^{q m} and stores it at q + m n/r.  After the last stage position
+//              p = m_0 N/r_0 + m_1 N/(r_0 r_1) + ... holds wavenumber k = m_0 + r_0 m_1 + r_0 r_1 m_2 + ...
+//   multiply = position p is scaled by table[min(k, N - k)], k = kperm[p] (folded into the last stage);
+//   inverse  = the exact mirror (decimation in time, stages in reverse order, conjugate twiddles): digit-
+//              reversed in, natural order out, scaled by N.
+// All batch rows go through a stage together, so a stage costs one __syncthreads for the whole batch.
+#pragma once
+#include "fft_rows.h"
+
+// one forward DIF stage over `nrows` rows of length N (row r starts at z + r * N)
+template <int R>
+__device__ __forceinline__ void gcm_dif_stage(double2* z, int N, int n, int nrows, const double2* __restrict__ tw,
+                                              const int* __restrict__ kperm, const double* __restrict__ table,
+                                              bool last, int tid, int nthr) {
+  const int stride = n / R;
+  const int nbf = N / R;
+  const int tstep = N / n;
+  const int total = nbf * nrows;
+  for (int w = tid; w < total; w += nthr) {
+    const int row = w / nbf, b = w - row * nbf;
+    const int blk = b / stride, q = b - blk * stride;
+    double2* base = z + row * N + blk * n + q;
+    double2 x[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[t] = base[t * stride];
+    GcmButterfly<R, -1>::run(x);
+    if (q > 0) {
+#pragma unroll
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&tw[q * m * tstep]));
+    }
+    if (last) {  // stride == 1: position p = blk * n + m holds wavenumber kperm[p]
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int k = __ldg(&kperm[blk * n + m]);
+        const double s = __ldg(&table[k <= N - k ? k : N - k]);
+        x[m].x *= s;
+        x[m].y *= s;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) base[m * stride] = x[m];
+  }
+}
+
+// one inverse DIT stage (mirror of gcm_dif_stage)
+template <int R>
+__device__ __forceinline__ void gcm_dit_stage(double2* z, int N, int n, int nrows, const double2* __restrict__ tw,
+                                              int tid, int nthr) {
+  const int stride = n / R;
+  const int nbf = N / R;
+  const int tstep = N / n;
+  const int total = nbf * nrows;
+  for (int w = tid; w < total; w += nthr) {
+    const int row = w / nbf, b = w - row * nbf;
+    const int blk = b / stride, q = b - blk * stride;
+    double2* base = z + row * N + blk * n + q;
+    double2 x[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) x[m] = base[m * stride];
+    if (q > 0) {
+#pragma unroll
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&tw[q * m * tstep]));
+    }
+    GcmButterfly<R, +1>::run(x);
+#pragma unroll
+    for (int t = 0; t < R; ++t) base[t * stride] = x[t];
+  }
+}
+
+// true when every radix of the plan has an unrolled in-place butterfly
+__host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
+  for (int p = 0; p < plan.npass; ++p) {
+    const int r = plan.radix[p];
+    if (r != 2 && r != 3 && r != 4 && r != 5) return false;
+  }
+  return true;
+}
+
+// Filter `nrows` packed rows in place.  On entry the rows are visible to the whole block; on exit they hold
+// N x (filtered rows) and are synchronised.
+__device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, const GcmFftPlan& plan,
+                                                        const double2* __restrict__ tw, const int* __restrict__ kperm,
+                                                        const double* __restrict__ table_row, int tid, int nthr) {
+  const int N = plan.n;
+  if (N == 1) return;  // low_pass.py:58-59
+  int n = N;
+  for (int p = 0; p < plan.npass; ++p) {
+    const int r = plan.radix[p];
+    const bool last = p == plan.npass - 1;
+    switch (r) {
+      case 2: gcm_dif_stage<2>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 3: gcm_dif_stage<3>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 4: gcm_dif_stage<4>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      default: gcm_dif_stage<5>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
+    }
+    n /= r;
+    __syncthreads();
+  }
+  // n == 1 here; walk the stages back up
+  for (int p = plan.npass - 1; p >= 0; --p) {
+    const int r = plan.radix[p];
+    n *= r;
+    switch (r) {
+      case 2: gcm_dit_stage<2>(z, N, n, nrows, tw, tid, nthr); break;
+      case 3: gcm_dit_stage<3>(z, N, n, nrows, tw, tid, nthr); break;
+      case 4: gcm_dit_stage<4>(z, N, n, nrows, tw, tid, nthr); break;
+      default: gcm_dit_stage<5>(z, N, n, nrows, tw, tid, nthr); break;
+    }
+    __syncthreads();
+  }
+}

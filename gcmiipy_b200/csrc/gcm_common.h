@@ -66,6 +66,14 @@ struct GcmGeomDev {
   const double* hmap;
   const double* smmz;   // [H][W/2+1]
   const double2* tw;    // [W]  exp(-2 pi i m / W)
+  // tables of the ALU-lean step kernels (pe25_fast.cu): reciprocals instead of divides, sig^kappa, and the
+  // digit-reversal map of the in-place FFT (fft_inplace.h)
+  const double* rdx_j;  // [H]  1 / dx_j
+  const double* rdx_h;  // [H]  1 / dx_h
+  const double* rdsig;  // [L]  1 / dsig
+  const double* sigkap; // [L]  sig^kappa
+  const int* kperm;     // [W]  wavenumber held at position p after the forward DIF transform
+  double rdy;           // 1 / dy
   GcmFftPlan plan;
 };
 

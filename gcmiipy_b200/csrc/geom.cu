@@ -66,7 +66,10 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   const size_t o_sig = 0, o_dsig = o_sig + up256(L * 8), o_sigb = o_dsig + up256(L * 8), o_sigt = o_sigb + up256(L * 8);
   const size_t o_dxj = o_sigt + up256(L * 8), o_dxh = o_dxj + up256(H * 8), o_hmap = o_dxh + up256(H * 8);
   const size_t o_smmz = o_hmap + up256((size_t)H * W * 8), o_tw = o_smmz + up256((size_t)H * nw * 8);
-  const size_t total = o_tw + up256((size_t)W * 16);
+  const size_t o_rdxj = o_tw + up256((size_t)W * 16), o_rdxh = o_rdxj + up256(H * 8);
+  const size_t o_rdsig = o_rdxh + up256(H * 8), o_sigkap = o_rdsig + up256(L * 8);
+  const size_t o_kperm = o_sigkap + up256(L * 8);
+  const size_t total = o_kperm + up256((size_t)W * 4);
 
   std::vector<unsigned char> host(total, 0);
   memcpy(&host[o_sig], d->h_sig, L * 8);
@@ -82,6 +85,27 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
     const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)W;
     tw[2 * m] = (double)cosl(a);
     tw[2 * m + 1] = (double)(-sinl(a));
+  }
+
+  {
+    double* rdxj = reinterpret_cast<double*>(&host[o_rdxj]);
+    double* rdxh = reinterpret_cast<double*>(&host[o_rdxh]);
+    double* rdsig = reinterpret_cast<double*>(&host[o_rdsig]);
+    double* sigkap = reinterpret_cast<double*>(&host[o_sigkap]);
+    int* kperm = reinterpret_cast<int*>(&host[o_kperm]);
+    for (int j = 0; j < H; ++j) { rdxj[j] = 1.0 / d->h_dx_j[j]; rdxh[j] = 1.0 / d->h_dx_h[j]; }
+    for (int k = 0; k < L; ++k) { rdsig[k] = 1.0 / d->h_dsig[k]; sigkap[k] = pow(d->h_sig[k], GCM_KAPPA); }
+    const GcmFftPlan& pl = g->d.plan;
+    for (int p = 0; p < W; ++p) {  // position after the forward DIF stages -> wavenumber (fft_inplace.h)
+      int k = 0, mult = 1, n = W, rem = p;
+      for (int s = 0; s < pl.npass; ++s) {
+        n /= pl.radix[s];
+        k += (rem / n) * mult;
+        rem %= n;
+        mult *= pl.radix[s];
+      }
+      kperm[p] = k;
+    }
   }
 
   void* blk = nullptr;
@@ -106,6 +130,12 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   g->d.hmap = (const double*)(b + o_hmap);
   g->d.smmz = (const double*)(b + o_smmz);
   g->d.tw = (const double2*)(b + o_tw);
+  g->d.rdx_j = (const double*)(b + o_rdxj);
+  g->d.rdx_h = (const double*)(b + o_rdxh);
+  g->d.rdsig = (const double*)(b + o_rdsig);
+  g->d.sigkap = (const double*)(b + o_sigkap);
+  g->d.kperm = (const int*)(b + o_kperm);
+  g->d.rdy = 1.0 / d->dy;
   *out = g;
   return GCM_OK;
 }

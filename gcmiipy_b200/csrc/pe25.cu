@@ -391,8 +391,24 @@ static int pe25_check_state(const gcm_state* s) {
   return GCM_OK;
 }
 
+// pe25_fast.cu
+bool gcm_pe25_fast_supported(const gcm_geom* g);
+int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                            double dt, int nbatch, double* spu, double* sd, double* phi, double* rho, double* pgf,
+                            double* pn, void* stream);
+
+static int g_pe25_path = 0;  // 0 = fused ALU-lean kernels when the geometry allows, 1 = always the 4-kernel path
+
+extern "C" int gcm_pe25_select_path(int path) {
+  GCM_REQUIRE(path == 0 || path == 1, GCM_EUNSUP);
+  g_pe25_path = path;
+  return GCM_OK;
+}
+
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
+  if (g_pe25_path == 0 && gcm_pe25_fast_supported(g))
+    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.rho, w.pgf, w.pn, stream);
   const GcmGeomDev& d = g->d;
   const int H = d.H, W = d.W, L = d.L;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;  // member strides of the caller's arrays

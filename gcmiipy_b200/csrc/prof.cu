@@ -43,6 +43,8 @@ extern "C" const char* gcm_prof_kind_name(int kind) {
     case GCM_K_COLUMN: return "pe25_column_kernel";
     case GCM_K_FILTER_PGF: return "pe25_pgf_filter_kernel";
     case GCM_K_UPDATE: return "pe25_update_kernel";
+    case GCM_K_ROW: return "pe25f_row_kernel";
+    case GCM_K_UPDATE_FAST: return "pe25f_update_kernel";
     default: return "?";
   }
 }

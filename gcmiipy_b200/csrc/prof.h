@@ -8,7 +8,9 @@ enum GcmProfKind {
   GCM_K_COLUMN = 1,       // pe25_column_kernel
   GCM_K_FILTER_PGF = 2,   // pe25_pgf_filter_kernel
   GCM_K_UPDATE = 3,       // pe25_update_kernel
-  GCM_K_COUNT = 4
+  GCM_K_ROW = 4,          // pe25f_row_kernel    (pe25_fast.cu)
+  GCM_K_UPDATE_FAST = 5,  // pe25f_update_kernel (pe25_fast.cu)
+  GCM_K_COUNT = 6
 };
 
 #ifdef GCM_EMU

@@ -96,6 +96,13 @@ int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state
 int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt, int nsteps,
                           int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Kernel path of the half step: 0 (default) = the fused ALU-lean kernels of pe25_fast.cu whenever the
+ * geometry allows (L in {3, 9}, W a product of 2, 3, 5, one row of all layers fits shared memory), else
+ * the general 4-kernel path; 1 = always the general path (A/B comparisons, widths with other prime factors). */
+int gcm_pe25_select_path(int path);
+/* launch-shape tuning knobs of the fused kernels (see pe25_fast.cu); 0 = automatic */
+int gcm_tuning_knob(int idx, int value);
+
 /* the operators half_timestep is built from, each on the owned rows of one member */
 int gcm_pe25_calc_pu(const gcm_geom* g, const double* d_p, const double* d_u, double* d_pu, void* stream);   /* dynamics.py:15 */
 int gcm_pe25_calc_pv(const gcm_geom* g, const double* d_p, const double* d_v, double* d_pv, void* stream);   /* dynamics.py:20 */
