@@ -16,31 +16,47 @@
 #pragma once
 #include "fft_rows.h"
 
+// (row, butterfly) of flat work item w without integer division (operands < 2^16, see gcm_fastdiv)
+struct GcmFftStage {
+  int N, n, stride, nbf, tstep;
+  unsigned magic_stride, magic_nbf;
+};
+__device__ __forceinline__ GcmFftStage gcm_fft_stage(const GcmFftPlan& plan, int s, int n) {
+  GcmFftStage st;
+  st.N = plan.n;
+  st.n = n;
+  st.stride = plan.stride[s];
+  st.nbf = plan.n / plan.radix[s];
+  st.tstep = plan.n / n;
+  st.magic_stride = plan.magic_stride[s];
+  st.magic_nbf = plan.magic_nbf[s];
+  return st;
+}
+
 // one forward DIF stage over `nrows` rows of length N (row r starts at z + r * N)
 template <int R>
-__device__ __forceinline__ void gcm_dif_stage(double2* z, int N, int n, int nrows, const double2* __restrict__ tw,
-                                              const int* __restrict__ kperm, const double* __restrict__ table,
-                                              bool last, int tid, int nthr) {
-  const int stride = n / R;
-  const int nbf = N / R;
-  const int tstep = N / n;
-  const int total = nbf * nrows;
+__device__ __forceinline__ void gcm_dif_stage(double2* z, const GcmFftStage st, int nrows,
+                                              const double2* __restrict__ tw, const int* __restrict__ kperm,
+                                              const double* __restrict__ table, bool last, int tid, int nthr) {
+  const int stride = st.stride, N = st.N;
+  const int total = st.nbf * nrows;
   for (int w = tid; w < total; w += nthr) {
-    const int row = w / nbf, b = w - row * nbf;
-    const int blk = b / stride, q = b - blk * stride;
-    double2* base = z + row * N + blk * n + q;
+    const int row = gcm_fastdiv(w, st.magic_nbf), b = w - row * st.nbf;
+    const int blk = gcm_fastdiv(b, st.magic_stride), q = b - blk * stride;
+    double2* base = z + row * N + blk * st.n + q;
     double2 x[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) x[t] = base[t * stride];
     GcmButterfly<R, -1>::run(x);
     if (q > 0) {
+      const int qt = q * st.tstep;
 #pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&tw[q * m * tstep]));
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&tw[qt * m]));
     }
     if (last) {  // stride == 1: position p = blk * n + m holds wavenumber kperm[p]
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const int k = __ldg(&kperm[blk * n + m]);
+        const int k = __ldg(&kperm[blk * st.n + m]);
         const double s = __ldg(&table[k <= N - k ? k : N - k]);
         x[m].x *= s;
         x[m].y *= s;
@@ -53,22 +69,21 @@ __device__ __forceinline__ void gcm_dif_stage(double2* z, int N, int n, int nrow
 
 // one inverse DIT stage (mirror of gcm_dif_stage)
 template <int R>
-__device__ __forceinline__ void gcm_dit_stage(double2* z, int N, int n, int nrows, const double2* __restrict__ tw,
-                                              int tid, int nthr) {
-  const int stride = n / R;
-  const int nbf = N / R;
-  const int tstep = N / n;
-  const int total = nbf * nrows;
+__device__ __forceinline__ void gcm_dit_stage(double2* z, const GcmFftStage st, int nrows,
+                                              const double2* __restrict__ tw, int tid, int nthr) {
+  const int stride = st.stride, N = st.N;
+  const int total = st.nbf * nrows;
   for (int w = tid; w < total; w += nthr) {
-    const int row = w / nbf, b = w - row * nbf;
-    const int blk = b / stride, q = b - blk * stride;
-    double2* base = z + row * N + blk * n + q;
+    const int row = gcm_fastdiv(w, st.magic_nbf), b = w - row * st.nbf;
+    const int blk = gcm_fastdiv(b, st.magic_stride), q = b - blk * stride;
+    double2* base = z + row * N + blk * st.n + q;
     double2 x[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) x[m] = base[m * stride];
     if (q > 0) {
+      const int qt = q * st.tstep;
 #pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&tw[q * m * tstep]));
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&tw[qt * m]));
     }
     GcmButterfly<R, +1>::run(x);
 #pragma unroll
@@ -96,11 +111,12 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
   for (int p = 0; p < plan.npass; ++p) {
     const int r = plan.radix[p];
     const bool last = p == plan.npass - 1;
+    const GcmFftStage st = gcm_fft_stage(plan, p, n);
     switch (r) {
-      case 2: gcm_dif_stage<2>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      case 3: gcm_dif_stage<3>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      case 4: gcm_dif_stage<4>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      default: gcm_dif_stage<5>(z, N, n, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 2: gcm_dif_stage<2>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 3: gcm_dif_stage<3>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 4: gcm_dif_stage<4>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      default: gcm_dif_stage<5>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
     }
     n /= r;
     __syncthreads();
@@ -109,11 +125,12 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
   for (int p = plan.npass - 1; p >= 0; --p) {
     const int r = plan.radix[p];
     n *= r;
+    const GcmFftStage st = gcm_fft_stage(plan, p, n);
     switch (r) {
-      case 2: gcm_dit_stage<2>(z, N, n, nrows, tw, tid, nthr); break;
-      case 3: gcm_dit_stage<3>(z, N, n, nrows, tw, tid, nthr); break;
-      case 4: gcm_dit_stage<4>(z, N, n, nrows, tw, tid, nthr); break;
-      default: gcm_dit_stage<5>(z, N, n, nrows, tw, tid, nthr); break;
+      case 2: gcm_dit_stage<2>(z, st, nrows, tw, tid, nthr); break;
+      case 3: gcm_dit_stage<3>(z, st, nrows, tw, tid, nthr); break;
+      case 4: gcm_dit_stage<4>(z, st, nrows, tw, tid, nthr); break;
+      default: gcm_dit_stage<5>(z, st, nrows, tw, tid, nthr); break;
     }
     __syncthreads();
   }

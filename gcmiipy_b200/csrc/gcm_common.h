@@ -48,7 +48,24 @@ struct GcmFftPlan {
   int n;
   int npass;
   int radix[GCM_MAX_RADIX_PASSES];
+  // in-place transform (fft_inplace.h): per stage the butterfly stride n_s / r_s and ceil(2^32 / x) multipliers
+  // that turn the two index divisions of a stage into one multiply-high each (operands are below 2^16)
+  int stride[GCM_MAX_RADIX_PASSES];
+  unsigned magic_stride[GCM_MAX_RADIX_PASSES];
+  unsigned magic_nbf[GCM_MAX_RADIX_PASSES];
 };
+
+// floor(x / d) for x < 2^16, d < 2^16, with m = ceil(2^32 / d); m == 0 encodes d == 1
+__host__ __device__ __forceinline__ unsigned gcm_magic(unsigned d) {
+  return d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d);
+}
+__device__ __forceinline__ int gcm_fastdiv(int x, unsigned m) {
+#ifdef GCM_EMU
+  return m ? (int)(((unsigned long long)(unsigned)x * m) >> 32) : x;
+#else
+  return m ? (int)__umulhi((unsigned)x, m) : x;
+#endif
+}
 
 // device-resident geometry tables, passed to kernels by value
 struct GcmGeomDev {

@@ -39,6 +39,14 @@ int gcm_fft_make_plan(int n, GcmFftPlan* plan) {
       plan->radix[plan->npass++] = p;
       m /= p;
     }
+  int len = n;
+  for (int s = 0; s < plan->npass; ++s) {
+    const int r = plan->radix[s];
+    plan->stride[s] = len / r;
+    plan->magic_stride[s] = gcm_magic((unsigned)(len / r));
+    plan->magic_nbf[s] = gcm_magic((unsigned)(n / r));
+    len /= r;
+  }
   return GCM_OK;
 }
 
