@@ -34,10 +34,14 @@ __device__ __forceinline__ GcmFftStage gcm_fft_stage(const GcmFftPlan& plan, int
 }
 
 // one forward DIF stage over `nrows` rows of length N (row r starts at z + r * N)
-template <int R>
+// `table` is the multiplier row of the first latitude; packed row r of the batch uses
+// table + ((pr0 + r) / NPJ) * table_stride (NPJ packed rows per latitude, pr0 = packed rows before this batch;
+// NPJ = 0: one table for the whole batch)
+template <int R, int NPJ>
 __device__ __forceinline__ void gcm_dif_stage(double2* z, const GcmFftStage st, int nrows,
                                               const double2* __restrict__ tw, const int* __restrict__ kperm,
-                                              const double* __restrict__ table, bool last, int tid, int nthr) {
+                                              const double* __restrict__ table, int table_stride, int pr0, bool last,
+                                              int tid, int nthr) {
   const int stride = st.stride, N = st.N;
   const int total = st.nbf * nrows;
   for (int w = tid; w < total; w += nthr) {
@@ -57,7 +61,8 @@ __device__ __forceinline__ void gcm_dif_stage(double2* z, const GcmFftStage st, 
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int k = __ldg(&kperm[blk * st.n + m]);
-        const double s = __ldg(&table[k <= N - k ? k : N - k]);
+        const double* trow = NPJ > 0 ? table + ((pr0 + row) / (NPJ > 0 ? NPJ : 1)) * table_stride : table;
+        const double s = __ldg(&trow[k <= N - k ? k : N - k]);
         x[m].x *= s;
         x[m].y *= s;
       }
@@ -93,18 +98,18 @@ __device__ __forceinline__ void gcm_dit_stage(double2* z, const GcmFftStage st, 
 
 // true when every radix of the plan has an unrolled in-place butterfly
 __host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
-  for (int p = 0; p < plan.npass; ++p) {
-    const int r = plan.radix[p];
-    if (r != 2 && r != 3 && r != 4 && r != 5) return false;
-  }
+  for (int p = 0; p < plan.npass; ++p)
+    if (!gcm_radix_unrolled(plan.radix[p])) return false;
   return true;
 }
 
 // Filter `nrows` packed rows in place.  On entry the rows are visible to the whole block; on exit they hold
 // N x (filtered rows) and are synchronised.
+template <int NPJ>
 __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, const GcmFftPlan& plan,
                                                         const double2* __restrict__ tw, const int* __restrict__ kperm,
-                                                        const double* __restrict__ table_row, int tid, int nthr) {
+                                                        const double* __restrict__ table_row, int table_stride, int pr0,
+                                                        int tid, int nthr) {
   const int N = plan.n;
   if (N == 1) return;  // low_pass.py:58-59
   int n = N;
@@ -113,10 +118,17 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
     const bool last = p == plan.npass - 1;
     const GcmFftStage st = gcm_fft_stage(plan, p, n);
     switch (r) {
-      case 2: gcm_dif_stage<2>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      case 3: gcm_dif_stage<3>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      case 4: gcm_dif_stage<4>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
-      default: gcm_dif_stage<5>(z, st, nrows, tw, kperm, table_row, last, tid, nthr); break;
+      case 2: gcm_dif_stage<2, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 3: gcm_dif_stage<3, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 4: gcm_dif_stage<4, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 5: gcm_dif_stage<5, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 6: gcm_dif_stage<6, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 8: gcm_dif_stage<8, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 9: gcm_dif_stage<9, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 10: gcm_dif_stage<10, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 12: gcm_dif_stage<12, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      case 15: gcm_dif_stage<15, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
+      default: gcm_dif_stage<16, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
     }
     n /= r;
     __syncthreads();
@@ -130,7 +142,14 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
       case 2: gcm_dit_stage<2>(z, st, nrows, tw, tid, nthr); break;
       case 3: gcm_dit_stage<3>(z, st, nrows, tw, tid, nthr); break;
       case 4: gcm_dit_stage<4>(z, st, nrows, tw, tid, nthr); break;
-      default: gcm_dit_stage<5>(z, st, nrows, tw, tid, nthr); break;
+      case 5: gcm_dit_stage<5>(z, st, nrows, tw, tid, nthr); break;
+      case 6: gcm_dit_stage<6>(z, st, nrows, tw, tid, nthr); break;
+      case 8: gcm_dit_stage<8>(z, st, nrows, tw, tid, nthr); break;
+      case 9: gcm_dit_stage<9>(z, st, nrows, tw, tid, nthr); break;
+      case 10: gcm_dit_stage<10>(z, st, nrows, tw, tid, nthr); break;
+      case 12: gcm_dit_stage<12>(z, st, nrows, tw, tid, nthr); break;
+      case 15: gcm_dit_stage<15>(z, st, nrows, tw, tid, nthr); break;
+      default: gcm_dit_stage<16>(z, st, nrows, tw, tid, nthr); break;
     }
     __syncthreads();
   }

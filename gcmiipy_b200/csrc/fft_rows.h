@@ -11,6 +11,8 @@
 #pragma once
 #include "gcm_common.h"
 
+#include "fft_consts.h"
+
 __device__ __forceinline__ double2 gcm_cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 gcm_csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 // a * w for DIR = -1 (forward), a * conj(w) for DIR = +1; the table holds w = exp(-i theta)
@@ -82,6 +84,64 @@ struct GcmButterfly<5, DIR> {
   }
 };
 
+// v * w_R^a for DIR = -1 (w_R = exp(-2 pi i / R)), v * conj(w_R^a) for DIR = +1.  R and a are compile-time
+// constants once the butterflies are unrolled, so the branches fold and the table values become immediates.
+template <int DIR>
+__device__ __forceinline__ double2 gcm_mul_const_tw(double2 v, int R, int a) {
+  a %= R;
+  if (a == 0) return v;
+  if (2 * a == R) return make_double2(-v.x, -v.y);
+  if (4 * a == R) return gcm_mul_i<DIR>(v);
+  if (4 * a == 3 * R) return gcm_mul_i<-DIR>(v);
+  const double c = gcm_tw_cos(R, a);
+  const double wy = DIR < 0 ? -gcm_tw_sin(R, a) : gcm_tw_sin(R, a);  // imaginary part of the factor
+  if ((8 * a) % R == 0) {  // odd eighth turn: |c| == |wy|
+    if ((c > 0) == (wy > 0)) return make_double2(c * (v.x - v.y), c * (v.x + v.y));
+    return make_double2(c * (v.x + v.y), c * (v.y - v.x));
+  }
+  return make_double2(v.x * c - v.y * wy, v.x * wy + v.y * c);
+}
+
+// Composite radix R = R1 R2 inside one thread (Cooley-Tukey): with t = R2 t1 + t2 and m = m1 + R1 m2,
+//   X[m1 + R1 m2] = sum_t2 w_R2^(t2 m2) * w_R^(t2 m1) * sum_t1 x[R2 t1 + t2] w_R1^(t1 m1)
+template <int R1, int R2, int DIR>
+struct GcmButterflyCT {
+  __device__ static __forceinline__ void run(double2* x) {
+    constexpr int R = R1 * R2;
+    double2 a[R];
+#pragma unroll
+    for (int t2 = 0; t2 < R2; ++t2) {
+      double2 y[R1];
+#pragma unroll
+      for (int t1 = 0; t1 < R1; ++t1) y[t1] = x[R2 * t1 + t2];
+      GcmButterfly<R1, DIR>::run(y);
+#pragma unroll
+      for (int m1 = 0; m1 < R1; ++m1) a[t2 * R1 + m1] = gcm_mul_const_tw<DIR>(y[m1], R, t2 * m1);
+    }
+#pragma unroll
+    for (int m1 = 0; m1 < R1; ++m1) {
+      double2 y[R2];
+#pragma unroll
+      for (int t2 = 0; t2 < R2; ++t2) y[t2] = a[t2 * R1 + m1];
+      GcmButterfly<R2, DIR>::run(y);
+#pragma unroll
+      for (int m2 = 0; m2 < R2; ++m2) x[m1 + R1 * m2] = y[m2];
+    }
+  }
+};
+template <int DIR> struct GcmButterfly<6, DIR> : GcmButterflyCT<3, 2, DIR> {};
+template <int DIR> struct GcmButterfly<8, DIR> : GcmButterflyCT<4, 2, DIR> {};
+template <int DIR> struct GcmButterfly<9, DIR> : GcmButterflyCT<3, 3, DIR> {};
+template <int DIR> struct GcmButterfly<10, DIR> : GcmButterflyCT<5, 2, DIR> {};
+template <int DIR> struct GcmButterfly<12, DIR> : GcmButterflyCT<4, 3, DIR> {};
+template <int DIR> struct GcmButterfly<15, DIR> : GcmButterflyCT<5, 3, DIR> {};
+template <int DIR> struct GcmButterfly<16, DIR> : GcmButterflyCT<4, 4, DIR> {};
+
+// radices with an unrolled butterfly
+__host__ __device__ inline bool gcm_radix_unrolled(int r) {
+  return r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 8 || r == 9 || r == 10 || r == 12 || r == 15 || r == 16;
+}
+
 template <int R, int DIR>
 __device__ __forceinline__ void gcm_fft_pass(const double2* in, double2* out, int n, int ns, const double2* tw, int tid,
                                              int nthr) {
@@ -138,6 +198,13 @@ __device__ __forceinline__ double2* gcm_fft_run(double2* a, double2* b, const Gc
       case 3: gcm_fft_pass<3, DIR>(a, b, n, ns, tw, tid, nthr); break;
       case 4: gcm_fft_pass<4, DIR>(a, b, n, ns, tw, tid, nthr); break;
       case 5: gcm_fft_pass<5, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 6: gcm_fft_pass<6, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 8: gcm_fft_pass<8, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 9: gcm_fft_pass<9, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 10: gcm_fft_pass<10, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 12: gcm_fft_pass<12, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 15: gcm_fft_pass<15, DIR>(a, b, n, ns, tw, tid, nthr); break;
+      case 16: gcm_fft_pass<16, DIR>(a, b, n, ns, tw, tid, nthr); break;
       default: gcm_fft_pass_generic<DIR>(a, b, n, r, ns, tw, tid, nthr); break;
     }
     __syncthreads();

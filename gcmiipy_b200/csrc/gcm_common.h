@@ -41,7 +41,8 @@
 #define GCM_P0 100000.0
 #define GCM_G 9.8
 
-#define GCM_MAX_RADIX_PASSES 24
+#define GCM_MAX_RADIX_PASSES 16
+#define GCM_MAXLC 16
 
 // Stockham mixed-radix plan for one row of length n (see fft_rows.h)
 struct GcmFftPlan {
@@ -90,7 +91,11 @@ struct GcmGeomDev {
   const double* rdsig;  // [L]  1 / dsig
   const double* sigkap; // [L]  sig^kappa
   const int* kperm;     // [W]  wavenumber held at position p after the forward DIF transform
+  const double* smmzw;  // [H][W/2+1]  smmz / W: the 1/n of numpy's irfft folded into the multiplier
   double rdy;           // 1 / dy
+  // per-layer tables by value (kernel parameters live in the constant bank: no load instruction) when L <= 16
+  double c_sig[GCM_MAXLC], c_dsig[GCM_MAXLC], c_sigb[GCM_MAXLC], c_sigt[GCM_MAXLC], c_rdsig[GCM_MAXLC],
+      c_sigkap[GCM_MAXLC];
   GcmFftPlan plan;
 };
 

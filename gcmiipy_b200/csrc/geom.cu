@@ -21,18 +21,57 @@ extern "C" const char* gcm_status_string(int s) {
   }
 }
 
-// radices 4,2,3,5 get unrolled butterflies; any other prime factor takes the generic O(R^2) pass
+// Radix plan of one row transform.  The 2-3-5-smooth part of n is split into as few in-register butterflies
+// as possible (radix <= 16, fft_rows.h), cheapest combination first by an estimate of flops per point plus a
+// fixed charge per pass (one shared-memory round trip, one barrier, one twiddle multiply); an odd radix goes
+// last so that the unit-stride stage is free of shared-memory bank conflicts.  Any other prime factor takes
+// the generic O(R^2) pass.
+static const int kRadix[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+static const double kRadixCost[] = {10.5, 16.5, 11.33, 12.4, 13.33, 7.0, 9.33, 8.0, 4.0, 5.33, 2.0};
+static const double kPassCost = 10.0;
+
+static void plan_search(int m, int first, int* cur, int ncur, double cost, int* best, int* nbest, double* bestcost) {
+  if (m == 1) {
+    if (cost < *bestcost) {
+      *bestcost = cost;
+      *nbest = ncur;
+      memcpy(best, cur, ncur * sizeof(int));
+    }
+    return;
+  }
+  if (ncur >= 12 || cost >= *bestcost) return;
+  for (int f = first; f < (int)(sizeof(kRadix) / sizeof(int)); ++f)
+    if (m % kRadix[f] == 0) {
+      cur[ncur] = kRadix[f];
+      plan_search(m / kRadix[f], f, cur, ncur + 1, cost + kRadixCost[f] + kPassCost, best, nbest, bestcost);
+    }
+}
+
 int gcm_fft_make_plan(int n, GcmFftPlan* plan) {
   plan->n = n;
   plan->npass = 0;
-  int m = n;
-  const int pref[4] = {4, 2, 3, 5};
-  for (int f = 0; f < 4; ++f)
-    while (m % pref[f] == 0) {
-      if (plan->npass >= GCM_MAX_RADIX_PASSES) return GCM_EUNSUP;
-      plan->radix[plan->npass++] = pref[f];
-      m /= pref[f];
+  int m = n, smooth = 1;
+  const int small[3] = {2, 3, 5};
+  for (int f = 0; f < 3; ++f)
+    while (m % small[f] == 0) {
+      m /= small[f];
+      smooth *= small[f];
     }
+  int cur[16], best[16], nbest = 0;
+  double bestcost = 1e30;
+  plan_search(smooth, 0, cur, 0, 0.0, best, &nbest, &bestcost);
+  // descending, one odd radix (if any) moved to the end
+  for (int a = 0; a < nbest; ++a)
+    for (int b = a + 1; b < nbest; ++b)
+      if (best[b] > best[a]) { int t = best[a]; best[a] = best[b]; best[b] = t; }
+  for (int a = 0; a < nbest; ++a)
+    if (best[a] % 2) {
+      const int odd = best[a];
+      for (int b = a; b + 1 < nbest; ++b) best[b] = best[b + 1];
+      best[nbest - 1] = odd;
+      break;
+    }
+  for (int a = 0; a < nbest; ++a) plan->radix[plan->npass++] = best[a];
   for (int p = 7; m > 1; p += 2)
     while (m % p == 0) {
       if (plan->npass >= GCM_MAX_RADIX_PASSES) return GCM_EUNSUP;
@@ -77,7 +116,8 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   const size_t o_rdxj = o_tw + up256((size_t)W * 16), o_rdxh = o_rdxj + up256(H * 8);
   const size_t o_rdsig = o_rdxh + up256(H * 8), o_sigkap = o_rdsig + up256(L * 8);
   const size_t o_kperm = o_sigkap + up256(L * 8);
-  const size_t total = o_kperm + up256((size_t)W * 4);
+  const size_t o_smmzw = o_kperm + up256((size_t)W * 4);
+  const size_t total = o_smmzw + up256((size_t)H * nw * 8);
 
   std::vector<unsigned char> host(total, 0);
   memcpy(&host[o_sig], d->h_sig, L * 8);
@@ -87,7 +127,12 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   memcpy(&host[o_dxj], d->h_dx_j, H * 8);
   memcpy(&host[o_dxh], d->h_dx_h, H * 8);
   if (d->h_heightmap) memcpy(&host[o_hmap], d->h_heightmap, (size_t)H * W * 8);
-  if (d->h_smmz) memcpy(&host[o_smmz], d->h_smmz, (size_t)H * nw * 8);
+  if (d->h_smmz) {
+    memcpy(&host[o_smmz], d->h_smmz, (size_t)H * nw * 8);
+    double* sw = reinterpret_cast<double*>(&host[o_smmzw]);
+    const double inv = 1.0 / W;
+    for (size_t e = 0; e < (size_t)H * nw; ++e) sw[e] = d->h_smmz[e] * inv;
+  }
   double* tw = reinterpret_cast<double*>(&host[o_tw]);
   for (int m = 0; m < W; ++m) {  // exp(-2 pi i m / W), evaluated in long double
     const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)W;
@@ -143,7 +188,16 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   g->d.rdsig = (const double*)(b + o_rdsig);
   g->d.sigkap = (const double*)(b + o_sigkap);
   g->d.kperm = (const int*)(b + o_kperm);
+  g->d.smmzw = (const double*)(b + o_smmzw);
   g->d.rdy = 1.0 / d->dy;
+  for (int k = 0; k < L && k < GCM_MAXLC; ++k) {
+    g->d.c_sig[k] = d->h_sig[k];
+    g->d.c_dsig[k] = d->h_dsig[k];
+    g->d.c_sigb[k] = d->h_sigb[k];
+    g->d.c_sigt[k] = d->h_sigt[k];
+    g->d.c_rdsig[k] = 1.0 / d->h_dsig[k];
+    g->d.c_sigkap[k] = pow(d->h_sig[k], GCM_KAPPA);
+  }
   *out = g;
   return GCM_OK;
 }

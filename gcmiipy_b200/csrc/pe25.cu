@@ -394,8 +394,8 @@ static int pe25_check_state(const gcm_state* s) {
 // pe25_fast.cu
 bool gcm_pe25_fast_supported(const gcm_geom* g);
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
-                            double dt, int nbatch, double* spu, double* sd, double* phi, double* rho, double* pgf,
-                            double* pn, void* stream);
+                            double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
+                            void* stream);
 
 static int g_pe25_path = 0;  // 0 = fused ALU-lean kernels when the geometry allows, 1 = always the 4-kernel path
 
@@ -408,7 +408,7 @@ extern "C" int gcm_pe25_select_path(int path) {
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
   if (g_pe25_path == 0 && gcm_pe25_fast_supported(g))
-    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.rho, w.pgf, w.pn, stream);
+    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, stream);  // fv in the phi slot
   const GcmGeomDev& d = g->d;
   const int H = d.H, W = d.W, L = d.L;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;  // member strides of the caller's arrays

@@ -1,25 +1,31 @@
-// pe25_fast.cu -- ALU-lean, fused kernels of the 2.5-D half step (reference dynamics.py:183-227).
+// pe25_fast.cu -- fused kernels of the 2.5-D half step (reference dynamics.py:183-227).
 //
-// The step is bound by the FP64 pipe and by HBM about equally, so this path cuts both:
-//   * 2 launches per half step instead of 4:
-//       R  pe25f_row_kernel     one CTA per latitude row, all layers: spu = filter(su iph(sp)) with an in-place
-//                               shared-memory FFT (fft_inplace.h), then the column work of that row straight
-//                               from shared memory (conv, pit, sd, p_n; hydrostatic phi, rho), then
-//                               pgf = filter(pgfu + phiu) through the same buffer      (dynamics.py:186-202)
-//       U  pe25f_update_kernel  one thread per column, k loop with the vertical neighbours and interface
-//                               fluxes carried in registers: momentum, tracer update     (dynamics.py:197-222)
-//   * divides by metric terms become multiplications by resident reciprocals (1/dx_j, 1/dx_h, 1/dy, 1/dsig),
-//     the three divides by p_n averages are done once per column instead of once per cell, and when ptop = 0
-//     (the reference's setting, geometry.py:147) the Exner factor ((sig p + ptop)/P0)^kappa factorises into
-//     sig^kappa (resident table) x (p/P0)^kappa: one pow per column instead of one per cell.
+// Two launches per half step, split at the only data dependences that span a whole latitude row (the zonal FFT
+// filter, low_pass.py:41-78) -- everything else is recomputed where it is needed instead of stored:
+//
+//   R  pe25f_row_kernel     one CTA per block of RB latitude rows of one member, all layers.  Several CTAs share an
+//                           SM (small FFT buffer), so one CTA's barriers and loads hide behind another's math.
+//        FA   spu = arakawa_1977(su * iph(sp)): NBAT layer pairs per pass through a shared-memory buffer,
+//             in-place mixed-radix FFT (fft_inplace.h), spu -> HBM                              (dynamics.py:187-189)
+//        P2a  one thread per column: spu back from L1/L2; conv, pit, sd, p_n                   (:35-46, :193-194)
+//        P2b  one warp per 31 columns, marching south over the rows: hydrostatic phi and rho by column
+//             (:111-142, :150-152), east neighbour by warp shuffle, north row kept in registers:
+//             pgfu + phiu -> HBM (unfiltered, :159-165), fv = phiv + pgv -> HBM (:160, :167-169)
+//        FB   pgf = arakawa_1977(pgfu + phiu), in place in HBM through the same buffer          (:202)
+//   U  pe25f_update_kernel  one thread per column of a 32 x 4 (i x j) tile, k loop with the vertical neighbours and
+//        interface fluxes carried in registers: momentum and tracer update                     (:197-222)
+//
+// Work fields in HBM between R and U: spu, sd, pgf, fv (3-D) and p_n (2-D).  phi and rho never leave the SM.
+//   * divides by metric terms are multiplications by resident reciprocals (1/dx_j, 1/dx_h, 1/dy, 1/dsig), the
+//     divides by p_n averages are done once per column, the 1/W of the inverse transform is folded into the
+//     filter table, and when ptop = 0 (the reference's setting, geometry.py:147) the Exner factor
+//     ((sig p + ptop)/P0)^kappa factorises into sig^kappa (resident) x (p/P0)^kappa: one pow per column;
+//   * per-layer tables ride in the kernel parameters (constant bank), indices are 32-bit.
 // FMA contraction is on for this file.  Results agree with the reference within the stated fp64 tolerance
 // (tests/test_parity.py); the bit-exact operator kernels stay in pe25.cu.
 #include "fft_inplace.h"
 #include "gcm_common.h"
 #include "prof.h"
-
-#define IDX3(k, j, i) (((size_t)(k) * H + (size_t)(j)) * W + (size_t)(i))
-#define IDX2(j, i) ((size_t)(j) * W + (size_t)(i))
 
 struct PfConst {
   const double *p, *u, *v, *t, *q;
@@ -28,150 +34,202 @@ struct PfMut {
   double *p, *u, *v, *t, *q;
 };
 struct PfWork {
-  double *spu, *sd, *phi, *rho, *pgf, *pn;
+  double *spu, *sd, *pgf, *fv, *pn;
 };
 
+// hydrostatic geopotential at layer centres and density of one column (dynamics.py:111-142, :150-152);
+// t points at layer 0 of the column, ks = layer stride
+template <int L, bool PTOP0>
+__device__ __forceinline__ void pf_column(const GcmGeomDev& g, double sp_c, double hm, const double* __restrict__ t,
+                                          int ks, double* phi, double* rho) {
+  const double ptop = g.ptop;
+  double pk_col = 0.0;
+  if (PTOP0) pk_col = pow(sp_c * (1.0 / GCM_P0), GCM_KAPPA);
+  double tk = t[0];
+  double pk = PTOP0 ? g.c_sigkap[0] * pk_col : pow((g.c_sig[0] * sp_c + ptop) / GCM_P0, GCM_KAPPA);
+  const double t0 = tk, pk0 = pk;
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    double t_n = t0, pk_n = pk0;  // k + 1 wraps to layer 0 (coordinates_3d.py:55); sigt[L-1] = 0 kills it
+    if (k + 1 < L) {
+      t_n = t[(k + 1) * ks];
+      pk_n = PTOP0 ? g.c_sigkap[k + 1] * pk_col : pow((g.c_sig[k + 1] * sp_c + ptop) / GCM_P0, GCM_KAPPA);
+    }
+    const double tp = sp_c * g.c_sig[k] + ptop;
+    const double rtt = GCM_RD * (tk * pk);                      // Rd * T
+    const double r = tp / rtt;                                  // rho (dynamics.py:152)
+    const double spa = PTOP0 ? rtt : (g.c_sig[k] * sp_c) / r;   // sig p / rho
+    const double stp = GCM_CP * ((tk + t_n) * 0.5) * (pk - pk_n);
+    sum += spa * g.c_dsig[k] - g.c_sigt[k] * stp;
+    rho[k] = r;
+    if (k + 1 < L) phi[k + 1] = stp;
+    tk = t_n;
+    pk = pk_n;
+  }
+  double run = sum + hm * GCM_G;
+  phi[0] = run;
+#pragma unroll
+  for (int k = 1; k < L; ++k) {
+    run += phi[k];
+    phi[k] = run;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
-// R: one CTA per (row, member)
+// R: one CTA per (block of RB rows, member)
 // ---------------------------------------------------------------------------------------------------
 template <int L, bool PTOP0>
-__global__ void __launch_bounds__(512, 1)
-pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, int ja, size_t bstride2,
-                 size_t bstride3) {
+__global__ void __launch_bounds__(256, 2)
+pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, int ja, int jend, int RB,
+                 int RG, int NBAT, unsigned magicW, size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double2, z);
   constexpr int NP = (L + 1) / 2;
-  const int H = g.H, W = g.W;
+  const int H = g.H, W = g.W, plane = H * W;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int j = ja + blockIdx.x;
+  const int j0 = ja + blockIdx.x * RB;
+  const int rb = jend - j0 < RB ? jend - j0 : RB;  // rows of this block
+  const int npr = rb * NP;                         // packed rows (layer pairs) of this block
   const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
-  const double* sp = star.p + o2;
-  const double* su = star.u + o3;
-  const double* sv = star.v + o3;
-  const double* st = star.t + o3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ su = star.u + o3;
+  const double* __restrict__ sv = star.v + o3;
+  const double* __restrict__ st = star.t + o3;
   p += o2;
-  double* spu = w.spu + o3;
-  double* sd = w.sd + o3;
-  double* phi = w.phi + o3;
-  double* rho = w.rho + o3;
+  double* spu = w.spu + o3;  // written, then read back by other threads of the block: no __restrict__
   double* pgf = w.pgf + o3;
-  double* pn = w.pn + o2;
-  const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
-  const double* sprow = sp + IDX2(j, 0);
-  const double* table = g.smmz + (size_t)j * (W / 2 + 1);
-  const double inv = W == 1 ? 1.0 : 1.0 / W;
-  const double rdxj = g.rdx_j[j], rdy = g.rdy;
+  double* __restrict__ sd = w.sd + o3;
+  double* __restrict__ fv = w.fv + o3;
+  double* __restrict__ pn = w.pn + o2;
+  const int nw = W / 2 + 1;
+  const double* table = g.smmzw + (size_t)j0 * nw;
+  const double rdy = g.rdy;
 
-  // 1. spu_orig = su * iph(sp), two layers per complex row  (dynamics.py:187)
-  for (int e = tid; e < NP * W; e += nthr) {
-    const int pr = e / W, i = e - pr * W;
-    const int k0 = 2 * pr, k1 = k0 + 1;
-    const double ph = (sprow[i] + sprow[gcm_ip(i, W)]) * 0.5;
-    const double x0 = su[IDX3(k0, j, i)] * ph;
-    const double x1 = k1 < L ? su[IDX3(k1, j, i)] * ph : 0.0;
-    z[e] = make_double2(x0, x1);
+  // FA. spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189), NBAT packed rows (two layers each) per pass
+  for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
+    const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
+    for (int e = tid; e < nb * W; e += nthr) {
+      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
+      const int row = (j0 + r) * W;
+      const double ph = (sp[row + i] + sp[row + gcm_ip(i, W)]) * 0.5;
+      const double x0 = su[k0 * plane + row + i] * ph;
+      const double x1 = k1 < L ? su[k1 * plane + row + i] * ph : 0.0;
+      z[e] = make_double2(x0, x1);
+    }
+    __syncthreads();
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tw, g.kperm, table, nw, pr0, tid, nthr);
+    for (int e = tid; e < nb * W; e += nthr) {
+      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
+      const int c2 = (j0 + r) * W + i;
+      const double2 v = z[e];
+      spu[k0 * plane + c2] = v.x;
+      if (k1 < L) spu[k1 * plane + c2] = v.y;
+    }
+    __syncthreads();  // the buffer is free for the next pass; spu of this block is visible to the block
   }
-  __syncthreads();
-  gcm_filter_rows_inplace(z, NP, g.plan, g.tw, g.kperm, table, tid, nthr);  // dynamics.py:189
-  for (int e = tid; e < NP * W; e += nthr) {
-    const int pr = e / W, i = e - pr * W;
-    const int k0 = 2 * pr, k1 = k0 + 1;
-    double2 v = z[e];
-    v.x *= inv;
-    v.y *= inv;
-    z[e] = v;
-    spu[IDX3(k0, j, i)] = v.x;
-    if (k1 < L) spu[IDX3(k1, j, i)] = v.y;
-  }
-  __syncthreads();
 
-  // 2. column work of this row: aflux (dynamics.py:35-46), p_n (:194), geopotential and rho (:111-142, :150-152)
-  for (int i = tid; i < W; i += nthr) {
-    const int im = gcm_im(i, W);
-    const double sp_c = sprow[i];
-    const double pjh = (sp_c + sp[IDX2(jp, i)]) * 0.5, pjh_m = (sp[IDX2(jm, i)] + sp_c) * 0.5;
+  // P2a. per column: aflux (dynamics.py:35-46), p_n (:194); spu comes back from L1/L2
+  for (int e = tid; e < rb * W; e += nthr) {
+    const int r = gcm_fastdiv(e, magicW), i = e - r * W;
+    const int j = j0 + r;
+    const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+    const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
+    const double sp_c = sp[c2];
+    const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
+    const double rdxj = g.rdx_j[j];
     double conv[L];
     double pit = 0.0;
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-      const double2 a = z[(k >> 1) * W + i], b = z[(k >> 1) * W + im];
-      const double pu_c = (k & 1) ? a.y : a.x, pu_im = (k & 1) ? b.y : b.x;
-      const double pv_c = sv[IDX3(k, j, i)] * pjh, pv_jm = sv[IDX3(k, jm, i)] * pjh_m;
-      conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.dsig[k];
+      const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
+      const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
+      conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
       pit += conv[k];
     }
     double acc = 0.0;
 #pragma unroll
     for (int k = L - 1; k >= 0; --k) {
       acc += conv[k];
-      sd[IDX3(k, j, i)] = k == 0 ? 0.0 : acc - pit * g.sigb[k];  // dynamics.py:42-44
+      sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
     }
-    pn[IDX2(j, i)] = p[IDX2(j, i)] - pit * dt;
-
-    // hydrostatic geopotential at layer centres
-    const double ptop = g.ptop;
-    double pk_col = 0.0;
-    if (PTOP0) pk_col = pow(sp_c / GCM_P0, GCM_KAPPA);
-    double tk = st[IDX3(0, j, i)];
-    double pk = PTOP0 ? g.sigkap[0] * pk_col : pow((g.sig[0] * sp_c + ptop) / GCM_P0, GCM_KAPPA);
-    const double t0 = tk, pk0 = pk;
-    double stp[L];
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-      double t_n = t0, pk_n = pk0;  // k + 1 wraps to layer 0 (coordinates_3d.py:55); sigt[L-1] = 0 kills it
-      if (k + 1 < L) {
-        t_n = st[IDX3(k + 1, j, i)];
-        pk_n = PTOP0 ? g.sigkap[k + 1] * pk_col : pow((g.sig[k + 1] * sp_c + ptop) / GCM_P0, GCM_KAPPA);
-      }
-      const double tp = sp_c * g.sig[k] + ptop;
-      const double rtt = GCM_RD * (tk * pk);  // Rd * T
-      const double r = tp / rtt;              // rho (dynamics.py:152)
-      const double spa = PTOP0 ? rtt : (g.sig[k] * sp_c) / r;  // sig p / rho
-      stp[k] = GCM_CP * ((tk + t_n) * 0.5) * (pk - pk_n);
-      sum += spa * g.dsig[k] - g.sigt[k] * stp[k];
-      rho[IDX3(k, j, i)] = r;
-      tk = t_n;
-      pk = pk_n;
-    }
-    double run = sum + g.hmap[IDX2(j, i)] * GCM_G;
-    phi[IDX3(0, j, i)] = run;
-#pragma unroll
-    for (int k = 1; k < L; ++k) {
-      run += stp[k - 1];
-      phi[IDX3(k, j, i)] = run;
-    }
+    pn[c2] = p[c2] - pit * dt;
   }
-  __syncthreads();  // z is free again; phi and rho of this row are visible to the block
 
-  // 3. pgfu + phiu (dynamics.py:159, :162-165) into the FFT buffer, filter (:202), write
-  for (int e = tid; e < NP * W; e += nthr) {
-    const int pr = e / W, i = e - pr * W;
-    const int ip = gcm_ip(i, W);
-    const int k0 = 2 * pr, k1 = k0 + 1;
-    const double p_c = sprow[i], p_ip = sprow[ip];
-    const double psum = p_c + p_ip, gradp = (p_ip - p_c) * rdxj;
-    const double a_u = psum * gradp;       // (p_c + p_ip) dp/dx
-    const double b_u = psum * 0.5 * rdxj;  // iph(p) / dx
-    double x[2] = {0.0, 0.0};
+  // P2b. hydrostatic columns; a warp owns 31 columns (+ lane 31 = east neighbour of lane 30) and marches south
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int nchunk = (W + 30) / 31, ngrp = (rb + RG - 1) / RG;
+    for (int task = warp; task < nchunk * ngrp; task += nwarp) {
+      const int grp = task / nchunk, c = task - grp * nchunk;
+      int i = c * 31 + lane;
+      const bool own = lane < 31 && i < W;
+      i = i % W;
+      const int r0 = grp * RG, r1 = r0 + RG < rb ? r0 + RG : rb;  // rows [r0, r1), row r1 only as the south neighbour
+      double phi_n[L], rho_n[L];  // the row to the north of the one being computed
+      double sp_n = 0.0;
+#pragma unroll 1
+      for (int r = r0; r <= r1; ++r) {
+        const int j = gcm_row(j0 + r - 1, 1, H, g.wrap_j);
+        const int c2 = j * W + i;
+        const double sp_c = sp[c2];
+        double phi[L], rho[L];
+        pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
+        if (r < r1) {  // pgfu + phiu of row j (dynamics.py:159, :162-165), east neighbour from lane + 1
+          const double sp_e = __shfl_down_sync(0xffffffffu, sp_c, 1);
+          const double rdxj = g.rdx_j[j];
+          const double psum = sp_c + sp_e, gradp = (sp_e - sp_c) * rdxj;
+          const double a_u = psum * gradp;       // (p_c + p_e) dp/dx
+          const double b_u = psum * 0.5 * rdxj;  // iph(p) / dx
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int k = s ? k1 : k0;
-      if (k < L) {
-        const size_t c = IDX3(k, j, i), cp = IDX3(k, j, ip);
-        const double pgu = g.sig[k] * a_u / (rho[c] + rho[cp]);
-        x[s] = pgu + b_u * (phi[cp] - phi[c]);
+          for (int k = 0; k < L; ++k) {
+            const double phi_e = __shfl_down_sync(0xffffffffu, phi[k], 1);
+            const double rho_e = __shfl_down_sync(0xffffffffu, rho[k], 1);
+            const double x = g.c_sig[k] * a_u / (rho[k] + rho_e) + b_u * (phi_e - phi[k]);
+            if (own) pgf[k * plane + c2] = x;  // unfiltered, filtered in place below
+          }
+        }
+        if (r > r0 && own) {  // fv = phiv + pgv of the row to the north (dynamics.py:160, :167-169)
+          const int cn = (j0 + r - 1) * W + i;
+          const double psum = sp_n + sp_c;
+          const double a_v = psum * ((sp_c - sp_n) * rdy);  // (p_c + p_jp) dp/dy
+          const double b_v = psum * 0.5 * rdy;              // jph(p) / dy
+#pragma unroll
+          for (int k = 0; k < L; ++k)
+            fv[k * plane + cn] = g.c_sig[k] * a_v / (rho_n[k] + rho[k]) + b_v * (phi[k] - phi_n[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+          phi_n[k] = phi[k];
+          rho_n[k] = rho[k];
+        }
+        sp_n = sp_c;
       }
     }
-    z[e] = make_double2(x[0], x[1]);
   }
-  __syncthreads();
-  gcm_filter_rows_inplace(z, NP, g.plan, g.tw, g.kperm, table, tid, nthr);
-  for (int e = tid; e < NP * W; e += nthr) {
-    const int pr = e / W, i = e - pr * W;
-    const int k0 = 2 * pr, k1 = k0 + 1;
-    const double2 v = z[e];
-    pgf[IDX3(k0, j, i)] = v.x * inv;
-    if (k1 < L) pgf[IDX3(k1, j, i)] = v.y * inv;
+  __syncthreads();  // pgfu + phiu of this block is visible to the block
+
+  // FB. pgf = arakawa_1977(pgfu + phiu) (dynamics.py:202), in place in HBM through the same buffer
+  for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
+    const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
+    for (int e = tid; e < nb * W; e += nthr) {
+      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
+      const int c2 = (j0 + r) * W + i;
+      z[e] = make_double2(pgf[k0 * plane + c2], k1 < L ? pgf[k1 * plane + c2] : 0.0);
+    }
+    __syncthreads();
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tw, g.kperm, table, nw, pr0, tid, nthr);
+    for (int e = tid; e < nb * W; e += nthr) {
+      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
+      const int c2 = (j0 + r) * W + i;
+      const double2 v = z[e];
+      pgf[k0 * plane + c2] = v.x;
+      if (k1 < L) pgf[k1 * plane + c2] = v.y;
+    }
+    __syncthreads();
   }
 }
 
@@ -179,90 +237,91 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
 // U: one thread per column, k loop
 // ---------------------------------------------------------------------------------------------------
 template <int L, int MINB>
-__global__ void __launch_bounds__(160, MINB)
-pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, int ja, size_t bstride2,
-                    size_t bstride3) {
-  const int H = g.H, W = g.W;
+__global__ void __launch_bounds__(128, MINB)
+pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, int ja, int jend,
+                    size_t bstride2, size_t bstride3) {
+  const int H = g.H, W = g.W, plane = H * W;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= W) return;
-  const int j = ja + blockIdx.y;
+  const int j = ja + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= W || j >= jend) return;
   const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
-  const double* p = base.p + o2;
-  const double* u = base.u + o3;
-  const double* v = base.v + o3;
-  const double* t = base.t + o3;
-  const double* q = base.q + o3;
-  const double* sp = star.p + o2;
-  const double* su = star.u + o3;
-  const double* sv = star.v + o3;
-  const double* st = star.t + o3;
-  const double* sq = star.q + o3;
-  const double* spu = w.spu + o3;
-  const double* sd = w.sd + o3;
-  const double* phi = w.phi + o3;
-  const double* rho = w.rho + o3;
-  const double* pgf = w.pgf + o3;
-  const double* pn = w.pn + o2;
+  const double* __restrict__ p = base.p + o2;
+  const double* __restrict__ u = base.u + o3;
+  const double* __restrict__ v = base.v + o3;
+  const double* __restrict__ t = base.t + o3;
+  const double* __restrict__ q = base.q + o3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ su = star.u + o3;
+  const double* __restrict__ sv = star.v + o3;
+  const double* __restrict__ st = star.t + o3;
+  const double* __restrict__ sq = star.q + o3;
+  const double* __restrict__ spu = w.spu + o3;
+  const double* __restrict__ sd = w.sd + o3;
+  const double* __restrict__ pgf = w.pgf + o3;
+  const double* __restrict__ fv = w.fv + o3;
+  const double* __restrict__ pn = w.pn + o2;
+  double* __restrict__ ou = out.u + o3;
+  double* __restrict__ ov = out.v + o3;
+  double* __restrict__ ot = out.t + o3;
+  double* __restrict__ oq = out.q + o3;
 
   const int wrap = g.wrap_j;
   const int jm = gcm_row(j, -1, H, wrap), jp = gcm_row(j, 1, H, wrap), jpp = gcm_row(jp, 1, H, wrap);
   const int im = gcm_im(i, W), ip = gcm_ip(i, W);
   const double rdxj = g.rdx_j[j], rdxh = g.rdx_h[j], rdy = g.rdy;
+  // element offsets of the seven stencil columns within a layer; they advance by one plane per layer
+  int e_c = j * W + i, e_im = j * W + im, e_ip = j * W + ip, e_jp = jp * W + i, e_jm = jm * W + i,
+      e_jp_im = jp * W + im, e_jm_ip = jm * W + ip;
 
   // per-column (2-D) factors
-  const double p_c = p[IDX2(j, i)], p_ip = p[IDX2(j, ip)], p_jp = p[IDX2(jp, i)];
-  const double pn_c = pn[IDX2(j, i)], pn_ip = pn[IDX2(j, ip)], pn_jp = pn[IDX2(jp, i)];
-  const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                 // calc_pu / calc_pv
+  const double p_c = p[e_c], p_ip = p[e_ip], p_jp = p[e_jp];
+  const double pn_c = pn[e_c], pn_ip = pn[e_ip], pn_jp = pn[e_jp];
+  const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                    // calc_pu / calc_pv
   const double r_pnu = 1.0 / ((pn_c + pn_ip) * 0.5), r_pnv = 1.0 / ((pn_c + pn_jp) * 0.5);  // un_pu / un_pv
   const double r_pn = 1.0 / pn_c;
-  const double sp_c = sp[IDX2(j, i)], sp_ip = sp[IDX2(j, ip)], sp_jp = sp[IDX2(jp, i)], sp_jm = sp[IDX2(jm, i)];
-  const double a_c = (sp_c + sp_jp) * 0.5;                                  // jph(sp) at (j, i)
-  const double a_ip = (sp_ip + sp[IDX2(jp, ip)]) * 0.5;                    // (j, i+1)
-  const double a_jm = (sp_jm + sp_c) * 0.5;                                // (j-1, i)
-  const double a_jm_ip = (sp[IDX2(jm, ip)] + sp_ip) * 0.5;                 // (j-1, i+1)
-  const double a_jp = (sp_jp + sp[IDX2(jpp, i)]) * 0.5;                    // (j+1, i)
-  const double a_v = (sp_c + sp_jp) * ((sp_jp - sp_c) * rdy);              // (p_c + p_jp) dp/dy
-  const double b_v = a_c * rdy;                                            // jph(p) / dy
+  const double sp_c = sp[e_c], sp_ip = sp[e_ip], sp_jp = sp[e_jp], sp_jm = sp[e_jm];
+  const double a_c = (sp_c + sp_jp) * 0.5;                   // jph(sp) at (j, i)
+  const double a_ip = (sp_ip + sp[jp * W + ip]) * 0.5;       // (j, i+1)
+  const double a_jm = (sp_jm + sp_c) * 0.5;                  // (j-1, i)
+  const double a_jm_ip = (sp[e_jm_ip] + sp_ip) * 0.5;        // (j-1, i+1)
+  const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;       // (j+1, i)
   const bool zero_v = j == g.zero_v_row;
 
   // vertical neighbours and interface fluxes carried in registers (advec_sig, dynamics.py:49-52)
-  double u_k = su[IDX3(0, j, i)], v_k = sv[IDX3(0, j, i)], t_k = st[IDX3(0, j, i)], q_k = sq[IDX3(0, j, i)];
-  double sd_c = sd[IDX3(0, j, i)], sd_ip = sd[IDX3(0, j, ip)], sd_jp = sd[IDX3(0, jp, i)];
+  double u_k = su[e_c], v_k = sv[e_c], t_k = st[e_c], q_k = sq[e_c];
+  double sd_c = sd[e_c], sd_ip = sd[e_ip], sd_jp = sd[e_jp];
   // flux through the bottom of layer 0 pairs layer 0 with layer L-1 (np.roll) times sd[0] = 0
-  double fu, fv, ft, fq;
+  double fu, fv_, ft, fq;
   {
-    const size_t c = IDX3(L - 1, j, i);
-    fu = (u_k + su[c]) * 0.5 * ((sd_c + sd_ip) * 0.5);
-    fv = (v_k + sv[c]) * 0.5 * ((sd_c + sd_jp) * 0.5);
-    ft = (t_k + st[c]) * 0.5 * sd_c;
-    fq = (q_k + sq[c]) * 0.5 * sd_c;
+    const int top = (L - 1) * plane + e_c;
+    fu = (u_k + su[top]) * 0.5 * ((sd_c + sd_ip) * 0.5);
+    fv_ = (v_k + sv[top]) * 0.5 * ((sd_c + sd_jp) * 0.5);
+    ft = (t_k + st[top]) * 0.5 * sd_c;
+    fq = (q_k + sq[top]) * 0.5 * sd_c;
   }
-  const double fu0 = fu, fv0 = fv, ft0 = ft, fq0 = fq;
+  const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
-    const size_t c = IDX3(k, j, i), c_im = IDX3(k, j, im), c_ip = IDX3(k, j, ip), c_jp = IDX3(k, jp, i),
-                 c_jm = IDX3(k, jm, i);
     // fluxes through the top of layer k
     double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
     double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
     if (k + 1 < L) {
-      const size_t cn = IDX3(k + 1, j, i);
-      u_kp = su[cn]; v_kp = sv[cn]; t_kp = st[cn]; q_kp = sq[cn];
-      sd_c = sd[cn]; sd_ip = sd[IDX3(k + 1, j, ip)]; sd_jp = sd[IDX3(k + 1, jp, i)];
+      u_kp = su[e_c + plane]; v_kp = sv[e_c + plane]; t_kp = st[e_c + plane]; q_kp = sq[e_c + plane];
+      sd_c = sd[e_c + plane]; sd_ip = sd[e_ip + plane]; sd_jp = sd[e_jp + plane];
       fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
       fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
       ft_n = (t_kp + t_k) * 0.5 * sd_c;
       fq_n = (q_kp + q_k) * 0.5 * sd_c;
     }
-    const double rds = g.rdsig[k];
-    const double dus = -((fu - fu_n) * rds), dvs = -((fv - fv_n) * rds);
-    const double ads_t = -((ft - ft_n) * rds), ads_q = -((fq - fq_n) * rds);
+    const double rds = g.c_rdsig[k];
+    const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;      // -(F_k - F_k+1) / dsig
+    const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
 
     // horizontal neighbours
-    const double u_im = su[c_im], u_ip = su[c_ip], u_jp = su[c_jp], u_jm = su[c_jm];
-    const double v_im = sv[c_im], v_ip = sv[c_ip], v_jp = sv[c_jp], v_jm = sv[c_jm], v_jm_ip = sv[IDX3(k, jm, ip)];
-    const double pu_c = spu[c], pu_im = spu[c_im], pu_ip = spu[c_ip], pu_jp = spu[c_jp], pu_jp_im = spu[IDX3(k, jp, im)];
+    const double u_im = su[e_im], u_ip = su[e_ip], u_jp = su[e_jp], u_jm = su[e_jm];
+    const double v_im = sv[e_im], v_ip = sv[e_ip], v_jp = sv[e_jp], v_jm = sv[e_jm], v_jm_ip = sv[e_jm_ip];
+    const double pu_c = spu[e_c], pu_im = spu[e_im], pu_ip = spu[e_ip], pu_jp = spu[e_jp], pu_jp_im = spu[e_jp_im];
     const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
                  pv_jp = v_jp * a_jp;
 
@@ -274,34 +333,31 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
     const double pvup = (v_k + v_ip) * (pu_c + pu_jp), pvum = (v_im + v_k) * (pu_im + pu_jp_im);
     const double dvt = ((pvvm - pvvp) * rdy + (pvum - pvup) * rdxh) * 0.25;
 
-    // pressure-gradient force, v direction (dynamics.py:160, :167-169)
-    const double phiv = b_v * (phi[c_jp] - phi[c]);
-    const double pgv = g.sig[k] * a_v / (rho[c] + rho[c_jp]);
-
-    const double pu_n = u[c] * pu_fac - (dut + dus + pgf[c]) * dt;           // dynamics.py:206
-    const double pv_n = v[c] * pv_fac - (dvt + dvs + phiv + pgv) * dt;       // dynamics.py:207
-    out.u[o3 + c] = pu_n * r_pnu;
+    const double pu_n = u[e_c] * pu_fac - (dut + dus + pgf[e_c]) * dt;   // dynamics.py:206
+    const double pv_n = v[e_c] * pv_fac - (dvt + dvs + fv[e_c]) * dt;    // dynamics.py:207
+    ou[e_c] = pu_n * r_pnu;
     double v_n = pv_n * r_pnv;
     if (zero_v) v_n *= 0.0;  // dynamics.py:222
-    out.v[o3 + c] = v_n;
+    ov[e_c] = v_n;
 
     // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
     {
-      const double x_ip = st[c_ip], x_im = st[c_im], x_jp = st[c_jp], x_jm = st[c_jm];
+      const double x_ip = st[e_ip], x_im = st[e_im], x_jp = st[e_jp], x_jm = st[e_jm];
       const double adv = ((pu_c * (t_k + x_ip) - pu_im * (x_im + t_k)) * rdxj +
                           (pv_c * (t_k + x_jp) - pv_jm * (x_jm + t_k)) * rdy) * 0.5;
-      out.t[o3 + c] = (t[c] * p_c - (adv + ads_t) * dt) * r_pn;
+      ot[e_c] = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
     }
     {
-      const double x_ip = sq[c_ip], x_im = sq[c_im], x_jp = sq[c_jp], x_jm = sq[c_jm];
+      const double x_ip = sq[e_ip], x_im = sq[e_im], x_jp = sq[e_jp], x_jm = sq[e_jm];
       const double adv = ((pu_c * (q_k + x_ip) - pu_im * (x_im + q_k)) * rdxj +
                           (pv_c * (q_k + x_jp) - pv_jm * (x_jm + q_k)) * rdy) * 0.5;
-      out.q[o3 + c] = (q[c] * p_c - (adv + ads_q) * dt) * r_pn;
+      oq[e_c] = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
     }
-    fu = fu_n; fv = fv_n; ft = ft_n; fq = fq_n;
+    fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
     u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
+    e_c += plane; e_im += plane; e_ip += plane; e_jp += plane; e_jm += plane; e_jp_im += plane; e_jm_ip += plane;
   }
-  out.p[o2 + IDX2(j, i)] = pn_c;
+  out.p[o2 + j * W + i] = pn_c;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -309,21 +365,23 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 // ---------------------------------------------------------------------------------------------------
 int g_gcm_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-// tuning knobs of the fast path (bench.py --knob i=v): 0 = min resident blocks of the update kernel (1..4),
-// 1 = threads per block of the update kernel (32..160, 0 = automatic), 2 = threads of the row kernel (0 = auto)
+// tuning knobs of the fast path (bench.py --knob i=v; 0 = automatic):
+//   0  min resident blocks per SM of the update kernel (1..4: registers per thread vs resident warps)
+//   1  update-kernel tile width in i (threads.x, multiple of 32)      2  threads of the row kernel
+//   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the row kernel (RB)
+//   5  rows per warp task of the row kernel's column phase (RG)      6  packed rows per FFT pass (NBAT)
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
   return GCM_OK;
 }
 
-static size_t pf_row_smem(int W, int L) { return (size_t)((L + 1) / 2) * W * sizeof(double2); }
-
 bool gcm_pe25_fast_supported(const gcm_geom* g) {
   const GcmGeomDev& d = g->d;
   if (d.L != 9 && d.L != 3) return false;
-  if (!gcm_plan_inplace_ok(d.plan)) return false;
-  return pf_row_smem(d.W, d.L) <= 200 * 1024;
+  if (d.W < 2 || !gcm_plan_inplace_ok(d.plan)) return false;
+  if ((double)d.L * d.H * d.W >= 2147483648.0) return false;  // 32-bit element offsets within a member
+  return (size_t)d.W * sizeof(double2) <= 200 * 1024;
 }
 
 template <int L>
@@ -334,15 +392,28 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;
   const int ja = d.row_lo, nrows = d.row_hi - d.row_lo;
   const int nrows_ext = d.wrap_j ? nrows : nrows + 1;  // band: also the first halo row to the south
-  const size_t smem = pf_row_smem(W, L);
-  const int work = ((L + 1) / 2) * W;
-  int tr = (work / 4 + 31) / 32 * 32;  // about four elements of the FFT buffer per thread
-  tr = tr < 64 ? 64 : (tr > 512 ? 512 : tr);
-  if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2];
+  const size_t prsmem = (size_t)W * sizeof(double2);  // one packed row (two layers of one latitude)
+  constexpr int NP = (L + 1) / 2;
+  // rows per CTA: enough for about 24 KB of packed rows, but keep at least two waves of CTAs
+  int RB = (int)((24 * 1024) / (prsmem * NP));
+  RB = RB < 1 ? 1 : (RB > 8 ? 8 : RB);
+  while (RB > 1 && (size_t)((nrows_ext + RB - 1) / RB) * nbatch < 296) --RB;
+  if (g_gcm_knob[4] > 0) RB = g_gcm_knob[4];
+  int RG = (RB + 3) / 4;
+  if (g_gcm_knob[5] > 0) RG = g_gcm_knob[5];
+  // packed rows per FFT pass: up to 48 KB of shared memory
+  int NBAT = (int)((48 * 1024) / prsmem);
+  if (g_gcm_knob[6] > 0) NBAT = g_gcm_knob[6];
+  NBAT = NBAT < 1 ? 1 : (NBAT > RB * NP ? RB * NP : NBAT);
+  const size_t smem = NBAT * prsmem;
+  int tr = (NBAT * W / 24 + 31) / 32 * 32;
+  tr = tr < 64 ? 64 : (tr > 256 ? 256 : tr);
+  if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2] > 256 ? 256 : g_gcm_knob[2];
   const PfConst cb{base->p, base->u, base->v, base->t, base->q};
   const PfConst cs{star->p, star->u, star->v, star->t, star->q};
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
+  const unsigned magicW = gcm_magic((unsigned)W);
 #ifndef GCM_EMU
   if (smem > 48 * 1024) {
     GCM_CUDA(cudaFuncSetAttribute(pe25f_row_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -351,27 +422,27 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
 #endif
   {
     GcmProfScope ps(GCM_K_ROW, stream);
+    const dim3 grid((nrows_ext + RB - 1) / RB, nbatch);
     if (ptop0)
-      GCM_LAUNCH((pe25f_row_kernel<L, true>), dim3(nrows_ext, nbatch), dim3(tr), smem, stream, d, base->p, cs, w, dt, ja,
-                 b2, b3);
+      GCM_LAUNCH((pe25f_row_kernel<L, true>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja, ja + nrows_ext, RB,
+                 RG, NBAT, magicW, b2, b3);
     else
-      GCM_LAUNCH((pe25f_row_kernel<L, false>), dim3(nrows_ext, nbatch), dim3(tr), smem, stream, d, base->p, cs, w, dt, ja,
-                 b2, b3);
+      GCM_LAUNCH((pe25f_row_kernel<L, false>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja, ja + nrows_ext,
+                 RB, RG, NBAT, magicW, b2, b3);
   }
   GCM_CHECK_LAUNCH();
-  int tc = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 160;
-  if (g_gcm_knob[1] > 0) {
-  } else if (W < 160) tc = (W + 31) / 32 * 32;
-  else if (W % 128 == 0) tc = 128;
-  else if (W % 96 == 0 && W % 160 != 0) tc = 96;
+  int tx = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 32;
+  int ty = g_gcm_knob[3] > 0 ? g_gcm_knob[3] : 4;
+  if (tx * ty > 128) ty = 128 / tx;
   {
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
-    const dim3 grid((W + tc - 1) / tc, nrows, nbatch);
+    const dim3 grid((W + tx - 1) / tx, (nrows + ty - 1) / ty, nbatch), block(tx, ty);
+    const int je = ja + nrows;
     switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
-      case 1: GCM_LAUNCH((pe25f_update_kernel<L, 1>), grid, dim3(tc), 0, stream, d, cb, cs, mo, w, dt, ja, b2, b3); break;
-      case 3: GCM_LAUNCH((pe25f_update_kernel<L, 3>), grid, dim3(tc), 0, stream, d, cb, cs, mo, w, dt, ja, b2, b3); break;
-      case 4: GCM_LAUNCH((pe25f_update_kernel<L, 4>), grid, dim3(tc), 0, stream, d, cb, cs, mo, w, dt, ja, b2, b3); break;
-      default: GCM_LAUNCH((pe25f_update_kernel<L, 2>), grid, dim3(tc), 0, stream, d, cb, cs, mo, w, dt, ja, b2, b3); break;
+      case 1: GCM_LAUNCH((pe25f_update_kernel<L, 1>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
+      case 3: GCM_LAUNCH((pe25f_update_kernel<L, 3>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
+      case 4: GCM_LAUNCH((pe25f_update_kernel<L, 4>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
+      default: GCM_LAUNCH((pe25f_update_kernel<L, 2>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
     }
   }
   GCM_CHECK_LAUNCH();
@@ -379,9 +450,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
 }
 
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
-                            double dt, int nbatch, double* spu, double* sd, double* phi, double* rho, double* pgf,
-                            double* pn, void* stream) {
-  const PfWork w{spu, sd, phi, rho, pgf, pn};
+                            double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
+                            void* stream) {
+  const PfWork w{spu, sd, pgf, fv, pn};
   if (g->d.L == 9) return pf_half_step<9>(g, base, star, out, dt, nbatch, w, stream);
   return pf_half_step<3>(g, base, star, out, dt, nbatch, w, stream);
 }
