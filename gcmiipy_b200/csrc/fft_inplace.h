@@ -18,30 +18,25 @@
 
 // (row, butterfly) of flat work item w without integer division (operands < 2^16, see gcm_fastdiv)
 struct GcmFftStage {
-  int N, n, stride, nbf, tstep;
+  int N, n, stride, nbf, twoff;
   unsigned magic_stride, magic_nbf;
 };
-__device__ __forceinline__ GcmFftStage gcm_fft_stage(const GcmFftPlan& plan, int s, int n) {
+__device__ __forceinline__ GcmFftStage gcm_fft_stage(const GcmFftPlan& plan, int s) {
   GcmFftStage st;
   st.N = plan.n;
-  st.n = n;
+  st.n = plan.blk[s];
   st.stride = plan.stride[s];
-  st.nbf = plan.n / plan.radix[s];
-  st.tstep = plan.n / n;
+  st.nbf = plan.nbf[s];
+  st.twoff = plan.twoff[s];
   st.magic_stride = plan.magic_stride[s];
   st.magic_nbf = plan.magic_nbf[s];
   return st;
 }
 
 // one forward DIF stage over `nrows` rows of length N (row r starts at z + r * N)
-// `table` is the multiplier row of the first latitude; packed row r of the batch uses
-// table + ((pr0 + r) / NPJ) * table_stride (NPJ packed rows per latitude, pr0 = packed rows before this batch;
-// NPJ = 0: one table for the whole batch)
-template <int R, int NPJ>
+template <int R>
 __device__ __forceinline__ void gcm_dif_stage(double2* z, const GcmFftStage st, int nrows,
-                                              const double2* __restrict__ tw, const int* __restrict__ kperm,
-                                              const double* __restrict__ table, int table_stride, int pr0, bool last,
-                                              int tid, int nthr) {
+                                              const double2* __restrict__ tw, int tid, int nthr) {
   const int stride = st.stride, N = st.N;
   const int total = st.nbf * nrows;
   for (int w = tid; w < total; w += nthr) {
@@ -53,19 +48,9 @@ __device__ __forceinline__ void gcm_dif_stage(double2* z, const GcmFftStage st, 
     for (int t = 0; t < R; ++t) x[t] = base[t * stride];
     GcmButterfly<R, -1>::run(x);
     if (q > 0) {
-      const int qt = q * st.tstep;
+      const double2* t = tw + st.twoff + q;  // lanes hold consecutive q: coalesced
 #pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&tw[qt * m]));
-    }
-    if (last) {  // stride == 1: position p = blk * n + m holds wavenumber kperm[p]
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const int k = __ldg(&kperm[blk * st.n + m]);
-        const double* trow = NPJ > 0 ? table + ((pr0 + row) / (NPJ > 0 ? NPJ : 1)) * table_stride : table;
-        const double s = __ldg(&trow[k <= N - k ? k : N - k]);
-        x[m].x *= s;
-        x[m].y *= s;
-      }
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&t[(m - 1) * stride]));
     }
 #pragma unroll
     for (int m = 0; m < R; ++m) base[m * stride] = x[m];
@@ -86,13 +71,42 @@ __device__ __forceinline__ void gcm_dit_stage(double2* z, const GcmFftStage st, 
 #pragma unroll
     for (int m = 0; m < R; ++m) x[m] = base[m * stride];
     if (q > 0) {
-      const int qt = q * st.tstep;
+      const double2* t = tw + st.twoff + q;
 #pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&tw[qt * m]));
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&t[(m - 1) * stride]));
     }
     GcmButterfly<R, +1>::run(x);
 #pragma unroll
     for (int t = 0; t < R; ++t) base[t * stride] = x[t];
+  }
+}
+
+// last forward stage + multiply + first inverse stage in one visit (stride 1: the R elements of a butterfly are
+// contiguous and q = 0, so no twiddles).  `table` is the multiplier of the first latitude of the block in transform
+// order (GcmGeomDev::smmzp); packed row r of the batch uses table + ((pr0 + r) / NPJ) * N (NPJ packed rows per
+// latitude, pr0 = packed rows before this batch; NPJ = 0: one table row for the whole batch).
+template <int R, int NPJ>
+__device__ __forceinline__ void gcm_mid_stage(double2* z, const GcmFftStage st, int nrows,
+                                              const double* __restrict__ table, int pr0, int tid, int nthr) {
+  const int N = st.N;
+  const int total = st.nbf * nrows;
+  for (int w = tid; w < total; w += nthr) {
+    const int row = gcm_fastdiv(w, st.magic_nbf), blk = w - row * st.nbf;
+    double2* base = z + row * N + blk * R;
+    const double* trow = (NPJ > 0 ? table + ((pr0 + row) / (NPJ > 0 ? NPJ : 1)) * N : table) + blk * R;
+    double2 x[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[t] = base[t];
+    GcmButterfly<R, -1>::run(x);
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const double s = __ldg(&trow[m]);
+      x[m].x *= s;
+      x[m].y *= s;
+    }
+    GcmButterfly<R, +1>::run(x);
+#pragma unroll
+    for (int t = 0; t < R; ++t) base[t] = x[t];
   }
 }
 
@@ -105,52 +119,46 @@ __host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
 
 // Filter `nrows` packed rows in place.  On entry the rows are visible to the whole block; on exit they hold
 // N x (filtered rows) and are synchronised.
+#define GCM_RADIX_SWITCH(r, CALL)   \
+  switch (r) {                     \
+    case 2: CALL(2); break;        \
+    case 3: CALL(3); break;        \
+    case 4: CALL(4); break;        \
+    case 5: CALL(5); break;        \
+    case 6: CALL(6); break;        \
+    case 8: CALL(8); break;        \
+    case 9: CALL(9); break;        \
+    case 10: CALL(10); break;      \
+    case 12: CALL(12); break;      \
+    case 15: CALL(15); break;      \
+    default: CALL(16); break;      \
+  }
+
 template <int NPJ>
 __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, const GcmFftPlan& plan,
-                                                        const double2* __restrict__ tw, const int* __restrict__ kperm,
-                                                        const double* __restrict__ table_row, int table_stride, int pr0,
-                                                        int tid, int nthr) {
-  const int N = plan.n;
-  if (N == 1) return;  // low_pass.py:58-59
-  int n = N;
-  for (int p = 0; p < plan.npass; ++p) {
-    const int r = plan.radix[p];
-    const bool last = p == plan.npass - 1;
-    const GcmFftStage st = gcm_fft_stage(plan, p, n);
-    switch (r) {
-      case 2: gcm_dif_stage<2, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 3: gcm_dif_stage<3, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 4: gcm_dif_stage<4, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 5: gcm_dif_stage<5, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 6: gcm_dif_stage<6, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 8: gcm_dif_stage<8, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 9: gcm_dif_stage<9, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 10: gcm_dif_stage<10, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 12: gcm_dif_stage<12, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      case 15: gcm_dif_stage<15, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-      default: gcm_dif_stage<16, NPJ>(z, st, nrows, tw, kperm, table_row, table_stride, pr0, last, tid, nthr); break;
-    }
-    n /= r;
+                                                        const double2* __restrict__ tw,
+                                                        const double* __restrict__ table, int pr0, int tid, int nthr) {
+  if (plan.n == 1) return;  // low_pass.py:58-59
+  const int last = plan.npass - 1;
+  for (int p = 0; p < last; ++p) {
+    const GcmFftStage st = gcm_fft_stage(plan, p);
+#define GCM_CALL(R) gcm_dif_stage<R>(z, st, nrows, tw, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
+#undef GCM_CALL
     __syncthreads();
   }
-  // n == 1 here; walk the stages back up
-  for (int p = plan.npass - 1; p >= 0; --p) {
-    const int r = plan.radix[p];
-    n *= r;
-    const GcmFftStage st = gcm_fft_stage(plan, p, n);
-    switch (r) {
-      case 2: gcm_dit_stage<2>(z, st, nrows, tw, tid, nthr); break;
-      case 3: gcm_dit_stage<3>(z, st, nrows, tw, tid, nthr); break;
-      case 4: gcm_dit_stage<4>(z, st, nrows, tw, tid, nthr); break;
-      case 5: gcm_dit_stage<5>(z, st, nrows, tw, tid, nthr); break;
-      case 6: gcm_dit_stage<6>(z, st, nrows, tw, tid, nthr); break;
-      case 8: gcm_dit_stage<8>(z, st, nrows, tw, tid, nthr); break;
-      case 9: gcm_dit_stage<9>(z, st, nrows, tw, tid, nthr); break;
-      case 10: gcm_dit_stage<10>(z, st, nrows, tw, tid, nthr); break;
-      case 12: gcm_dit_stage<12>(z, st, nrows, tw, tid, nthr); break;
-      case 15: gcm_dit_stage<15>(z, st, nrows, tw, tid, nthr); break;
-      default: gcm_dit_stage<16>(z, st, nrows, tw, tid, nthr); break;
-    }
+  {
+    const GcmFftStage st = gcm_fft_stage(plan, last);
+#define GCM_CALL(R) gcm_mid_stage<R, NPJ>(z, st, nrows, table, pr0, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[last], GCM_CALL)
+#undef GCM_CALL
+    __syncthreads();
+  }
+  for (int p = last - 1; p >= 0; --p) {
+    const GcmFftStage st = gcm_fft_stage(plan, p);
+#define GCM_CALL(R) gcm_dit_stage<R>(z, st, nrows, tw, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
+#undef GCM_CALL
     __syncthreads();
   }
 }

@@ -54,6 +54,10 @@ struct GcmFftPlan {
   int stride[GCM_MAX_RADIX_PASSES];
   unsigned magic_stride[GCM_MAX_RADIX_PASSES];
   unsigned magic_nbf[GCM_MAX_RADIX_PASSES];
+  int blk[GCM_MAX_RADIX_PASSES];    // block length n_s entering stage s (n_0 = n)
+  int nbf[GCM_MAX_RADIX_PASSES];    // butterflies per row: n / r_s
+  int tstep[GCM_MAX_RADIX_PASSES];  // twiddle table step n / n_s
+  int twoff[GCM_MAX_RADIX_PASSES];  // start of stage s in the per-stage twiddle table (GcmGeomDev::tws)
 };
 
 // floor(x / d) for x < 2^16, d < 2^16, with m = ceil(2^32 / d); m == 0 encodes d == 1
@@ -65,6 +69,30 @@ __device__ __forceinline__ int gcm_fastdiv(int x, unsigned m) {
   return m ? (int)(((unsigned long long)(unsigned)x * m) >> 32) : x;
 #else
   return m ? (int)__umulhi((unsigned)x, m) : x;
+#endif
+}
+
+// 1 / b to about 1 ulp without the special-case branches of the IEEE division sequence: hardware seed
+// (rcp.approx.ftz.f64, 2^-23) + two Newton steps.  Only for the fast kernels (pe25_fast.cu).
+__device__ __forceinline__ double gcm_rcp(double b) {
+#ifdef GCM_EMU
+  return 1.0 / b;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+#endif
+}
+
+// ask L2 for the 128-byte line at p (no register, no scoreboard): used to start a later phase's rows early
+__device__ __forceinline__ void gcm_prefetch_l2(const void* p) {
+#ifndef GCM_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
 #endif
 }
 
@@ -91,7 +119,10 @@ struct GcmGeomDev {
   const double* rdsig;  // [L]  1 / dsig
   const double* sigkap; // [L]  sig^kappa
   const int* kperm;     // [W]  wavenumber held at position p after the forward DIF transform
-  const double* smmzw;  // [H][W/2+1]  smmz / W: the 1/n of numpy's irfft folded into the multiplier
+  const double* smmzp;  // [H][W]  smmz[j][min(k, W-k)] / W at the position p that holds wavenumber k = kperm[p]
+                        //         after the forward in-place transform (the 1/n of numpy's irfft folded in)
+  const double2* tws;   // per-stage twiddles of the in-place transform, contiguous in the butterfly index:
+                        //         tws[twoff[s] + (m-1) stride_s + q] = exp(-2 pi i q m / n_s)
   double rdy;           // 1 / dy
   // per-layer tables by value (kernel parameters live in the constant bank: no load instruction) when L <= 16
   double c_sig[GCM_MAXLC], c_dsig[GCM_MAXLC], c_sigb[GCM_MAXLC], c_sigt[GCM_MAXLC], c_rdsig[GCM_MAXLC],

@@ -84,6 +84,10 @@ int gcm_fft_make_plan(int n, GcmFftPlan* plan) {
     plan->stride[s] = len / r;
     plan->magic_stride[s] = gcm_magic((unsigned)(len / r));
     plan->magic_nbf[s] = gcm_magic((unsigned)(n / r));
+    plan->blk[s] = len;
+    plan->nbf[s] = n / r;
+    plan->tstep[s] = n / len;
+    plan->twoff[s] = s == 0 ? 0 : plan->twoff[s - 1] + (plan->radix[s - 1] - 1) * plan->stride[s - 1];
     len /= r;
   }
   return GCM_OK;
@@ -116,8 +120,12 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   const size_t o_rdxj = o_tw + up256((size_t)W * 16), o_rdxh = o_rdxj + up256(H * 8);
   const size_t o_rdsig = o_rdxh + up256(H * 8), o_sigkap = o_rdsig + up256(L * 8);
   const size_t o_kperm = o_sigkap + up256(L * 8);
-  const size_t o_smmzw = o_kperm + up256((size_t)W * 4);
-  const size_t total = o_smmzw + up256((size_t)H * nw * 8);
+  const size_t o_smmzp = o_kperm + up256((size_t)W * 4);
+  const GcmFftPlan& pl0 = g->d.plan;
+  size_t ntws = 0;
+  for (int s2 = 0; s2 < pl0.npass; ++s2) ntws += (size_t)(pl0.radix[s2] - 1) * pl0.stride[s2];
+  const size_t o_tws = o_smmzp + up256((size_t)H * W * 8);
+  const size_t total = o_tws + up256(ntws * 16);
 
   std::vector<unsigned char> host(total, 0);
   memcpy(&host[o_sig], d->h_sig, L * 8);
@@ -127,12 +135,7 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   memcpy(&host[o_dxj], d->h_dx_j, H * 8);
   memcpy(&host[o_dxh], d->h_dx_h, H * 8);
   if (d->h_heightmap) memcpy(&host[o_hmap], d->h_heightmap, (size_t)H * W * 8);
-  if (d->h_smmz) {
-    memcpy(&host[o_smmz], d->h_smmz, (size_t)H * nw * 8);
-    double* sw = reinterpret_cast<double*>(&host[o_smmzw]);
-    const double inv = 1.0 / W;
-    for (size_t e = 0; e < (size_t)H * nw; ++e) sw[e] = d->h_smmz[e] * inv;
-  }
+  if (d->h_smmz) memcpy(&host[o_smmz], d->h_smmz, (size_t)H * nw * 8);
   double* tw = reinterpret_cast<double*>(&host[o_tw]);
   for (int m = 0; m < W; ++m) {  // exp(-2 pi i m / W), evaluated in long double
     const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)W;
@@ -158,6 +161,27 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
         mult *= pl.radix[s];
       }
       kperm[p] = k;
+    }
+    if (d->h_smmz) {  // multiplier in transform order, 1/W folded in
+      double* sp = reinterpret_cast<double*>(&host[o_smmzp]);
+      const double inv = 1.0 / W;
+      for (int j = 0; j < H; ++j)
+        for (int p = 0; p < W; ++p) {
+          const int k = kperm[p];
+          sp[(size_t)j * W + p] = d->h_smmz[(size_t)j * nw + (k <= W - k ? k : W - k)] * inv;
+        }
+    }
+    double* tws = reinterpret_cast<double*>(&host[o_tws]);
+    const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int s2 = 0; s2 < pl.npass; ++s2) {
+      const int R = pl.radix[s2], stride = pl.stride[s2], nblk = pl.blk[s2];
+      for (int m = 1; m < R; ++m)
+        for (int q = 0; q < stride; ++q) {
+          const long double a = twopi * (long double)((long long)q * m % nblk) / (long double)nblk;
+          const size_t e = (size_t)pl.twoff[s2] + (size_t)(m - 1) * stride + q;
+          tws[2 * e] = (double)cosl(a);
+          tws[2 * e + 1] = (double)(-sinl(a));
+        }
     }
   }
 
@@ -188,7 +212,8 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   g->d.rdsig = (const double*)(b + o_rdsig);
   g->d.sigkap = (const double*)(b + o_sigkap);
   g->d.kperm = (const int*)(b + o_kperm);
-  g->d.smmzw = (const double*)(b + o_smmzw);
+  g->d.smmzp = (const double*)(b + o_smmzp);
+  g->d.tws = (const double2*)(b + o_tws);
   g->d.rdy = 1.0 / d->dy;
   for (int k = 0; k < L && k < GCM_MAXLC; ++k) {
     g->d.c_sig[k] = d->h_sig[k];

@@ -44,7 +44,7 @@ __device__ __forceinline__ void pf_column(const GcmGeomDev& g, double sp_c, doub
                                           int ks, double* phi, double* rho) {
   const double ptop = g.ptop;
   double pk_col = 0.0;
-  if (PTOP0) pk_col = pow(sp_c * (1.0 / GCM_P0), GCM_KAPPA);
+  if (PTOP0) pk_col = exp(GCM_KAPPA * log(sp_c * (1.0 / GCM_P0)));  // (p / P0)^kappa
   double tk = t[0];
   double pk = PTOP0 ? g.c_sigkap[0] * pk_col : pow((g.c_sig[0] * sp_c + ptop) / GCM_P0, GCM_KAPPA);
   const double t0 = tk, pk0 = pk;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void pf_column(const GcmGeomDev& g, double sp_c, doub
     }
     const double tp = sp_c * g.c_sig[k] + ptop;
     const double rtt = GCM_RD * (tk * pk);                      // Rd * T
-    const double r = tp / rtt;                                  // rho (dynamics.py:152)
+    const double r = tp * gcm_rcp(rtt);                         // rho (dynamics.py:152)
     const double spa = PTOP0 ? rtt : (g.c_sig[k] * sp_c) / r;   // sig p / rho
     const double stp = GCM_CP * ((tk + t_n) * 0.5) * (pk - pk_n);
     sum += spa * g.c_dsig[k] - g.c_sigt[k] * stp;
@@ -79,8 +79,76 @@ __device__ __forceinline__ void pf_column(const GcmGeomDev& g, double sp_c, doub
 // ---------------------------------------------------------------------------------------------------
 // R: one CTA per (block of RB rows, member)
 // ---------------------------------------------------------------------------------------------------
+// flat index e = prl * W + i over the packed rows of an FFT pass, advanced by the block size without a division
+struct PfRowIdx {
+  int prl, i;
+  __device__ __forceinline__ PfRowIdx(int tid, unsigned magicW, int W) {
+    prl = gcm_fastdiv(tid, magicW);
+    i = tid - prl * W;
+  }
+  __device__ __forceinline__ void advance(int nthr, int W) {
+    i += nthr;
+    while (i >= W) {
+      i -= W;
+      ++prl;
+    }
+  }
+};
+
+// f(prl, i) for every element of `nb` rows of length W, spread over the block.  Rows at least as long as the block
+// take the nested form (row-invariant index math hoisted, four independent iterations in flight).
+template <class F>
+__device__ __forceinline__ void pf_foreach(int nb, int W, int tid, int nthr, unsigned magicW, F f) {
+  if (W >= nthr) {
+    for (int prl = 0; prl < nb; ++prl) {
+#pragma unroll 4
+      for (int i = tid; i < W; i += nthr) f(prl, i);
+    }
+  } else {
+    PfRowIdx x(tid, magicW, W);
+    for (int e = tid; e < nb * W; e += nthr, x.advance(nthr, W)) f(x.prl, x.i);
+  }
+}
+
+// Column phase of one row for one lane: phi and rho of column (j, i) into (phi, rho); if emit_pre, pgfu + phiu of
+// row j (dynamics.py:159, :162-165; east neighbour from lane + 1) -> pgf, unfiltered; if emit_fv, fv = phiv + pgv of
+// the row to the north (:160, :167-169) from (phi_n, rho_n, sp_n) -> fv at cn.  All lanes of the warp must call.
 template <int L, bool PTOP0>
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ double pf_row_step(const GcmGeomDev& g, const double* __restrict__ sp,
+                                              const double* __restrict__ st, double* pgf, double* __restrict__ fv,
+                                              int plane, int c2, int cn, int j, bool own, bool emit_pre, bool emit_fv,
+                                              double* phi, double* rho, const double* phi_n, const double* rho_n,
+                                              double sp_n) {
+  const double sp_c = sp[c2];
+  pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
+  if (emit_pre) {
+    const double sp_e = __shfl_down_sync(0xffffffffu, sp_c, 1);
+    const double rdxj = g.rdx_j[j];
+    const double psum = sp_c + sp_e, gradp = (sp_e - sp_c) * rdxj;
+    const double a_u = psum * gradp;       // (p_c + p_e) dp/dx
+    const double b_u = psum * 0.5 * rdxj;  // iph(p) / dx
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const double phi_e = __shfl_down_sync(0xffffffffu, phi[k], 1);
+      const double rho_e = __shfl_down_sync(0xffffffffu, rho[k], 1);
+      const double x = g.c_sig[k] * a_u * gcm_rcp(rho[k] + rho_e) + b_u * (phi_e - phi[k]);
+      if (own) pgf[k * plane + c2] = x;
+    }
+  }
+  if (emit_fv && own) {
+    const double rdy = g.rdy;
+    const double psum = sp_n + sp_c;
+    const double a_v = psum * ((sp_c - sp_n) * rdy);  // (p_c + p_jp) dp/dy
+    const double b_v = psum * 0.5 * rdy;              // jph(p) / dy
+#pragma unroll
+    for (int k = 0; k < L; ++k)
+      fv[k * plane + cn] = g.c_sig[k] * a_v * gcm_rcp(rho_n[k] + rho[k]) + b_v * (phi[k] - phi_n[k]);
+  }
+  return sp_c;
+}
+
+template <int L, bool PTOP0, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, int ja, int jend, int RB,
                  int RG, int NBAT, unsigned magicW, size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double2, z);
@@ -101,63 +169,77 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
   double* __restrict__ sd = w.sd + o3;
   double* __restrict__ fv = w.fv + o3;
   double* __restrict__ pn = w.pn + o2;
-  const int nw = W / 2 + 1;
-  const double* table = g.smmzw + (size_t)j0 * nw;
+  const double* table = g.smmzp + (size_t)j0 * W;
   const double rdy = g.rdy;
+
+  // start the rows of the column phases on their way to L2 while the first filter runs:
+  // sv rows j-1 .. j+rb-1 and st rows j .. j+rb of every layer, one request per 128-byte line
+  {
+    const int lines = (W * 8 + 127) / 128;
+    const int nrow = rb + 1;
+    for (int e = tid; e < L * nrow * lines; e += nthr) {
+      const int ln = e % lines, rk = e / lines, r = rk % nrow, k = rk / nrow;
+      const int jv = gcm_row(j0 + r, -1, H, g.wrap_j), jt = gcm_row(j0 + r - 1, 1, H, g.wrap_j);
+      gcm_prefetch_l2(sv + k * plane + jv * W + ln * 16);
+      gcm_prefetch_l2(st + k * plane + jt * W + ln * 16);
+    }
+  }
 
   // FA. spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189), NBAT packed rows (two layers each) per pass
   for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
     const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
-    for (int e = tid; e < nb * W; e += nthr) {
-      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
-      const int row = (j0 + r) * W;
-      const double ph = (sp[row + i] + sp[row + gcm_ip(i, W)]) * 0.5;
-      const double x0 = su[k0 * plane + row + i] * ph;
-      const double x1 = k1 < L ? su[k1 * plane + row + i] * ph : 0.0;
-      z[e] = make_double2(x0, x1);
-    }
+    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+      const double* __restrict__ spr = sp + (j0 + r) * W;
+      const double* __restrict__ s0 = su + k0 * plane + (j0 + r) * W;
+      const double ph = (spr[i] + spr[gcm_ip(i, W)]) * 0.5;
+      const double x0 = s0[i] * ph;
+      const double x1 = k0 + 1 < L ? s0[plane + i] * ph : 0.0;
+      z[prl * W + i] = make_double2(x0, x1);
+    });
     __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tw, g.kperm, table, nw, pr0, tid, nthr);
-    for (int e = tid; e < nb * W; e += nthr) {
-      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
-      const int c2 = (j0 + r) * W + i;
-      const double2 v = z[e];
-      spu[k0 * plane + c2] = v.x;
-      if (k1 < L) spu[k1 * plane + c2] = v.y;
-    }
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, table, pr0, tid, nthr);
+    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+      double* o = spu + k0 * plane + (j0 + r) * W;
+      const double2 v = z[prl * W + i];
+      o[i] = v.x;
+      if (k0 + 1 < L) o[plane + i] = v.y;
+    });
     __syncthreads();  // the buffer is free for the next pass; spu of this block is visible to the block
   }
 
   // P2a. per column: aflux (dynamics.py:35-46), p_n (:194); spu comes back from L1/L2
-  for (int e = tid; e < rb * W; e += nthr) {
-    const int r = gcm_fastdiv(e, magicW), i = e - r * W;
-    const int j = j0 + r;
-    const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
-    const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
-    const double sp_c = sp[c2];
-    const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
-    const double rdxj = g.rdx_j[j];
-    double conv[L];
-    double pit = 0.0;
+  {
+    PfRowIdx x(tid, magicW, W);
+    for (int e = tid; e < rb * W; e += nthr, x.advance(nthr, W)) {
+      const int i = x.i, j = j0 + x.prl;
+      const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+      const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
+      const double sp_c = sp[c2];
+      const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
+      const double rdxj = g.rdx_j[j];
+      double conv[L];
+      double pit = 0.0;
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
-      const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
-      const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
-      conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
-      pit += conv[k];
-    }
-    double acc = 0.0;
+      for (int k = 0; k < L; ++k) {
+        const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
+        const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
+        conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
+        pit += conv[k];
+      }
+      double acc = 0.0;
 #pragma unroll
-    for (int k = L - 1; k >= 0; --k) {
-      acc += conv[k];
-      sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+      for (int k = L - 1; k >= 0; --k) {
+        acc += conv[k];
+        sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+      }
+      pn[c2] = p[c2] - pit * dt;
     }
-    pn[c2] = p[c2] - pit * dt;
   }
 
-  // P2b. hydrostatic columns; a warp owns 31 columns (+ lane 31 = east neighbour of lane 30) and marches south
+  // P2b. hydrostatic columns; a warp owns 31 columns (+ lane 31 = east neighbour of lane 30) and marches south,
+  // the two register sets (A, B) alternating between "this row" and "the row to the north"
   {
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int nchunk = (W + 30) / 31, ngrp = (rb + RG - 1) / RG;
@@ -167,44 +249,23 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
       const bool own = lane < 31 && i < W;
       i = i % W;
       const int r0 = grp * RG, r1 = r0 + RG < rb ? r0 + RG : rb;  // rows [r0, r1), row r1 only as the south neighbour
-      double phi_n[L], rho_n[L];  // the row to the north of the one being computed
-      double sp_n = 0.0;
+      double phiA[L], rhoA[L], phiB[L], rhoB[L];
+      int jn = j0 + r0;  // r0 < rb: no wrap
+      double spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, jn * W + i, 0, jn, own, true, false, phiA, rhoA,
+                                         phiA, rhoA, 0.0);
+      double spB = 0.0;
 #pragma unroll 1
-      for (int r = r0; r <= r1; ++r) {
-        const int j = gcm_row(j0 + r - 1, 1, H, g.wrap_j);
-        const int c2 = j * W + i;
-        const double sp_c = sp[c2];
-        double phi[L], rho[L];
-        pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
-        if (r < r1) {  // pgfu + phiu of row j (dynamics.py:159, :162-165), east neighbour from lane + 1
-          const double sp_e = __shfl_down_sync(0xffffffffu, sp_c, 1);
-          const double rdxj = g.rdx_j[j];
-          const double psum = sp_c + sp_e, gradp = (sp_e - sp_c) * rdxj;
-          const double a_u = psum * gradp;       // (p_c + p_e) dp/dx
-          const double b_u = psum * 0.5 * rdxj;  // iph(p) / dx
-#pragma unroll
-          for (int k = 0; k < L; ++k) {
-            const double phi_e = __shfl_down_sync(0xffffffffu, phi[k], 1);
-            const double rho_e = __shfl_down_sync(0xffffffffu, rho[k], 1);
-            const double x = g.c_sig[k] * a_u / (rho[k] + rho_e) + b_u * (phi_e - phi[k]);
-            if (own) pgf[k * plane + c2] = x;  // unfiltered, filtered in place below
-          }
+      for (int r = r0 + 1; r <= r1; r += 2) {
+        int j = gcm_row(jn, 1, H, g.wrap_j);
+        spB = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r < r1, true, phiB, rhoB,
+                                    phiA, rhoA, spA);
+        jn = j;
+        if (r + 1 <= r1) {
+          j = gcm_row(jn, 1, H, g.wrap_j);
+          spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r + 1 < r1, true, phiA,
+                                      rhoA, phiB, rhoB, spB);
+          jn = j;
         }
-        if (r > r0 && own) {  // fv = phiv + pgv of the row to the north (dynamics.py:160, :167-169)
-          const int cn = (j0 + r - 1) * W + i;
-          const double psum = sp_n + sp_c;
-          const double a_v = psum * ((sp_c - sp_n) * rdy);  // (p_c + p_jp) dp/dy
-          const double b_v = psum * 0.5 * rdy;              // jph(p) / dy
-#pragma unroll
-          for (int k = 0; k < L; ++k)
-            fv[k * plane + cn] = g.c_sig[k] * a_v / (rho_n[k] + rho[k]) + b_v * (phi[k] - phi_n[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-          phi_n[k] = phi[k];
-          rho_n[k] = rho[k];
-        }
-        sp_n = sp_c;
       }
     }
   }
@@ -213,22 +274,20 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
   // FB. pgf = arakawa_1977(pgfu + phiu) (dynamics.py:202), in place in HBM through the same buffer
   for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
     const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
-    for (int e = tid; e < nb * W; e += nthr) {
-      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
-      const int c2 = (j0 + r) * W + i;
-      z[e] = make_double2(pgf[k0 * plane + c2], k1 < L ? pgf[k1 * plane + c2] : 0.0);
-    }
+    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+      const double* o = pgf + k0 * plane + (j0 + r) * W;
+      z[prl * W + i] = make_double2(o[i], k0 + 1 < L ? o[plane + i] : 0.0);
+    });
     __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tw, g.kperm, table, nw, pr0, tid, nthr);
-    for (int e = tid; e < nb * W; e += nthr) {
-      const int prl = gcm_fastdiv(e, magicW), i = e - prl * W;
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP), k1 = k0 + 1;
-      const int c2 = (j0 + r) * W + i;
-      const double2 v = z[e];
-      pgf[k0 * plane + c2] = v.x;
-      if (k1 < L) pgf[k1 * plane + c2] = v.y;
-    }
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, table, pr0, tid, nthr);
+    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+      double* o = pgf + k0 * plane + (j0 + r) * W;
+      const double2 v = z[prl * W + i];
+      o[i] = v.x;
+      if (k0 + 1 < L) o[plane + i] = v.y;
+    });
     __syncthreads();
   }
 }
@@ -370,6 +429,7 @@ int g_gcm_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 //   1  update-kernel tile width in i (threads.x, multiple of 32)      2  threads of the row kernel
 //   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the row kernel (RB)
 //   5  rows per warp task of the row kernel's column phase (RG)      6  packed rows per FFT pass (NBAT)
+//   7  register budget of the row kernel: 1 = 128 regs (default), 2 = 102 regs / five 128-thread CTAs per SM
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
@@ -401,35 +461,53 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   if (g_gcm_knob[4] > 0) RB = g_gcm_knob[4];
   int RG = (RB + 3) / 4;
   if (g_gcm_knob[5] > 0) RG = g_gcm_knob[5];
-  // packed rows per FFT pass: up to 48 KB of shared memory
-  int NBAT = (int)((48 * 1024) / prsmem);
+  // packed rows per FFT pass: about 24 KB of shared memory, so that five or more CTAs share an SM
+  int NBAT = (int)((24 * 1024) / prsmem);
   if (g_gcm_knob[6] > 0) NBAT = g_gcm_knob[6];
   NBAT = NBAT < 1 ? 1 : (NBAT > RB * NP ? RB * NP : NBAT);
   const size_t smem = NBAT * prsmem;
-  int tr = (NBAT * W / 24 + 31) / 32 * 32;
-  tr = tr < 64 ? 64 : (tr > 256 ? 256 : tr);
+  // threads per CTA (measured on B200, profiles/r01h): few CTAs (less than two per SM) want wide CTAs; long rows
+  // run five 128-thread CTAs per SM on the 102-register build; many small CTAs want two warps each
+  const size_t nctas = (size_t)((nrows_ext + RB - 1) / RB) * nbatch;
+  int variant = 0;
+  int tr = 64;
+  if (nctas < 296) tr = 192;
+  else if (W >= 512) { tr = 128; variant = 1; }
   if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2] > 256 ? 256 : g_gcm_knob[2];
+  if (g_gcm_knob[7] > 0) variant = g_gcm_knob[7] - 1;
   const PfConst cb{base->p, base->u, base->v, base->t, base->q};
   const PfConst cs{star->p, star->u, star->v, star->t, star->q};
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
   const unsigned magicW = gcm_magic((unsigned)W);
-#ifndef GCM_EMU
-  if (smem > 48 * 1024) {
-    GCM_CUDA(cudaFuncSetAttribute(pe25f_row_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GCM_CUDA(cudaFuncSetAttribute(pe25f_row_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  // register budget of the row kernel: 128 per thread up to 256 threads (variant 0), or 102 per thread = five
+  // 128-thread CTAs per SM (variant 1)
+  if (variant == 1 && tr > 128) tr = 128;
+#ifdef GCM_EMU
+#define PF_ROW_SMEM(PT, MAXT, MINB)
+#else
+#define PF_ROW_SMEM(PT, MAXT, MINB)                                                                                    \
+  if (smem > 48 * 1024)                                                                                                \
+    GCM_CUDA(cudaFuncSetAttribute(pe25f_row_kernel<L, PT, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem));
 #endif
+#define PF_ROW_LAUNCH(PT, MAXT, MINB)                                                                                  \
+  do {                                                                                                                 \
+    PF_ROW_SMEM(PT, MAXT, MINB)                                                                                        \
+    GCM_LAUNCH((pe25f_row_kernel<L, PT, MAXT, MINB>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja,         \
+               ja + nrows_ext, RB, RG, NBAT, magicW, b2, b3);                                                          \
+  } while (0)
   {
     GcmProfScope ps(GCM_K_ROW, stream);
     const dim3 grid((nrows_ext + RB - 1) / RB, nbatch);
-    if (ptop0)
-      GCM_LAUNCH((pe25f_row_kernel<L, true>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja, ja + nrows_ext, RB,
-                 RG, NBAT, magicW, b2, b3);
-    else
-      GCM_LAUNCH((pe25f_row_kernel<L, false>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja, ja + nrows_ext,
-                 RB, RG, NBAT, magicW, b2, b3);
+    if (variant == 1) {
+      if (ptop0) PF_ROW_LAUNCH(true, 128, 5); else PF_ROW_LAUNCH(false, 128, 5);
+    } else {
+      if (ptop0) PF_ROW_LAUNCH(true, 256, 2); else PF_ROW_LAUNCH(false, 256, 2);
+    }
   }
+#undef PF_ROW_LAUNCH
+#undef PF_ROW_SMEM
   GCM_CHECK_LAUNCH();
   int tx = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 32;
   int ty = g_gcm_knob[3] > 0 ? g_gcm_knob[3] : 4;
