@@ -29,6 +29,12 @@ SIGNATURES = {
     "gcm_pe25_workspace_bytes": (_z, [_geom, _i]),
     "gcm_pe25_half_step": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, c_stream]),
     "gcm_pe25_matsuno_step": (_i, [_geom, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
+    "gcm_pe25_half_step_rows": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     c_stream]),
+    "gcm_comm_unique_id": (_i, [C.c_void_p]),
+    "gcm_comm_create": (_i, [_i, _i, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gcm_comm_destroy": (_i, [C.c_void_p]),
+    "gcm_band_matsuno_step": (_i, [_geom, C.c_void_p, _st, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
     "gcm_pe25_select_path": (_i, [_i]),
     "gcm_tuning_knob": (_i, [_i, _i]),
     "gcm_pe25_calc_pu": (_i, [_geom, c_dp, c_dp, c_dp, c_stream]),

@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 SOURCES = {
     "geom.cu": [],
     "prof.cu": [],
+    "comm.cu": [],
     "pe25.cu": ["-fmad=false"],
     "pe25_fast.cu": [],
     "sw2d.cu": ["-fmad=false"],
@@ -80,7 +81,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
     lib = lib_path()
     if force or procs or _newer(lib, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -7,6 +7,11 @@ The j-stencil of a half step reaches rows j-1 .. j+2 (dynamics.py:183-227), so e
 to the north and two to the south; ranks form a ring (the reference's roll is periodic over the pole) and
 exchange halo rows twice per Matsuno step: before the predictor (base state) and before the corrector (star
 state).  The same kernels run on every band, so an R-rank run is bit-identical to the 1-rank run.
+
+On GPUs the whole loop runs inside the library (`gcm_band_matsuno_step`, csrc/comm.cu): ncclSend/ncclRecv with both
+ring neighbours on a side stream while the interior rows are computed, then the three rows next to the halos.  The
+torch.distributed path below (`exchange` + `_half`) is the same schedule without the overlap; the CPU tests drive it
+over gloo.
 """
 import ctypes
 
@@ -26,7 +31,7 @@ class BandStepper:
     rank / world default to the initialised torch.distributed group (NCCL on GPUs).  world == 1 runs the same
     band code against itself (the ring closes on the rank's own rows)."""
 
-    def __init__(self, geom, p, u, v, t, q, rank=None, world=None, group=None):
+    def __init__(self, geom, p, u, v, t, q, rank=None, world=None, group=None, native=None):
         self.group = group
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -57,6 +62,34 @@ class BandStepper:
         self.send_south, self.recv_north = mk(n_n), mk(n_n)      # my last owned row     -> south neighbour's north halo
         self.north, self.south = (rank - 1) % world, (rank + 1) % world
         self.nsteps_done = 0
+        self.overlap = True
+        self.comm = None
+        if native is None:
+            native = self.cur[0].is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
+        if native:
+            self._make_comm()
+
+    # ---- native ring: gcm_comm (NCCL bound inside the library) + the C++ band loop -------------------------
+    def _make_comm(self):
+        lib = _lib.lib()
+        idbuf = (ctypes.c_ubyte * 128)()
+        if self.world > 1:
+            if self.rank == 0:
+                _lib.check(lib.gcm_comm_unique_id(idbuf), "gcm_comm_unique_id")
+            t = torch.tensor(list(idbuf), dtype=torch.uint8, device=_lib.device())
+            dist.broadcast(t, 0, group=self.group)           # rank 0 within the group ships the NCCL unique id
+            idbuf = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        h = ctypes.c_void_p()
+        _lib.check(lib.gcm_comm_create(self.world, self.rank, idbuf, ctypes.byref(h)), "gcm_comm_create")
+        self.comm = h
+
+    def __del__(self):
+        try:
+            if self.comm is not None:
+                _lib.lib().gcm_comm_destroy(self.comm)
+                self.comm = None
+        except Exception:
+            pass
 
     # ---- halo exchange ------------------------------------------------------------------------------
     def exchange(self, state):
@@ -93,13 +126,24 @@ class BandStepper:
 
     def step(self, dt, nsteps=1):
         dt = _host.scalar(dt)
-        for _ in range(int(nsteps)):
+        nsteps = int(nsteps)
+        if self.comm is not None and nsteps > 0:
+            ws, need = _workspace(self.dg, 1)
+            sc, ss, sn = _struct(self.cur), _struct(self.star), _struct(self.nxt)
+            _lib.check(_lib.lib().gcm_band_matsuno_step(self.dg.handle, self.comm, ctypes.byref(sc), ctypes.byref(ss),
+                                                        ctypes.byref(sn), float(dt), nsteps, int(self.overlap),
+                                                        _host.ptr(ws), need, _lib.stream()), "gcm_band_matsuno_step")
+            if nsteps % 2:
+                self.cur, self.nxt = self.nxt, self.cur
+            self.nsteps_done += nsteps
+            return
+        for _ in range(nsteps):
             self.exchange(self.cur)
             self._half(self.cur, self.cur, self.star, dt)        # dynamics.py:231
             self.exchange(self.star)
             self._half(self.cur, self.star, self.nxt, dt)        # dynamics.py:234
             self.cur, self.nxt = self.nxt, self.cur
-        self.nsteps_done += int(nsteps)
+        self.nsteps_done += nsteps
 
     def step_host(self, host_in, host_out, dt, nsteps=1):
         """host_in / host_out: this rank's band (with halo rows) as five pinned host tensors."""

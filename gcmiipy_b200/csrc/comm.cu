@@ -1,0 +1,231 @@
+// comm.cu -- latitude-band Matsuno loop with the halo exchange over NCCL (NVLink 5 / NVSwitch).
+//
+// The reference is one process: every j-shift is np.roll over the whole array (coordinates_3d.py:43-48).  Here rank r
+// owns a band of rows (all i, all k) with one halo row to the north and two to the south; ranks form a ring (the
+// roll is periodic across the pole).  Per half step the band
+//   comm stream : packs its first two / last owned rows, ncclSend/ncclRecv with both neighbours in one group,
+//                 unpacks into the halo rows;
+//   main stream : meanwhile computes the interior rows (they read owned rows only), then waits for the halos and
+//                 computes the three rows next to them (gcm_pe25_half_step_rows, two-segment launches).
+// The whole loop over steps runs here, so the host cost per step is a dozen launches and two NCCL groups.
+//
+// NCCL is bound at run time (dlopen of the libnccl the process already uses -- torch's -- else the system one): the
+// library has no link-time dependency on it, so single-GPU users and the CPU-side ABI check never need NCCL.
+#include <stdlib.h>
+#include <string.h>
+
+#include "gcm_common.h"
+
+#ifndef GCM_EMU
+#include <dlfcn.h>
+#endif
+
+extern "C" int gcm_pe25_half_step(const gcm_geom*, const gcm_state*, const gcm_state*, const gcm_state*, double, int,
+                                  void*, size_t, void*);
+extern "C" int gcm_pe25_half_step_rows(const gcm_geom*, const gcm_state*, const gcm_state*, const gcm_state*, double, int,
+                                       void*, size_t, const int*, const int*, void*);
+
+#define GCM_HALO_N 1
+#define GCM_HALO_S 2
+#define GCM_ENCCL_BASE 1000000  // status = GCM_ENCCL_BASE + ncclResult_t
+
+typedef struct {
+  char internal[128];
+} gcm_nccl_id;
+typedef void* gcm_nccl_comm;
+
+struct GcmNccl {
+  void* handle;
+  int (*GetUniqueId)(gcm_nccl_id*);
+  int (*CommInitRank)(gcm_nccl_comm*, int, gcm_nccl_id, int);
+  int (*CommDestroy)(gcm_nccl_comm);
+  int (*Send)(const void*, size_t, int, int, gcm_nccl_comm, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, gcm_nccl_comm, cudaStream_t);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
+};
+static GcmNccl g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static int gcm_nccl_load() {
+#ifdef GCM_EMU
+  return GCM_EUNSUP;
+#else
+  if (g_nccl.handle) return GCM_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (int pass = 0; pass < 2 && !h; ++pass)  // first the copy already in the process (torch's), then a fresh load
+    for (int n = 0; n < 2 && !h; ++n) h = dlopen(names[n], RTLD_NOW | (pass == 0 ? RTLD_NOLOAD : 0));
+  GCM_REQUIRE(h, GCM_EUNSUP);
+  GcmNccl t;
+  t.handle = h;
+  t.GetUniqueId = (int (*)(gcm_nccl_id*))dlsym(h, "ncclGetUniqueId");
+  t.CommInitRank = (int (*)(gcm_nccl_comm*, int, gcm_nccl_id, int))dlsym(h, "ncclCommInitRank");
+  t.CommDestroy = (int (*)(gcm_nccl_comm))dlsym(h, "ncclCommDestroy");
+  t.Send = (int (*)(const void*, size_t, int, int, gcm_nccl_comm, cudaStream_t))dlsym(h, "ncclSend");
+  t.Recv = (int (*)(void*, size_t, int, int, gcm_nccl_comm, cudaStream_t))dlsym(h, "ncclRecv");
+  t.GroupStart = (int (*)(void))dlsym(h, "ncclGroupStart");
+  t.GroupEnd = (int (*)(void))dlsym(h, "ncclGroupEnd");
+  GCM_REQUIRE(t.GetUniqueId && t.CommInitRank && t.CommDestroy && t.Send && t.Recv && t.GroupStart && t.GroupEnd,
+              GCM_EUNSUP);
+  g_nccl = t;
+  return GCM_OK;
+#endif
+}
+
+#define GCM_NCCL(call)                             \
+  do {                                             \
+    int r_ = (call);                               \
+    if (r_ != 0) return GCM_ENCCL_BASE + r_;       \
+  } while (0)
+
+struct gcm_comm {
+  int nranks, rank;
+  gcm_nccl_comm comm;
+  cudaStream_t stream;          // halo traffic runs here, beside the caller's stream
+  cudaEvent_t ev_ready, ev_halo;
+  double* buf;                  // send_n | send_s | recv_s | recv_n
+  size_t buf_doubles;
+};
+
+extern "C" int gcm_comm_unique_id(unsigned char* out128) {
+  GCM_REQUIRE(out128, GCM_ENULL);
+  int st = gcm_nccl_load();
+  if (st) return st;
+  gcm_nccl_id id;
+  GCM_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out128, id.internal, 128);
+  return GCM_OK;
+}
+
+extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128, gcm_comm** out) {
+  GCM_REQUIRE(out, GCM_ENULL);
+  GCM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, GCM_ESHAPE);
+  gcm_comm* c = (gcm_comm*)calloc(1, sizeof(gcm_comm));
+  GCM_REQUIRE(c, (int)cudaErrorMemoryAllocation);
+  c->nranks = nranks;
+  c->rank = rank;
+#ifndef GCM_EMU
+  if (nranks > 1) {
+    int st = id128 ? gcm_nccl_load() : GCM_ENULL;
+    if (st) { free(c); return st; }
+    gcm_nccl_id id;
+    memcpy(id.internal, id128, 128);
+    int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) { free(c); return GCM_ENCCL_BASE + r; }
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+  if (e != cudaSuccess) { free(c); return (int)e; }
+#else
+  (void)id128;
+  GCM_REQUIRE(nranks == 1, GCM_EUNSUP);
+#endif
+  *out = c;
+  return GCM_OK;
+}
+
+extern "C" int gcm_comm_destroy(gcm_comm* c) {
+  if (!c) return GCM_OK;
+#ifndef GCM_EMU
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+#endif
+  if (c->buf) cudaFree(c->buf);
+  free(c);
+  return GCM_OK;
+}
+
+extern "C" size_t gcm_halo_buffer_doubles(const gcm_geom* g, int nrows);
+extern "C" int gcm_halo_pack(const gcm_geom*, const gcm_state*, int, int, double*, void*);
+extern "C" int gcm_halo_unpack(const gcm_geom*, const gcm_state*, int, int, const double*, void*);
+extern "C" int gcm_halo_copy_rows(const gcm_geom*, const gcm_state*, int, const gcm_state*, int, int, void*);
+
+// fill the halo rows of `s` (1 north, 2 south) from the ring neighbours, on stream `q`
+static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, cudaStream_t q) {
+  const int lo = g->d.row_lo, hi = g->d.row_hi;
+  int st;
+  if (c->nranks == 1) {  // the ring closes on the band itself
+    if ((st = gcm_halo_copy_rows(g, s, lo, s, hi, GCM_HALO_S, q))) return st;
+    return gcm_halo_copy_rows(g, s, hi - GCM_HALO_N, s, lo - GCM_HALO_N, GCM_HALO_N, q);
+  }
+#ifdef GCM_EMU
+  return GCM_EUNSUP;
+#else
+  const size_t ns = gcm_halo_buffer_doubles(g, GCM_HALO_S), nn = gcm_halo_buffer_doubles(g, GCM_HALO_N);
+  if (c->buf_doubles < 2 * (ns + nn)) {
+    if (c->buf) cudaFree(c->buf);
+    c->buf = nullptr;
+    GCM_CUDA(cudaMalloc((void**)&c->buf, 2 * (ns + nn) * sizeof(double)));
+    c->buf_doubles = 2 * (ns + nn);
+  }
+  double *send_n = c->buf, *send_s = send_n + ns, *recv_s = send_s + nn, *recv_n = recv_s + ns;
+  const int north = (c->rank + c->nranks - 1) % c->nranks, south = (c->rank + 1) % c->nranks;
+  if ((st = gcm_halo_pack(g, s, lo, GCM_HALO_S, send_n, q))) return st;               // -> north's south halo
+  if ((st = gcm_halo_pack(g, s, hi - GCM_HALO_N, GCM_HALO_N, send_s, q))) return st;  // -> south's north halo
+  GCM_NCCL(g_nccl.GroupStart());
+  GCM_NCCL(g_nccl.Send(send_n, ns, 8 /* ncclFloat64 */, north, c->comm, q));
+  GCM_NCCL(g_nccl.Send(send_s, nn, 8, south, c->comm, q));
+  GCM_NCCL(g_nccl.Recv(recv_s, ns, 8, south, c->comm, q));
+  GCM_NCCL(g_nccl.Recv(recv_n, nn, 8, north, c->comm, q));
+  GCM_NCCL(g_nccl.GroupEnd());
+  if ((st = gcm_halo_unpack(g, s, hi, GCM_HALO_S, recv_s, q))) return st;
+  return gcm_halo_unpack(g, s, lo - GCM_HALO_N, GCM_HALO_N, recv_n, q);
+#endif
+}
+
+// out = base + dt F(star) on the band, halos of `star` exchanged first; interior rows overlap the exchange
+static int band_half_step(const gcm_geom* g, gcm_comm* c, const gcm_state* base, const gcm_state* star,
+                          const gcm_state* out, double dt, int overlap, void* ws, size_t ws_bytes, cudaStream_t main) {
+  const int lo = g->d.row_lo, hi = g->d.row_hi, n = hi - lo;
+  int st;
+#ifndef GCM_EMU
+  if (overlap && n >= 4) {
+    GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // `star` is complete on the main stream
+    GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
+    if ((st = band_exchange(g, c, star, c->stream))) return st;
+    GCM_CUDA(cudaEventRecord(c->ev_halo, c->stream));
+    const int ri[4] = {lo + 1, n - 2, 0, 0}, ui[4] = {lo + 1, n - 3, 0, 0};  // rows that read owned rows only
+    st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, ri, ui, main);
+    if (st == GCM_OK) {
+      GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));
+      const int rb[4] = {lo, 1, hi - 1, 2}, ub[4] = {lo, 1, hi - 2, 2};  // the rows next to the halos
+      return gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, rb, ub, main);
+    }
+    if (st != GCM_EUNSUP) return st;
+    GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));  // no segmented kernels for this geometry: whole band now
+    return gcm_pe25_half_step(g, base, star, out, dt, 1, ws, ws_bytes, main);
+  }
+#else
+  (void)overlap;
+  (void)n;
+#endif
+  if ((st = band_exchange(g, c, star, main))) return st;
+  return gcm_pe25_half_step(g, base, star, out, dt, 1, ws, ws_bytes, main);
+}
+
+// dynamics.matsuno_timestep (dynamics.py:230-237) `nsteps` times on one latitude band.  `cur` holds the band with
+// halo rows (any content); after the call the newest state is in `nxt` if nsteps is odd, else in `cur` (the two
+// alternate); `star` is scratch.  Halos of the result are NOT filled.
+extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_state* cur, const gcm_state* star,
+                                     const gcm_state* nxt, double dt, int nsteps, int overlap, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  GCM_REQUIRE(g && c && cur && star && nxt && ws, GCM_ENULL);
+  GCM_REQUIRE(nsteps > 0, GCM_ESHAPE);
+  GCM_REQUIRE(!g->d.wrap_j, GCM_EUNSUP);
+  GCM_REQUIRE(g->d.row_lo == GCM_HALO_N && g->d.row_hi + GCM_HALO_S == g->d.H, GCM_ESHAPE);
+  GCM_REQUIRE(g->d.row_hi - g->d.row_lo >= GCM_HALO_S, GCM_ESHAPE);
+  cudaStream_t main = (cudaStream_t)stream;
+  const gcm_state *a = cur, *b = nxt;
+  int st;
+  for (int s = 0; s < nsteps; ++s) {
+    if ((st = band_half_step(g, c, a, a, star, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:231
+    if ((st = band_half_step(g, c, a, star, b, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:234
+    const gcm_state* t = a;
+    a = b;
+    b = t;
+  }
+  return GCM_OK;
+}

@@ -82,18 +82,20 @@ __device__ __forceinline__ void gcm_dit_stage(double2* z, const GcmFftStage st, 
 }
 
 // last forward stage + multiply + first inverse stage in one visit (stride 1: the R elements of a butterfly are
-// contiguous and q = 0, so no twiddles).  `table` is the multiplier of the first latitude of the block in transform
-// order (GcmGeomDev::smmzp); packed row r of the batch uses table + ((pr0 + r) / NPJ) * N (NPJ packed rows per
-// latitude, pr0 = packed rows before this batch; NPJ = 0: one table row for the whole batch).
+// contiguous and q = 0, so no twiddles).  `table` is the multiplier in transform order (GcmGeomDev::smmzp, or one row
+// of it when NPJ = 0); packed row r of the batch belongs to latitude gcm_seg_row(seg, (pr0 + r) / NPJ) (NPJ packed
+// rows per latitude, pr0 = packed rows of the launch before this batch).
 template <int R, int NPJ>
 __device__ __forceinline__ void gcm_mid_stage(double2* z, const GcmFftStage st, int nrows,
-                                              const double* __restrict__ table, int pr0, int tid, int nthr) {
+                                              const double* __restrict__ table, const GcmRowSeg seg, int pr0, int tid,
+                                              int nthr) {
   const int N = st.N;
   const int total = st.nbf * nrows;
   for (int w = tid; w < total; w += nthr) {
     const int row = gcm_fastdiv(w, st.magic_nbf), blk = w - row * st.nbf;
     double2* base = z + row * N + blk * R;
-    const double* trow = (NPJ > 0 ? table + ((pr0 + row) / (NPJ > 0 ? NPJ : 1)) * N : table) + blk * R;
+    const double* trow =
+        (NPJ > 0 ? table + (size_t)gcm_seg_row(seg, (pr0 + row) / (NPJ > 0 ? NPJ : 1)) * N : table) + blk * R;
     double2 x[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) x[t] = base[t];
@@ -137,7 +139,8 @@ __host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
 template <int NPJ>
 __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, const GcmFftPlan& plan,
                                                         const double2* __restrict__ tw,
-                                                        const double* __restrict__ table, int pr0, int tid, int nthr) {
+                                                        const double* __restrict__ table, const GcmRowSeg seg, int pr0,
+                                                        int tid, int nthr) {
   if (plan.n == 1) return;  // low_pass.py:58-59
   const int last = plan.npass - 1;
   for (int p = 0; p < last; ++p) {
@@ -149,7 +152,7 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
   }
   {
     const GcmFftStage st = gcm_fft_stage(plan, last);
-#define GCM_CALL(R) gcm_mid_stage<R, NPJ>(z, st, nrows, table, pr0, tid, nthr)
+#define GCM_CALL(R) gcm_mid_stage<R, NPJ>(z, st, nrows, table, seg, pr0, tid, nthr)
     GCM_RADIX_SWITCH(plan.radix[last], GCM_CALL)
 #undef GCM_CALL
     __syncthreads();

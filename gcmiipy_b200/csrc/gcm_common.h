@@ -96,6 +96,14 @@ __device__ __forceinline__ void gcm_prefetch_l2(const void* p) {
 #endif
 }
 
+__device__ __forceinline__ void gcm_prefetch_l1(const void* p) {
+#ifndef GCM_EMU
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // device-resident geometry tables, passed to kernels by value
 struct GcmGeomDev {
   int H, W, L;
@@ -134,6 +142,15 @@ struct gcm_geom {
   GcmGeomDev d;
   void* d_block;  // one device allocation holding every table
 };
+
+// rows of one launch: n1 rows from a, then n2 rows from c.  One segment covers a whole band; the rows next to the
+// halos (first owned row + last owned rows) form a two-segment launch once the halo exchange has landed.
+struct GcmRowSeg {
+  int a, n1, c, n2;
+};
+__host__ __device__ __forceinline__ int gcm_seg_row(const GcmRowSeg& s, int r) {
+  return r < s.n1 ? s.a + r : s.c + (r - s.n1);
+}
 
 static inline bool gcm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

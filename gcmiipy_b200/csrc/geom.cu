@@ -17,7 +17,9 @@ extern "C" const char* gcm_status_string(int s) {
     case GCM_EALIGN: return "device pointer not 16-byte aligned";
     case GCM_EUNSUP: return "unsupported combination";
     case GCM_EWORK: return "workspace too small";
-    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+    default:
+      if (s >= 1000000) return "NCCL error (status - 1000000 = ncclResult_t)";
+      return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
   }
 }
 

@@ -395,7 +395,7 @@ static int pe25_check_state(const gcm_state* s) {
 bool gcm_pe25_fast_supported(const gcm_geom* g);
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                             double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
-                            void* stream);
+                            const int* seg_r, const int* seg_u, void* stream);
 
 static int g_pe25_path = 0;  // 0 = fused ALU-lean kernels when the geometry allows, 1 = always the 4-kernel path
 
@@ -408,7 +408,8 @@ extern "C" int gcm_pe25_select_path(int path) {
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
   if (g_pe25_path == 0 && gcm_pe25_fast_supported(g))
-    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, stream);  // fv in the phi slot
+    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, nullptr, nullptr,
+                                   stream);  // fv in the phi slot
   const GcmGeomDev& d = g->d;
   const int H = d.H, W = d.W, L = d.L;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;  // member strides of the caller's arrays
@@ -478,6 +479,30 @@ extern "C" int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, cons
   Pe25Work w;
   pe25_carve(g, nbatch, ws, &w);
   return pe25_half_step_impl(g, base, star, out, dt, nbatch, w, stream);
+}
+
+// The same on explicit row segments (fused kernels only): the row phase on seg_r = {a, n1, c, n2} (n1 stored rows
+// from a, then n2 from c) and the update on seg_u.  Lets a band overlap its halo exchange with the interior rows.
+extern "C" int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base, const gcm_state* star,
+                                       const gcm_state* out, double dt, int nbatch, void* ws, size_t ws_bytes,
+                                       const int* seg_r, const int* seg_u, void* stream) {
+  GCM_REQUIRE(g && ws && seg_r && seg_u, GCM_ENULL);
+  GCM_REQUIRE(nbatch > 0, GCM_ESHAPE);
+  int st;
+  if ((st = pe25_check_state(base)) || (st = pe25_check_state(star)) || (st = pe25_check_state(out))) return st;
+  GCM_REQUIRE(gcm_aligned16(ws), GCM_EALIGN);
+  GCM_REQUIRE(ws_bytes >= gcm_pe25_workspace_bytes(g, nbatch), GCM_EWORK);
+  GCM_REQUIRE(gcm_pe25_fast_supported(g) && g_pe25_path == 0, GCM_EUNSUP);
+  const int H = g->d.H;
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int* sg = s2 ? seg_u : seg_r;
+    GCM_REQUIRE(sg[1] >= 0 && sg[3] >= 0, GCM_ESHAPE);
+    GCM_REQUIRE(sg[1] == 0 || (sg[0] >= 0 && sg[0] + sg[1] <= H), GCM_ESHAPE);
+    GCM_REQUIRE(sg[3] == 0 || (sg[2] >= 0 && sg[2] + sg[3] <= H), GCM_ESHAPE);
+  }
+  Pe25Work w;
+  pe25_carve(g, nbatch, ws, &w);
+  return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, seg_r, seg_u, stream);
 }
 
 extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt,

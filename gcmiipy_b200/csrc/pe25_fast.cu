@@ -169,7 +169,7 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
   double* __restrict__ sd = w.sd + o3;
   double* __restrict__ fv = w.fv + o3;
   double* __restrict__ pn = w.pn + o2;
-  const double* table = g.smmzp + (size_t)j0 * W;
+  const GcmRowSeg rseg{j0, rb, 0, 0};
   const double rdy = g.rdy;
 
   // start the rows of the column phases on their way to L2 while the first filter runs:
@@ -198,7 +198,7 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
       z[prl * W + i] = make_double2(x0, x1);
     });
     __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, table, pr0, tid, nthr);
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, rseg, pr0, tid, nthr);
     pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
       const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
       double* o = spu + k0 * plane + (j0 + r) * W;
@@ -280,7 +280,7 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
       z[prl * W + i] = make_double2(o[i], k0 + 1 < L ? o[plane + i] : 0.0);
     });
     __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, table, pr0, tid, nthr);
+    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, rseg, pr0, tid, nthr);
     pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
       const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
       double* o = pgf + k0 * plane + (j0 + r) * W;
@@ -293,16 +293,147 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
 }
 
 // ---------------------------------------------------------------------------------------------------
-// U: one thread per column, k loop
+// The same work as three launches (F: filter, C: columns, F: filter): every (row, layer pair) and every
+// (row group, column chunk) is its own unit of parallelism, so a latitude band of a few dozen rows (strong scaling
+// over GPUs) still fills the chip, and the column march can span RG rows (RG + 1 column evaluations per RG rows).
 // ---------------------------------------------------------------------------------------------------
-template <int L, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, int ja, int jend,
+// MODE 1: spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189);  MODE 0: x = arakawa_1977(x) in place (:202).
+// One CTA per NBAT packed rows of the flattened (row, layer pair) list of the rows of `seg`.
+template <int L, int MODE>
+__global__ void __launch_bounds__(256, 2)
+pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
+                    unsigned magicW, size_t bstride2, size_t bstride3) {
+  GCM_DYN_SMEM(double2, z);
+  constexpr int NP = (L + 1) / 2;
+  const int W = g.W, plane = g.H * W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int npr_total = (seg.n1 + seg.n2) * NP;
+  const int pr0 = blockIdx.x * NBAT;
+  const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
+  sp += blockIdx.y * bstride2;
+  in += blockIdx.y * bstride3;
+  out += blockIdx.y * bstride3;
+  pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+    const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+    const int j = gcm_seg_row(seg, r);
+    const double* s0 = in + k0 * plane + j * W;
+    double x0 = s0[i], x1 = k0 + 1 < L ? s0[plane + i] : 0.0;
+    if (MODE == 1) {
+      const double* __restrict__ spr = sp + j * W;
+      const double ph = (spr[i] + spr[gcm_ip(i, W)]) * 0.5;
+      x0 *= ph;
+      x1 *= ph;
+    }
+    z[prl * W + i] = make_double2(x0, x1);
+  });
+  __syncthreads();
+  gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, tid, nthr);
+  pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
+    const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
+    double* o = out + k0 * plane + gcm_seg_row(seg, r) * W;
+    const double2 v = z[prl * W + i];
+    o[i] = v.x;
+    if (k0 + 1 < L) o[plane + i] = v.y;
+  });
+}
+
+// Columns: one warp per (group of RG rows, chunk of 31 columns).  aflux, p_n (dynamics.py:35-46, :193-194) for the
+// group's rows, then the hydrostatic march (pf_row_step) over the group's rows and their south neighbour.
+template <int L, bool PTOP0>
+__global__ void __launch_bounds__(128, 4)
+pe25f_column_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, GcmRowSeg seg, int RG,
                     size_t bstride2, size_t bstride3) {
   const int H = g.H, W = g.W, plane = H * W;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = ja + blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= W || j >= jend) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = (W + 30) / 31, nrows = seg.n1 + seg.n2, ngrp = (nrows + RG - 1) / RG;
+  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= nchunk * ngrp) return;  // whole warps leave together
+  const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ sv = star.v + o3;
+  const double* __restrict__ st = star.t + o3;
+  const double* __restrict__ spu = w.spu + o3;
+  p += o2;
+  double* pgf = w.pgf + o3;
+  double* __restrict__ sd = w.sd + o3;
+  double* __restrict__ fv = w.fv + o3;
+  double* __restrict__ pn = w.pn + o2;
+  const double rdy = g.rdy;
+  const int grp = task / nchunk, c = task - grp * nchunk;
+  int i = c * 31 + lane;
+  const bool own = lane < 31 && i < W;
+  i = i % W;
+  // rows [j0, j0 + rg), row j0 + rg only as the south neighbour (a two-segment launch has RG = 1)
+  const int j0 = gcm_seg_row(seg, grp * RG);
+  const int rg = nrows - grp * RG < RG ? nrows - grp * RG : RG;
+
+  if (own) {
+#pragma unroll 1
+    for (int r = 0; r < rg; ++r) {
+      const int j = j0 + r;
+      const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+      const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
+      const double sp_c = sp[c2];
+      const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
+      const double rdxj = g.rdx_j[j];
+      double conv[L];
+      double pit = 0.0;
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
+        const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
+        conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
+        pit += conv[k];
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int k = L - 1; k >= 0; --k) {
+        acc += conv[k];
+        sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+      }
+      pn[c2] = p[c2] - pit * dt;
+    }
+  }
+
+  double phiA[L], rhoA[L], phiB[L], rhoB[L];
+  int jn = j0;
+  double spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, jn * W + i, 0, jn, own, true, false, phiA, rhoA, phiA,
+                                     rhoA, 0.0);
+  double spB = 0.0;
+#pragma unroll 1
+  for (int r = 1; r <= rg; r += 2) {
+    int j = gcm_row(jn, 1, H, g.wrap_j);
+    spB = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r < rg, true, phiB, rhoB, phiA,
+                                rhoA, spA);
+    jn = j;
+    if (r + 1 <= rg) {
+      j = gcm_row(jn, 1, H, g.wrap_j);
+      spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r + 1 < rg, true, phiA, rhoA,
+                                  phiB, rhoB, spB);
+      jn = j;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// U: one thread per column, k loop
+// ---------------------------------------------------------------------------------------------------
+template <int L, int MINB, bool PF>
+__global__ void __launch_bounds__(128, MINB)
+pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg, int pfd,
+                    unsigned flatW, size_t bstride2, size_t bstride3) {
+  const int H = g.H, W = g.W, plane = H * W;
+  int i, r;
+  if (flatW) {  // short rows: threads run over the (row, column) pairs of the launch in row-major order
+    const int t = blockIdx.x * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
+    r = gcm_fastdiv(t, flatW);
+    i = t - r * W;
+  } else {
+    i = blockIdx.x * blockDim.x + threadIdx.x;
+    r = blockIdx.y * blockDim.y + threadIdx.y;
+  }
+  if (i >= W || r >= seg.n1 + seg.n2) return;
+  const int j = gcm_seg_row(seg, r);
   const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
   const double* __restrict__ p = base.p + o2;
   const double* __restrict__ u = base.u + o3;
@@ -360,8 +491,24 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
   }
   const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
 
+  // pfd > 0: ask for the lines of layer k + pfd while layer k is computed (no registers held, no scoreboard)
+  auto prefetch_layer = [&](int ec, int ejp, int ejm) {
+    gcm_prefetch_l1(su + ec); gcm_prefetch_l1(su + ejp); gcm_prefetch_l1(su + ejm);
+    gcm_prefetch_l1(sv + ec); gcm_prefetch_l1(sv + ejp); gcm_prefetch_l1(sv + ejm);
+    gcm_prefetch_l1(st + ec); gcm_prefetch_l1(st + ejp); gcm_prefetch_l1(st + ejm);
+    gcm_prefetch_l1(sq + ec); gcm_prefetch_l1(sq + ejp); gcm_prefetch_l1(sq + ejm);
+    gcm_prefetch_l1(spu + ec); gcm_prefetch_l1(spu + ejp);
+    gcm_prefetch_l1(sd + ec); gcm_prefetch_l1(sd + ejp);
+    gcm_prefetch_l1(pgf + ec); gcm_prefetch_l1(fv + ec);
+    gcm_prefetch_l1(u + ec); gcm_prefetch_l1(v + ec); gcm_prefetch_l1(t + ec); gcm_prefetch_l1(q + ec);
+  };
+  if (PF) {
+    for (int k = 0; k < pfd && k < L; ++k) prefetch_layer(e_c + k * plane, e_jp + k * plane, e_jm + k * plane);
+  }
+
 #pragma unroll
   for (int k = 0; k < L; ++k) {
+    if (PF && k + pfd < L) prefetch_layer(e_c + pfd * plane, e_jp + pfd * plane, e_jm + pfd * plane);
     // fluxes through the top of layer k
     double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
     double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
@@ -422,16 +569,19 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int g_gcm_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_gcm_knob[16] = {0};
 
 // tuning knobs of the fast path (bench.py --knob i=v; 0 = automatic):
 //   0  min resident blocks per SM of the update kernel (1..4: registers per thread vs resident warps)
 //   1  update-kernel tile width in i (threads.x, multiple of 32)      2  threads of the row kernel
 //   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the row kernel (RB)
 //   5  rows per warp task of the row kernel's column phase (RG)      6  packed rows per FFT pass (NBAT)
-//   7  register budget of the row kernel: 1 = 128 regs (default), 2 = 102 regs / five 128-thread CTAs per SM
+//   7  register budget of the row kernel: 1 = 128 regs, 2 = 102 regs / five 128-thread CTAs per SM
+//   8  1 = one fused row kernel per half step, 2 = filter / column / filter as three launches
+//   9  threads of the filter kernel (three-launch form)
+//  10  update kernel: prefetch distance in layers + 1 (1 = off; default distance 1)
 extern "C" int gcm_tuning_knob(int idx, int value) {
-  GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
+  GCM_REQUIRE(idx >= 0 && idx < 16, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
   return GCM_OK;
 }
@@ -444,45 +594,93 @@ bool gcm_pe25_fast_supported(const gcm_geom* g) {
   return (size_t)d.W * sizeof(double2) <= 200 * 1024;
 }
 
+// One half step on the rows of `segR` (row phase: spu, sd, p_n, pgf, fv) and `segU` (update).  A whole grid or band
+// is one segment each (segR = owned rows + the first halo row to the south in band mode); gcm_pe25_half_step_rows
+// passes two-segment launches for the rows next to the halos.
 template <int L>
 static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out, double dt,
-                        int nbatch, const PfWork& w, void* stream) {
+                        int nbatch, const PfWork& w, GcmRowSeg segR, GcmRowSeg segU, void* stream) {
   const GcmGeomDev& d = g->d;
   const int H = d.H, W = d.W;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;
-  const int ja = d.row_lo, nrows = d.row_hi - d.row_lo;
-  const int nrows_ext = d.wrap_j ? nrows : nrows + 1;  // band: also the first halo row to the south
+  const int nrowsR = segR.n1 + segR.n2, nrowsU = segU.n1 + segU.n2;
   const size_t prsmem = (size_t)W * sizeof(double2);  // one packed row (two layers of one latitude)
   constexpr int NP = (L + 1) / 2;
-  // rows per CTA: enough for about 24 KB of packed rows, but keep at least two waves of CTAs
-  int RB = (int)((24 * 1024) / (prsmem * NP));
-  RB = RB < 1 ? 1 : (RB > 8 ? 8 : RB);
-  while (RB > 1 && (size_t)((nrows_ext + RB - 1) / RB) * nbatch < 296) --RB;
-  if (g_gcm_knob[4] > 0) RB = g_gcm_knob[4];
-  int RG = (RB + 3) / 4;
-  if (g_gcm_knob[5] > 0) RG = g_gcm_knob[5];
-  // packed rows per FFT pass: about 24 KB of shared memory, so that five or more CTAs share an SM
-  int NBAT = (int)((24 * 1024) / prsmem);
-  if (g_gcm_knob[6] > 0) NBAT = g_gcm_knob[6];
-  NBAT = NBAT < 1 ? 1 : (NBAT > RB * NP ? RB * NP : NBAT);
-  const size_t smem = NBAT * prsmem;
-  // threads per CTA (measured on B200, profiles/r01h): few CTAs (less than two per SM) want wide CTAs; long rows
-  // run five 128-thread CTAs per SM on the 102-register build; many small CTAs want two warps each
-  const size_t nctas = (size_t)((nrows_ext + RB - 1) / RB) * nbatch;
-  int variant = 0;
-  int tr = 64;
-  if (nctas < 296) tr = 192;
-  else if (W >= 512) { tr = 128; variant = 1; }
-  if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2] > 256 ? 256 : g_gcm_knob[2];
-  if (g_gcm_knob[7] > 0) variant = g_gcm_knob[7] - 1;
   const PfConst cb{base->p, base->u, base->v, base->t, base->q};
   const PfConst cs{star->p, star->u, star->v, star->t, star->q};
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
   const unsigned magicW = gcm_magic((unsigned)W);
-  // register budget of the row kernel: 128 per thread up to 256 threads (variant 0), or 102 per thread = five
-  // 128-thread CTAs per SM (variant 1)
-  if (variant == 1 && tr > 128) tr = 128;
+  const bool one_seg = segR.n2 == 0;
+  const int split = !one_seg || (g_gcm_knob[8] > 0 ? g_gcm_knob[8] == 2 : 1);
+  if (nrowsR > 0 && split) {
+    // filter launches: NBAT packed rows per CTA, about 1440 elements, but at least four CTAs per SM when possible
+    const int npr_total = nrowsR * NP;
+    int nbf = 1440 / W < 1 ? 1 : 1440 / W;
+    while (nbf > 1 && (size_t)((npr_total + nbf - 1) / nbf) * nbatch < 592) --nbf;
+    if (g_gcm_knob[6] > 0) nbf = g_gcm_knob[6];
+    int tf = (nbf * W / 12 + 31) / 32 * 32;
+    tf = tf < 32 ? 32 : (tf > 256 ? 256 : tf);
+    if (g_gcm_knob[9] > 0) tf = g_gcm_knob[9];
+    const size_t smf = nbf * prsmem;
+    const dim3 gridf((npr_total + nbf - 1) / nbf, nbatch);
+#ifndef GCM_EMU
+    if (smf > 48 * 1024) {
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+    }
+#endif
+    {
+      GcmProfScope ps(GCM_K_FILTER_A, stream);
+      GCM_LAUNCH((pe25f_filter_kernel<L, 1>), gridf, dim3(tf), smf, stream, d, star->p, star->u, w.spu, segR, nbf, magicW,
+                 b2, b3);
+    }
+    GCM_CHECK_LAUNCH();
+    // column launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
+    const int nchunk = (W + 30) / 31;
+    int rg = 4;
+    while (rg > 1 && (size_t)nchunk * ((nrowsR + rg - 1) / rg) * nbatch < 2368) rg /= 2;
+    if (g_gcm_knob[5] > 0) rg = g_gcm_knob[5];
+    if (!one_seg) rg = 1;  // a group of rows must be contiguous
+    const int ntasks = nchunk * ((nrowsR + rg - 1) / rg);
+    {
+      GcmProfScope ps(GCM_K_COLUMN_F, stream);
+      const dim3 gridc((ntasks + 3) / 4, nbatch);
+      if (ptop0)
+        GCM_LAUNCH((pe25f_column_kernel<L, true>), gridc, dim3(128), 0, stream, d, base->p, cs, w, dt, segR, rg, b2, b3);
+      else
+        GCM_LAUNCH((pe25f_column_kernel<L, false>), gridc, dim3(128), 0, stream, d, base->p, cs, w, dt, segR, rg, b2, b3);
+    }
+    GCM_CHECK_LAUNCH();
+    {
+      GcmProfScope ps(GCM_K_FILTER_B, stream);
+      GCM_LAUNCH((pe25f_filter_kernel<L, 0>), gridf, dim3(tf), smf, stream, d, star->p, w.pgf, w.pgf, segR, nbf, magicW, b2,
+                 b3);
+    }
+    GCM_CHECK_LAUNCH();
+  } else if (nrowsR > 0) {
+    // one fused row kernel (tuning knob 8 = 1): rows per CTA for about 24 KB of packed rows, at least two waves
+    const int ja = segR.a;
+    int RB = (int)((24 * 1024) / (prsmem * NP));
+    RB = RB < 1 ? 1 : (RB > 8 ? 8 : RB);
+    while (RB > 1 && (size_t)((nrowsR + RB - 1) / RB) * nbatch < 296) --RB;
+    if (g_gcm_knob[4] > 0) RB = g_gcm_knob[4];
+    int RG = (RB + 3) / 4;
+    if (g_gcm_knob[5] > 0) RG = g_gcm_knob[5];
+    int NBAT = (int)((24 * 1024) / prsmem);
+    if (g_gcm_knob[6] > 0) NBAT = g_gcm_knob[6];
+    NBAT = NBAT < 1 ? 1 : (NBAT > RB * NP ? RB * NP : NBAT);
+    const size_t smem = NBAT * prsmem;
+    // threads per CTA (measured, profiles/r01h): few CTAs want wide CTAs; long rows run five 128-thread CTAs per SM
+    // on the 102-register build; many small CTAs want two warps each
+    const size_t nctas = (size_t)((nrowsR + RB - 1) / RB) * nbatch;
+    int variant = 0;
+    int tr = 64;
+    if (nctas < 296) tr = 192;
+    else if (W >= 512) { tr = 128; variant = 1; }
+    if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2] > 256 ? 256 : g_gcm_knob[2];
+    if (g_gcm_knob[7] > 0) variant = g_gcm_knob[7] - 1;
+    if (variant == 1 && tr > 128) tr = 128;
 #ifdef GCM_EMU
 #define PF_ROW_SMEM(PT, MAXT, MINB)
 #else
@@ -495,33 +693,49 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   do {                                                                                                                 \
     PF_ROW_SMEM(PT, MAXT, MINB)                                                                                        \
     GCM_LAUNCH((pe25f_row_kernel<L, PT, MAXT, MINB>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja,         \
-               ja + nrows_ext, RB, RG, NBAT, magicW, b2, b3);                                                          \
+               ja + nrowsR, RB, RG, NBAT, magicW, b2, b3);                                                             \
   } while (0)
-  {
-    GcmProfScope ps(GCM_K_ROW, stream);
-    const dim3 grid((nrows_ext + RB - 1) / RB, nbatch);
-    if (variant == 1) {
-      if (ptop0) PF_ROW_LAUNCH(true, 128, 5); else PF_ROW_LAUNCH(false, 128, 5);
-    } else {
-      if (ptop0) PF_ROW_LAUNCH(true, 256, 2); else PF_ROW_LAUNCH(false, 256, 2);
+    {
+      GcmProfScope ps(GCM_K_ROW, stream);
+      const dim3 grid((nrowsR + RB - 1) / RB, nbatch);
+      if (variant == 1) {
+        if (ptop0) PF_ROW_LAUNCH(true, 128, 5); else PF_ROW_LAUNCH(false, 128, 5);
+      } else {
+        if (ptop0) PF_ROW_LAUNCH(true, 256, 2); else PF_ROW_LAUNCH(false, 256, 2);
+      }
     }
-  }
 #undef PF_ROW_LAUNCH
 #undef PF_ROW_SMEM
-  GCM_CHECK_LAUNCH();
-  int tx = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 32;
-  int ty = g_gcm_knob[3] > 0 ? g_gcm_knob[3] : 4;
-  if (tx * ty > 128) ty = 128 / tx;
-  {
+    GCM_CHECK_LAUNCH();
+  }
+  if (nrowsU > 0) {
+    // update: 32 x 4 (i x j) tiles; rows shorter than 128 that do not fill 32-wide tiles run flat over (row, column)
+    int tx = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 32;
+    int ty = g_gcm_knob[3] > 0 ? g_gcm_knob[3] : 4;
+    if (tx * ty > 128) ty = 128 / tx;
+    const bool flat = W < 128 && W % 32 != 0 && (size_t)nrowsU * W < (1u << 22);
+    const unsigned flatW = flat ? gcm_magic((unsigned)W) : 0u;
+    const dim3 block(tx, ty);
+    const dim3 grid = flat ? dim3((nrowsU * W + tx * ty - 1) / (tx * ty), 1, nbatch)
+                           : dim3((W + tx - 1) / tx, (nrowsU + ty - 1) / ty, nbatch);
+    const int pfd = g_gcm_knob[10] > 0 ? g_gcm_knob[10] - 1 : 1;  // prefetch distance in layers (knob: value + 1)
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
-    const dim3 grid((W + tx - 1) / tx, (nrows + ty - 1) / ty, nbatch), block(tx, ty);
-    const int je = ja + nrows;
-    switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
-      case 1: GCM_LAUNCH((pe25f_update_kernel<L, 1>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
-      case 3: GCM_LAUNCH((pe25f_update_kernel<L, 3>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
-      case 4: GCM_LAUNCH((pe25f_update_kernel<L, 4>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
-      default: GCM_LAUNCH((pe25f_update_kernel<L, 2>), grid, block, 0, stream, d, cb, cs, mo, w, dt, ja, je, b2, b3); break;
+#define PF_UPD(MINB, PF) \
+  GCM_LAUNCH((pe25f_update_kernel<L, MINB, PF>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, flatW, b2, b3)
+    if (pfd > 0) {
+      switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
+        case 2: PF_UPD(2, true); break;
+        case 3: PF_UPD(3, true); break;
+        default: PF_UPD(4, true); break;
+      }
+    } else {
+      switch (g_gcm_knob[0]) {
+        case 3: PF_UPD(3, false); break;
+        case 4: PF_UPD(4, false); break;
+        default: PF_UPD(2, false); break;
+      }
     }
+#undef PF_UPD
   }
   GCM_CHECK_LAUNCH();
   return GCM_OK;
@@ -529,8 +743,14 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
 
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                             double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
-                            void* stream) {
+                            const int* seg_r, const int* seg_u, void* stream) {
   const PfWork w{spu, sd, pgf, fv, pn};
-  if (g->d.L == 9) return pf_half_step<9>(g, base, star, out, dt, nbatch, w, stream);
-  return pf_half_step<3>(g, base, star, out, dt, nbatch, w, stream);
+  const GcmGeomDev& d = g->d;
+  const int nrows = d.row_hi - d.row_lo;
+  GcmRowSeg sr{d.row_lo, d.wrap_j ? nrows : nrows + 1, 0, 0};  // band: also the first halo row to the south
+  GcmRowSeg su{d.row_lo, nrows, 0, 0};
+  if (seg_r) sr = GcmRowSeg{seg_r[0], seg_r[1], seg_r[2], seg_r[3]};
+  if (seg_u) su = GcmRowSeg{seg_u[0], seg_u[1], seg_u[2], seg_u[3]};
+  if (d.L == 9) return pf_half_step<9>(g, base, star, out, dt, nbatch, w, sr, su, stream);
+  return pf_half_step<3>(g, base, star, out, dt, nbatch, w, sr, su, stream);
 }

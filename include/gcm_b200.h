@@ -91,6 +91,15 @@ size_t gcm_pe25_workspace_bytes(const gcm_geom* g, int nbatch);
 int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                        double dt, int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same half step restricted to explicit stored-row segments (fused kernels only, else GCM_EUNSUP):
+ * seg = {a, n1, c, n2} = n1 rows from a, then n2 rows from c.  The row phase (filtered mass flux, sigma-dot, p_n,
+ * filtered pressure-gradient force) runs on seg_r, the update on seg_u; row j of the update needs the row phase of
+ * rows j and j + 1.  A latitude band computes its interior rows while the halo exchange is in flight and the rows
+ * next to the halos afterwards.  No counterpart in the reference (single process, np.roll). */
+int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                            double dt, int nbatch, void* d_workspace, size_t workspace_bytes, const int* seg_r,
+                            const int* seg_u, void* stream);
+
 /* dynamics.matsuno_timestep (dynamics.py:230-237), `nsteps` times, whole-grid geometry (wrap_j = 1).
  * `in` is not modified; the result of the last step lands in `out`. */
 int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt, int nsteps,
@@ -146,6 +155,25 @@ int gcm_halo_unpack(const gcm_geom* g, const gcm_state* s, int row0, int nrows, 
  * neighbour memory over NVLink): dst rows [dst_row0, +nrows) <- src rows [src_row0, +nrows) */
 int gcm_halo_copy_rows(const gcm_geom* g, const gcm_state* src, int src_row0, const gcm_state* dst, int dst_row0,
                        int nrows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latitude bands across GPUs: one process per GPU, ring of bands (np.roll over j is periodic), halo rows moved with
+ * ncclSend / ncclRecv over NVLink on a side stream while the interior rows are computed.  NCCL is bound at run time
+ * (dlopen of the libnccl already in the process, e.g. torch's); status >= 1000000 = 1000000 + ncclResult_t.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gcm_comm gcm_comm;
+/* rank 0 makes the 128-byte NCCL unique id; the caller ships it to the other ranks (e.g. torch.distributed) */
+int gcm_comm_unique_id(unsigned char* h_out128);
+/* collective over the ranks of the ring; nranks == 1 needs no NCCL and no id (the ring closes on the band itself) */
+int gcm_comm_create(int nranks, int rank, const unsigned char* h_id128, gcm_comm** out);
+int gcm_comm_destroy(gcm_comm* c);
+/* dynamics.matsuno_timestep (dynamics.py:230-237) `nsteps` times on this rank's band (geometry with wrap_j = 0,
+ * 1 halo row north, 2 south).  `cur` = the band incl. halo rows (halo content is overwritten), `star` = scratch
+ * state of the same shape; the newest state ends in `nxt` if nsteps is odd, else in `cur`.  overlap = 1: interior
+ * rows run while the halos are in flight.  Bit-identical to the whole-grid step for any number of ranks. */
+int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_state* cur, const gcm_state* star,
+                          const gcm_state* nxt, double dt, int nsteps, int overlap, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 2-D schemes on a uniform doubly periodic grid.

@@ -56,6 +56,50 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend):
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
+def test_native_band_loop_single_rank(backend):
+    """gcm_band_matsuno_step (csrc/comm.cu): the C++ loop with the ring closed on the band itself.  On the GPU this
+    runs the overlapped schedule (side stream, interior rows first, two-segment launches next to the halos)."""
+    geom, s = _case()
+    whole = dynamics.Stepper(geom, *s)
+    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
+    assert band.comm is not None
+    for n in (3, 2):                                    # odd, then even: both buffer parities
+        whole.step(450.0, n)
+        band.step(450.0, n)
+        for a, b in zip(band.gather(), whole.download()):
+            assert np.array_equal(a, b)
+    band.overlap = False
+    whole.step(450.0, 1)
+    band.step(450.0, 1)
+    for a, b in zip(band.gather(), whole.download()):
+        assert np.array_equal(a, b)
+
+
+def test_half_step_on_row_segments_equals_whole_band(backend):
+    """gcm_pe25_half_step_rows: interior rows, then the rows next to the halos as one two-segment launch."""
+    import ctypes
+    from gcmiipy_b200 import _host, _lib
+    from gcmiipy_b200.dynamics import _struct, _workspace
+    geom, s = _case(H=24)
+    b = bands.BandStepper(geom, *s, rank=1, world=3, native=False)
+    rows = np.arange(b.j0 - 1, b.j1 + 2) % 24
+    full = [torch.from_numpy(np.ascontiguousarray(np.take(x, rows, axis=-2))).to(b.cur[0].device) for x in s]
+    for dst, src in zip(b.cur, full):
+        dst.copy_(src)
+    b._half(b.cur, b.cur, b.star, 450.0)
+    lo, hi = b.dg.row_lo, b.dg.row_hi
+    n = hi - lo
+    out = [torch.zeros_like(x) for x in b.cur]
+    ws, need = _workspace(b.dg, 1)
+    sb, so = _struct(b.cur), _struct(out)
+    seg = lambda *v: (ctypes.c_int * 4)(*v)
+    for sr, su in ((seg(lo + 1, n - 2, 0, 0), seg(lo + 1, n - 3, 0, 0)), (seg(lo, 1, hi - 1, 2), seg(lo, 1, hi - 2, 2))):
+        _lib.check(_lib.lib().gcm_pe25_half_step_rows(b.dg.handle, ctypes.byref(sb), ctypes.byref(sb), ctypes.byref(so),
+                                                      450.0, 1, _host.ptr(ws), need, sr, su, _lib.stream()), "rows")
+    for got, want in zip(out, b.star):
+        assert np.array_equal(got.cpu().numpy()[..., lo:hi, :], want.cpu().numpy()[..., lo:hi, :])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
