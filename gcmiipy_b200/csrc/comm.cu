@@ -3,10 +3,10 @@
 // The reference is one process: every j-shift is np.roll over the whole array (coordinates_3d.py:43-48).  Here rank r
 // owns a band of rows (all i, all k) with one halo row to the north and two to the south; ranks form a ring (the
 // roll is periodic across the pole).  Per half step the band
-//   comm stream : packs its first two / last owned rows, ncclSend/ncclRecv with both neighbours in one group,
-//                 unpacks into the halo rows;
-//   main stream : meanwhile computes the interior rows (they read owned rows only), then waits for the halos and
-//                 computes the three rows next to them (gcm_pe25_half_step_rows, two-segment launches).
+//   side stream : packs its first two / last owned rows, ncclSend/ncclRecv with both neighbours in one group,
+//                 unpacks into the halo rows, then computes the three rows next to the halos
+//                 (gcm_pe25_half_step_rows, two-segment launches);
+//   main stream : meanwhile computes the interior rows (they read owned rows only) and joins the side stream.
 // The whole loop over steps runs here, so the host cost per step is a dozen launches and two NCCL groups.
 //
 // NCCL is bound at run time (dlopen of the libnccl the process already uses -- torch's -- else the system one): the
@@ -82,7 +82,7 @@ struct gcm_comm {
   int nranks, rank;
   gcm_nccl_comm comm;
   cudaStream_t stream;          // halo traffic runs here, beside the caller's stream
-  cudaEvent_t ev_ready, ev_halo;
+  cudaEvent_t ev_ready, ev_halo, ev_rint;
   double* buf;                  // send_n | send_s | recv_s | recv_n
   size_t buf_doubles;
 };
@@ -116,6 +116,7 @@ extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128,
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rint, cudaEventDisableTiming);
   if (e != cudaSuccess) { free(c); return (int)e; }
 #else
   (void)id128;
@@ -132,6 +133,7 @@ extern "C" int gcm_comm_destroy(gcm_comm* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->ev_rint) cudaEventDestroy(c->ev_rint);
 #endif
   if (c->buf) cudaFree(c->buf);
   free(c);
@@ -183,18 +185,27 @@ static int band_half_step(const gcm_geom* g, gcm_comm* c, const gcm_state* base,
   int st;
 #ifndef GCM_EMU
   if (overlap && n >= 4) {
+    // main stream: row phase and update of the interior rows (they read owned rows only);
+    // side stream: halo exchange, then the rows next to the halos (two-segment launches), beside the interior.
+    const int none[4] = {0, 0, 0, 0};
+    const int ri[4] = {lo + 1, n - 2, 0, 0}, ui[4] = {lo + 1, n - 3, 0, 0};
+    const int rb[4] = {lo, 1, hi - 1, 2}, ub[4] = {lo, 1, hi - 2, 2};
     GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // `star` is complete on the main stream
     GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
     if ((st = band_exchange(g, c, star, c->stream))) return st;
-    GCM_CUDA(cudaEventRecord(c->ev_halo, c->stream));
-    const int ri[4] = {lo + 1, n - 2, 0, 0}, ui[4] = {lo + 1, n - 3, 0, 0};  // rows that read owned rows only
-    st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, ri, ui, main);
+    st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, ri, none, main);
     if (st == GCM_OK) {
+      GCM_CUDA(cudaEventRecord(c->ev_rint, main));  // row phase of the interior is done
+      if ((st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, none, ui, main))) return st;
+      if ((st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, rb, none, c->stream))) return st;
+      GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rint, 0));  // update of rows lo and hi-2 reads rows lo+1, hi-2
+      if ((st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, none, ub, c->stream))) return st;
+      GCM_CUDA(cudaEventRecord(c->ev_halo, c->stream));
       GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));
-      const int rb[4] = {lo, 1, hi - 1, 2}, ub[4] = {lo, 1, hi - 2, 2};  // the rows next to the halos
-      return gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, rb, ub, main);
+      return GCM_OK;
     }
     if (st != GCM_EUNSUP) return st;
+    GCM_CUDA(cudaEventRecord(c->ev_halo, c->stream));
     GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));  // no segmented kernels for this geometry: whole band now
     return gcm_pe25_half_step(g, base, star, out, dt, 1, ws, ws_bytes, main);
   }
