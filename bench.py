@@ -47,6 +47,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the newest committed `ncu --set full`
+    summary under profiles/ (tools/ncu_summary.py) that lists it; None if no capture names the kernel."""
+    import csv
+    import glob
+    base = kernel.split("<")[0]
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_summary.csv")), reverse=True):
+        with open(path) as f:
+            rows = [r for r in csv.DictReader(f) if r.get("kernel", "").startswith(base)]
+        if rows:
+            mb = [float(r["dram_read_MB"]) + float(r["dram_write_MB"]) for r in rows]
+            return {"bytes_per_launch": 1e6 * sum(mb) / len(mb), "source": os.path.relpath(path, ROOT),
+                    "launches_averaged": len(mb)}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -218,7 +234,6 @@ def run_native(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
     finite = all(bool(torch.isfinite(x).all()) for x in stepper.tensors())
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -244,6 +259,8 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_value = total_cells * args.steps / (float(tms.item()) * 1e-3)
+    # clocks / throttle reasons sampled across both timed regions (the device-resident one alone lasts ~50 ms)
+    clocks = sampler.stop() if sampler else None
 
     # ---- per-kernel timing pass (CUDA events on the launching stream) for the roofline of the dominant kernel ----
     roofline, launches_per_step = None, None
@@ -269,8 +286,10 @@ def run_native(args):
         launches_of_kind_per_step = n / psteps
         alg_bytes = b_alg(L) * cells_rank / launches_of_kind_per_step      # the kernel's share of one cell-update
         achieved = alg_bytes / (tot / n * 1e-3) / 1e9
+        traffic = ncu_traffic(name) if (args.workload == "c5" and world == 1) else None
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+                    "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                     "avg_launch_ms": tot / n, "alg_bytes_per_launch": alg_bytes,
                     "kernel_share_of_step": tot / sum(t for _, t, _ in kinds),
                     "kernels_ms_per_step": {nm: t / psteps for nm, t, _ in kinds},

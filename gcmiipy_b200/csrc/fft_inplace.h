@@ -112,6 +112,82 @@ __device__ __forceinline__ void gcm_mid_stage(double2* z, const GcmFftStage st, 
   }
 }
 
+// ---- transform fed from / drained to global memory ------------------------------------------------------------
+// IO supplies the packed rows: ctx = io.begin(row) once per butterfly (row-invariant pointers), io.load(ctx, pos) the
+// complex element at position pos of that row, io.store(ctx, pos, v) the filtered element.  The first forward stage
+// reads its R inputs straight from global memory (lanes hold consecutive positions: coalesced) and the last inverse
+// stage writes straight back, so the data crosses shared memory 2 npass - 2 times instead of 2 npass, and the two
+// copy loops with their barriers are gone.
+template <int R, class IO>
+__device__ __forceinline__ void gcm_dif_stage_first(double2* z, const GcmFftStage st, int nrows,
+                                                    const double2* __restrict__ tw, IO& io, int tid, int nthr) {
+  const int stride = st.stride, N = st.N;  // stage 0: one block per row, stride = N / R = butterflies per row
+  const int total = stride * nrows;
+  for (int w = tid; w < total; w += nthr) {
+    const int row = gcm_fastdiv(w, st.magic_nbf), q = w - row * stride;
+    const auto ctx = io.begin(row);
+    double2 x[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[t] = io.load(ctx, q + t * stride);
+    GcmButterfly<R, -1>::run(x);
+    if (q > 0) {
+      const double2* t = tw + st.twoff + q;
+#pragma unroll
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<-1>(x[m], __ldg(&t[(m - 1) * stride]));
+    }
+    double2* base = z + row * N + q;
+#pragma unroll
+    for (int m = 0; m < R; ++m) base[m * stride] = x[m];
+  }
+}
+
+template <int R, class IO>
+__device__ __forceinline__ void gcm_dit_stage_last(const double2* z, const GcmFftStage st, int nrows,
+                                                   const double2* __restrict__ tw, IO& io, int tid, int nthr) {
+  const int stride = st.stride, N = st.N;
+  const int total = stride * nrows;
+  for (int w = tid; w < total; w += nthr) {
+    const int row = gcm_fastdiv(w, st.magic_nbf), q = w - row * stride;
+    const double2* base = z + row * N + q;
+    double2 x[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) x[m] = base[m * stride];
+    if (q > 0) {
+      const double2* t = tw + st.twoff + q;
+#pragma unroll
+      for (int m = 1; m < R; ++m) x[m] = gcm_cmul_tw<+1>(x[m], __ldg(&t[(m - 1) * stride]));
+    }
+    GcmButterfly<R, +1>::run(x);
+    const auto ctx = io.begin(row);
+#pragma unroll
+    for (int t = 0; t < R; ++t) io.store(ctx, q + t * stride, x[t]);
+  }
+}
+
+// single-stage plans (N = R): global -> butterfly -> multiply -> inverse butterfly -> global, no shared memory
+template <int R, int NPJ, class IO>
+__device__ __forceinline__ void gcm_mid_stage_io(const GcmFftStage st, int nrows, const double* __restrict__ table,
+                                                 const GcmRowSeg seg, int pr0, IO& io, int tid, int nthr) {
+  for (int row = tid; row < nrows; row += nthr) {
+    const double* trow = NPJ > 0 ? table + (size_t)gcm_seg_row(seg, (pr0 + row) / (NPJ > 0 ? NPJ : 1)) * R : table;
+    const auto ctx = io.begin(row);
+    double2 x[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[t] = io.load(ctx, t);
+    GcmButterfly<R, -1>::run(x);
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const double s = __ldg(&trow[m]);
+      x[m].x *= s;
+      x[m].y *= s;
+    }
+    GcmButterfly<R, +1>::run(x);
+#pragma unroll
+    for (int t = 0; t < R; ++t) io.store(ctx, t, x[t]);
+  }
+  (void)st;
+}
+
 // true when every radix of the plan has an unrolled in-place butterfly
 __host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
   for (int p = 0; p < plan.npass; ++p)
@@ -164,4 +240,55 @@ __device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, c
 #undef GCM_CALL
     __syncthreads();
   }
+}
+
+// The same filter with the rows read from and written to global memory through `io` (see gcm_dif_stage_first).
+// z is only the inter-stage buffer; on exit it may be reused at once.
+template <int NPJ, class IO>
+__device__ __forceinline__ void gcm_filter_rows_io(double2* z, int nrows, const GcmFftPlan& plan,
+                                                   const double2* __restrict__ tw, const double* __restrict__ table,
+                                                   const GcmRowSeg seg, int pr0, IO& io, int tid, int nthr) {
+  const int last = plan.npass - 1;
+  if (last == 0) {
+    const GcmFftStage st = gcm_fft_stage(plan, 0);
+#define GCM_CALL(R) gcm_mid_stage_io<R, NPJ>(st, nrows, table, seg, pr0, io, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[0], GCM_CALL)
+#undef GCM_CALL
+    return;
+  }
+  {
+    const GcmFftStage st = gcm_fft_stage(plan, 0);
+#define GCM_CALL(R) gcm_dif_stage_first<R>(z, st, nrows, tw, io, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[0], GCM_CALL)
+#undef GCM_CALL
+    __syncthreads();
+  }
+  for (int p = 1; p < last; ++p) {
+    const GcmFftStage st = gcm_fft_stage(plan, p);
+#define GCM_CALL(R) gcm_dif_stage<R>(z, st, nrows, tw, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
+#undef GCM_CALL
+    __syncthreads();
+  }
+  {
+    const GcmFftStage st = gcm_fft_stage(plan, last);
+#define GCM_CALL(R) gcm_mid_stage<R, NPJ>(z, st, nrows, table, seg, pr0, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[last], GCM_CALL)
+#undef GCM_CALL
+    __syncthreads();
+  }
+  for (int p = last - 1; p >= 1; --p) {
+    const GcmFftStage st = gcm_fft_stage(plan, p);
+#define GCM_CALL(R) gcm_dit_stage<R>(z, st, nrows, tw, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
+#undef GCM_CALL
+    __syncthreads();
+  }
+  {
+    const GcmFftStage st = gcm_fft_stage(plan, 0);
+#define GCM_CALL(R) gcm_dit_stage_last<R>(z, st, nrows, tw, io, tid, nthr)
+    GCM_RADIX_SWITCH(plan.radix[0], GCM_CALL)
+#undef GCM_CALL
+  }
+  __syncthreads();
 }

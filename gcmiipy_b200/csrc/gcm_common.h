@@ -141,7 +141,14 @@ struct GcmGeomDev {
 struct gcm_geom {
   GcmGeomDev d;
   void* d_block;  // one device allocation holding every table
+  // side stream + fork/join events: the two independent kernel chains of a half step's row phase run side by side
+  // (pe25_fast.cu); created on first use, one user thread per geometry
+  void* aux_stream;
+  void* ev_fork;
+  void* ev_join;
 };
+// lazily creates the side stream and events; returns a cudaError_t / GCM_OK
+int gcm_geom_aux(const gcm_geom* g, void** stream, void** ev_fork, void** ev_join);
 
 // rows of one launch: n1 rows from a, then n2 rows from c.  One segment covers a whole band; the rows next to the
 // halos (first owned row + last owned rows) form a two-segment launch once the halo exchange has landed.

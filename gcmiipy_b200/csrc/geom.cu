@@ -31,6 +31,7 @@ extern "C" const char* gcm_status_string(int s) {
 static const int kRadix[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
 static const double kRadixCost[] = {10.5, 16.5, 11.33, 12.4, 13.33, 7.0, 9.33, 8.0, 4.0, 5.33, 2.0};
 static const double kPassCost = 10.0;
+extern int g_gcm_knob[16];  // pe25_fast.cu
 
 static void plan_search(int m, int first, int* cur, int ncur, double cost, int* best, int* nbest, double* bestcost) {
   if (m == 1) {
@@ -43,7 +44,7 @@ static void plan_search(int m, int first, int* cur, int ncur, double cost, int* 
   }
   if (ncur >= 12 || cost >= *bestcost) return;
   for (int f = first; f < (int)(sizeof(kRadix) / sizeof(int)); ++f)
-    if (m % kRadix[f] == 0) {
+    if (m % kRadix[f] == 0 && (g_gcm_knob[12] <= 0 || kRadix[f] <= g_gcm_knob[12])) {  // knob 12: largest radix
       cur[ncur] = kRadix[f];
       plan_search(m / kRadix[f], f, cur, ncur + 1, cost + kRadixCost[f] + kPassCost, best, nbest, bestcost);
     }
@@ -229,8 +230,33 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   return GCM_OK;
 }
 
+int gcm_geom_aux(const gcm_geom* cg, void** stream, void** ev_fork, void** ev_join) {
+  gcm_geom* g = const_cast<gcm_geom*>(cg);
+#ifndef GCM_EMU
+  if (!g->aux_stream) {
+    cudaStream_t q;
+    cudaEvent_t a, b;
+    GCM_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    GCM_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    GCM_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    g->aux_stream = q;
+    g->ev_fork = a;
+    g->ev_join = b;
+  }
+#endif
+  *stream = g->aux_stream;
+  *ev_fork = g->ev_fork;
+  *ev_join = g->ev_join;
+  return GCM_OK;
+}
+
 extern "C" int gcm_geom_destroy(gcm_geom* g) {
   if (!g) return GCM_OK;
+#ifndef GCM_EMU
+  if (g->aux_stream) cudaStreamDestroy((cudaStream_t)g->aux_stream);
+  if (g->ev_fork) cudaEventDestroy((cudaEvent_t)g->ev_fork);
+  if (g->ev_join) cudaEventDestroy((cudaEvent_t)g->ev_join);
+#endif
   cudaFree(g->d_block);
   free(g);
   return GCM_OK;

@@ -299,50 +299,106 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
 // ---------------------------------------------------------------------------------------------------
 // MODE 1: spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189);  MODE 0: x = arakawa_1977(x) in place (:202).
 // One CTA per NBAT packed rows of the flattened (row, layer pair) list of the rows of `seg`.
+// rows of the filter kernel as seen by the transform (fft_inplace.h: gcm_filter_rows_io)
 template <int L, int MODE>
-__global__ void __launch_bounds__(256, 2)
+struct PfFilterIO {
+  const double* __restrict__ sp;
+  const double* in;
+  double* out;
+  GcmRowSeg seg;
+  int pr0, W, plane;
+  struct Ctx {
+    const double* s0;
+    const double* spr;
+    double* o;
+    bool two;
+  };
+  __device__ __forceinline__ Ctx begin(int row) const {
+    constexpr int NP = (L + 1) / 2;
+    const int pr = pr0 + row, r = pr / NP, k0 = 2 * (pr - r * NP);
+    const int j = gcm_seg_row(seg, r);
+    Ctx c;
+    c.s0 = in + k0 * plane + j * W;
+    c.spr = sp + j * W;
+    c.o = out + k0 * plane + j * W;
+    c.two = k0 + 1 < L;
+    return c;
+  }
+  __device__ __forceinline__ double2 load(const Ctx& c, int i) const {
+    double x0 = c.s0[i], x1 = c.two ? c.s0[plane + i] : 0.0;
+    if (MODE == 1) {  // su * iph(sp)  (dynamics.py:187)
+      const double ph = (c.spr[i] + c.spr[gcm_ip(i, W)]) * 0.5;
+      x0 *= ph;
+      x1 *= ph;
+    }
+    return make_double2(x0, x1);
+  }
+  __device__ __forceinline__ void store(const Ctx& c, int i, double2 v) const {
+    c.o[i] = v.x;
+    if (c.two) c.o[plane + i] = v.y;
+  }
+};
+
+template <int L, int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
                     unsigned magicW, size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double2, z);
   constexpr int NP = (L + 1) / 2;
-  const int W = g.W, plane = g.H * W;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int W = g.W;
   const int npr_total = (seg.n1 + seg.n2) * NP;
   const int pr0 = blockIdx.x * NBAT;
   const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
-  sp += blockIdx.y * bstride2;
-  in += blockIdx.y * bstride3;
-  out += blockIdx.y * bstride3;
-  pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-    const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-    const int j = gcm_seg_row(seg, r);
-    const double* s0 = in + k0 * plane + j * W;
-    double x0 = s0[i], x1 = k0 + 1 < L ? s0[plane + i] : 0.0;
-    if (MODE == 1) {
-      const double* __restrict__ spr = sp + j * W;
-      const double ph = (spr[i] + spr[gcm_ip(i, W)]) * 0.5;
-      x0 *= ph;
-      x1 *= ph;
-    }
-    z[prl * W + i] = make_double2(x0, x1);
-  });
-  __syncthreads();
-  gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, tid, nthr);
-  pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-    const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-    double* o = out + k0 * plane + gcm_seg_row(seg, r) * W;
-    const double2 v = z[prl * W + i];
-    o[i] = v.x;
-    if (k0 + 1 < L) o[plane + i] = v.y;
-  });
+  PfFilterIO<L, MODE> io{sp + blockIdx.y * bstride2, in + blockIdx.y * bstride3, out + blockIdx.y * bstride3, seg, pr0, W,
+                         g.H * W};
+  gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
+  (void)magicW;
 }
 
-// Columns: one warp per (group of RG rows, chunk of 31 columns).  aflux, p_n (dynamics.py:35-46, :193-194) for the
-// group's rows, then the hydrostatic march (pf_row_step) over the group's rows and their south neighbour.
+// aflux (dynamics.py:35-46) and p_n (:193-194): one thread per column of the rows of `seg`; needs the filtered spu.
+template <int L>
+__global__ void __launch_bounds__(128)
+pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ sp_,
+                   const double* __restrict__ sv_, PfWork w, double dt, GcmRowSeg seg, unsigned magicW, size_t bstride2,
+                   size_t bstride3) {
+  const int H = g.H, W = g.W, plane = H * W;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gcm_fastdiv(t, magicW), i = t - r * W;
+  if (r >= seg.n1 + seg.n2) return;
+  const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
+  const double* __restrict__ sp = sp_ + o2;
+  const double* __restrict__ sv = sv_ + o3;
+  const double* __restrict__ spu = w.spu + o3;
+  double* __restrict__ sd = w.sd + o3;
+  const int j = gcm_seg_row(seg, r);
+  const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+  const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
+  const double sp_c = sp[c2];
+  const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
+  const double rdxj = g.rdx_j[j], rdy = g.rdy;
+  double conv[L];
+  double pit = 0.0;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
+    const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
+    conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
+    pit += conv[k];
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int k = L - 1; k >= 0; --k) {
+    acc += conv[k];
+    sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+  }
+  w.pn[o2 + c2] = p[o2 + c2] - pit * dt;
+}
+
+// Hydrostatic columns: one warp per (group of RG rows, chunk of 31 columns) marches south over the group's rows and
+// their south neighbour (pf_row_step): pgfu + phiu (unfiltered) -> pgf, fv = phiv + pgv.  Independent of spu.
 template <int L, bool PTOP0>
 __global__ void __launch_bounds__(128, 4)
-pe25f_column_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, GcmRowSeg seg, int RG,
-                    size_t bstride2, size_t bstride3) {
+pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, size_t bstride2, size_t bstride3) {
   const int H = g.H, W = g.W, plane = H * W;
   const int lane = threadIdx.x & 31;
   const int nchunk = (W + 30) / 31, nrows = seg.n1 + seg.n2, ngrp = (nrows + RG - 1) / RG;
@@ -350,15 +406,9 @@ pe25f_column_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, Pf
   if (task >= nchunk * ngrp) return;  // whole warps leave together
   const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
   const double* __restrict__ sp = star.p + o2;
-  const double* __restrict__ sv = star.v + o3;
   const double* __restrict__ st = star.t + o3;
-  const double* __restrict__ spu = w.spu + o3;
-  p += o2;
   double* pgf = w.pgf + o3;
-  double* __restrict__ sd = w.sd + o3;
   double* __restrict__ fv = w.fv + o3;
-  double* __restrict__ pn = w.pn + o2;
-  const double rdy = g.rdy;
   const int grp = task / nchunk, c = task - grp * nchunk;
   int i = c * 31 + lane;
   const bool own = lane < 31 && i < W;
@@ -366,35 +416,6 @@ pe25f_column_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, Pf
   // rows [j0, j0 + rg), row j0 + rg only as the south neighbour (a two-segment launch has RG = 1)
   const int j0 = gcm_seg_row(seg, grp * RG);
   const int rg = nrows - grp * RG < RG ? nrows - grp * RG : RG;
-
-  if (own) {
-#pragma unroll 1
-    for (int r = 0; r < rg; ++r) {
-      const int j = j0 + r;
-      const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
-      const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
-      const double sp_c = sp[c2];
-      const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
-      const double rdxj = g.rdx_j[j];
-      double conv[L];
-      double pit = 0.0;
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
-        const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
-        conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
-        pit += conv[k];
-      }
-      double acc = 0.0;
-#pragma unroll
-      for (int k = L - 1; k >= 0; --k) {
-        acc += conv[k];
-        sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
-      }
-      pn[c2] = p[c2] - pit * dt;
-    }
-  }
-
   double phiA[L], rhoA[L], phiB[L], rhoB[L];
   int jn = j0;
   double spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, jn * W + i, 0, jn, own, true, false, phiA, rhoA, phiA,
@@ -421,7 +442,7 @@ pe25f_column_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, Pf
 template <int L, int MINB, bool PF>
 __global__ void __launch_bounds__(128, MINB)
 pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg, int pfd,
-                    unsigned flatW, size_t bstride2, size_t bstride3) {
+                    int pf2, unsigned flatW, size_t bstride2, size_t bstride3) {
   const int H = g.H, W = g.W, plane = H * W;
   int i, r;
   if (flatW) {  // short rows: threads run over the (row, column) pairs of the launch in row-major order
@@ -502,12 +523,24 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
     gcm_prefetch_l1(pgf + ec); gcm_prefetch_l1(fv + ec);
     gcm_prefetch_l1(u + ec); gcm_prefetch_l1(v + ec); gcm_prefetch_l1(t + ec); gcm_prefetch_l1(q + ec);
   };
+  // pf2 > 0: the lines of this thread's own column (the ones that come from HBM) of layer k + pf2 are asked into L2
+  // by two lanes per warp-row (one per 128-byte line)
+  const bool pf2_lane = PF && pf2 > 0 && (threadIdx.x & 15) == 0;
+  auto prefetch_l2_layer = [&](int ec) {
+    gcm_prefetch_l2(su + ec); gcm_prefetch_l2(sv + ec); gcm_prefetch_l2(st + ec); gcm_prefetch_l2(sq + ec);
+    gcm_prefetch_l2(spu + ec); gcm_prefetch_l2(sd + ec); gcm_prefetch_l2(pgf + ec); gcm_prefetch_l2(fv + ec);
+    gcm_prefetch_l2(u + ec); gcm_prefetch_l2(v + ec); gcm_prefetch_l2(t + ec); gcm_prefetch_l2(q + ec);
+  };
+  if (pf2_lane) {
+    for (int k = 0; k < pf2 && k < L; ++k) prefetch_l2_layer(e_c + k * plane);
+  }
   if (PF) {
     for (int k = 0; k < pfd && k < L; ++k) prefetch_layer(e_c + k * plane, e_jp + k * plane, e_jm + k * plane);
   }
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
+    if (pf2_lane && k + pf2 < L) prefetch_l2_layer(e_c + pf2 * plane);
     if (PF && k + pfd < L) prefetch_layer(e_c + pfd * plane, e_jp + pfd * plane, e_jm + pfd * plane);
     // fluxes through the top of layer k
     double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
@@ -580,6 +613,10 @@ int g_gcm_knob[16] = {0};
 //   8  1 = one fused row kernel per half step, 2 = filter / column / filter as three launches
 //   9  threads of the filter kernel (three-launch form)
 //  10  update kernel: prefetch distance in layers + 1 (1 = off; default distance 1)
+//  14  update kernel: L2 prefetch distance in layers for the thread's own column (0 = off)
+//  11  1 = the two chains of the row phase one after the other on the caller's stream (default: side by side)
+//  12  largest FFT radix the planner may use (set before the geometry is created; 0 = 16)
+//  13  1 = filter kernel with 168 registers per thread (three CTAs per SM)
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 16, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
@@ -614,6 +651,24 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const bool one_seg = segR.n2 == 0;
   const int split = !one_seg || (g_gcm_knob[8] > 0 ? g_gcm_knob[8] == 2 : 1);
   if (nrowsR > 0 && split) {
+    // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run
+    // side by side (caller's stream + the geometry's side stream): the filters are bound by shared memory and latency,
+    // the column kernels by HBM and FP64, so each fills the other's gaps.  Knob 11 = 1: one after the other.
+    cudaStream_t qa = (cudaStream_t)stream, qb = (cudaStream_t)stream;
+#ifndef GCM_EMU
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool side = one_seg && g_gcm_knob[11] != 1;
+    if (side) {
+      void *q2, *e1, *e2;
+      int st2 = gcm_geom_aux(g, &q2, &e1, &e2);
+      if (st2) return st2;
+      qb = (cudaStream_t)q2;
+      ev_fork = (cudaEvent_t)e1;
+      ev_join = (cudaEvent_t)e2;
+      GCM_CUDA(cudaEventRecord(ev_fork, qa));
+      GCM_CUDA(cudaStreamWaitEvent(qb, ev_fork, 0));
+    }
+#endif
     // filter launches: NBAT packed rows per CTA, about 1440 elements, but at least four CTAs per SM when possible
     const int npr_total = nrowsR * NP;
     int nbf = 1440 / W < 1 ? 1 : 1440 / W;
@@ -624,19 +679,16 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     if (g_gcm_knob[9] > 0) tf = g_gcm_knob[9];
     const size_t smf = nbf * prsmem;
     const dim3 gridf((npr_total + nbf - 1) / nbf, nbatch);
+    const bool wide_regs = g_gcm_knob[13] == 1 && tf <= 128;  // knob 13 = 1: 168 registers, three CTAs per SM
 #ifndef GCM_EMU
     if (smf > 48 * 1024) {
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smf));
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smf));
     }
 #endif
-    {
-      GcmProfScope ps(GCM_K_FILTER_A, stream);
-      GCM_LAUNCH((pe25f_filter_kernel<L, 1>), gridf, dim3(tf), smf, stream, d, star->p, star->u, w.spu, segR, nbf, magicW,
-                 b2, b3);
-    }
-    GCM_CHECK_LAUNCH();
-    // column launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
+    // hydro launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
     const int nchunk = (W + 30) / 31;
     int rg = 4;
     while (rg > 1 && (size_t)nchunk * ((nrowsR + rg - 1) / rg) * nbatch < 2368) rg /= 2;
@@ -644,20 +696,47 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     if (!one_seg) rg = 1;  // a group of rows must be contiguous
     const int ntasks = nchunk * ((nrowsR + rg - 1) / rg);
     {
-      GcmProfScope ps(GCM_K_COLUMN_F, stream);
-      const dim3 gridc((ntasks + 3) / 4, nbatch);
-      if (ptop0)
-        GCM_LAUNCH((pe25f_column_kernel<L, true>), gridc, dim3(128), 0, stream, d, base->p, cs, w, dt, segR, rg, b2, b3);
+      GcmProfScope ps(GCM_K_FILTER_A, qa);
+      if (wide_regs)
+        GCM_LAUNCH((pe25f_filter_kernel<L, 1, 128, 3>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf,
+                   magicW, b2, b3);
       else
-        GCM_LAUNCH((pe25f_column_kernel<L, false>), gridc, dim3(128), 0, stream, d, base->p, cs, w, dt, segR, rg, b2, b3);
+        GCM_LAUNCH((pe25f_filter_kernel<L, 1, 256, 2>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf,
+                   magicW, b2, b3);
     }
     GCM_CHECK_LAUNCH();
     {
-      GcmProfScope ps(GCM_K_FILTER_B, stream);
-      GCM_LAUNCH((pe25f_filter_kernel<L, 0>), gridf, dim3(tf), smf, stream, d, star->p, w.pgf, w.pgf, segR, nbf, magicW, b2,
+      GcmProfScope ps(GCM_K_COLUMN_F, qb);
+      const dim3 gridc((ntasks + 3) / 4, nbatch);
+      if (ptop0)
+        GCM_LAUNCH((pe25f_hydro_kernel<L, true>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+      else
+        GCM_LAUNCH((pe25f_hydro_kernel<L, false>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+    }
+    GCM_CHECK_LAUNCH();
+    {
+      GcmProfScope ps(GCM_K_AFLUX_F, qa);
+      const dim3 grida((nrowsR * W + 127) / 128, nbatch);
+      GCM_LAUNCH((pe25f_aflux_kernel<L>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR, magicW, b2,
                  b3);
     }
     GCM_CHECK_LAUNCH();
+    {
+      GcmProfScope ps(GCM_K_FILTER_B, qb);
+      if (wide_regs)
+        GCM_LAUNCH((pe25f_filter_kernel<L, 0, 128, 3>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf,
+                   magicW, b2, b3);
+      else
+        GCM_LAUNCH((pe25f_filter_kernel<L, 0, 256, 2>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf,
+                   magicW, b2, b3);
+    }
+    GCM_CHECK_LAUNCH();
+#ifndef GCM_EMU
+    if (side) {
+      GCM_CUDA(cudaEventRecord(ev_join, qb));
+      GCM_CUDA(cudaStreamWaitEvent(qa, ev_join, 0));
+    }
+#endif
   } else if (nrowsR > 0) {
     // one fused row kernel (tuning knob 8 = 1): rows per CTA for about 24 KB of packed rows, at least two waves
     const int ja = segR.a;
@@ -721,7 +800,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const int pfd = g_gcm_knob[10] > 0 ? g_gcm_knob[10] - 1 : 1;  // prefetch distance in layers (knob: value + 1)
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
 #define PF_UPD(MINB, PF) \
-  GCM_LAUNCH((pe25f_update_kernel<L, MINB, PF>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, flatW, b2, b3)
+  GCM_LAUNCH((pe25f_update_kernel<L, MINB, PF>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, g_gcm_knob[14], flatW, b2, b3)
     if (pfd > 0) {
       switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
         case 2: PF_UPD(2, true); break;

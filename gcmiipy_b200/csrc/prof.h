@@ -11,9 +11,10 @@ enum GcmProfKind {
   GCM_K_ROW = 4,          // pe25f_row_kernel    (pe25_fast.cu)
   GCM_K_UPDATE_FAST = 5,  // pe25f_update_kernel (pe25_fast.cu)
   GCM_K_FILTER_A = 6,     // pe25f_filter_kernel<1>
-  GCM_K_COLUMN_F = 7,     // pe25f_column_kernel
+  GCM_K_COLUMN_F = 7,     // pe25f_hydro_kernel
   GCM_K_FILTER_B = 8,     // pe25f_filter_kernel<0>
-  GCM_K_COUNT = 9
+  GCM_K_AFLUX_F = 9,      // pe25f_aflux_kernel
+  GCM_K_COUNT = 10
 };
 
 #ifdef GCM_EMU

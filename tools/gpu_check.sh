@@ -17,6 +17,6 @@ if [ -z "$2" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
   echo "ncu launches exit $?"
   $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:pe25_ -s 40 -c 8 -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:pe25f -s 40 -c 10 -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
   echo "ncu full exit $?"
 fi
