@@ -104,6 +104,28 @@ __device__ __forceinline__ void gcm_prefetch_l1(const void* p) {
 #endif
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard; completion by group
+__device__ __forceinline__ void gcm_cp_async8(double* smem_dst, const double* gmem_src) {
+#ifdef GCM_EMU
+  *smem_dst = *gmem_src;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void gcm_cp_async_commit() {
+#ifndef GCM_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// wait until at most N of this thread's committed groups are still in flight
+template <int N>
+__device__ __forceinline__ void gcm_cp_async_wait() {
+#ifndef GCM_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // device-resident geometry tables, passed to kernels by value
 struct GcmGeomDev {
   int H, W, L;

@@ -513,15 +513,21 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
   const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
 
   // pfd > 0: ask for the lines of layer k + pfd while layer k is computed (no registers held, no scoreboard)
+  // the rows to the north / south are prefetched by the tile's own threads of those rows, except at the tile's edges
+  const bool pf_n = pf2 < 0 ? (threadIdx.y == 0 || flatW != 0) : true;
+  const bool pf_s = pf2 < 0 ? (threadIdx.y + 1 == blockDim.y || flatW != 0) : true;
   auto prefetch_layer = [&](int ec, int ejp, int ejm) {
-    gcm_prefetch_l1(su + ec); gcm_prefetch_l1(su + ejp); gcm_prefetch_l1(su + ejm);
-    gcm_prefetch_l1(sv + ec); gcm_prefetch_l1(sv + ejp); gcm_prefetch_l1(sv + ejm);
-    gcm_prefetch_l1(st + ec); gcm_prefetch_l1(st + ejp); gcm_prefetch_l1(st + ejm);
-    gcm_prefetch_l1(sq + ec); gcm_prefetch_l1(sq + ejp); gcm_prefetch_l1(sq + ejm);
-    gcm_prefetch_l1(spu + ec); gcm_prefetch_l1(spu + ejp);
-    gcm_prefetch_l1(sd + ec); gcm_prefetch_l1(sd + ejp);
+    gcm_prefetch_l1(su + ec); gcm_prefetch_l1(sv + ec); gcm_prefetch_l1(st + ec); gcm_prefetch_l1(sq + ec);
+    gcm_prefetch_l1(spu + ec); gcm_prefetch_l1(sd + ec);
     gcm_prefetch_l1(pgf + ec); gcm_prefetch_l1(fv + ec);
     gcm_prefetch_l1(u + ec); gcm_prefetch_l1(v + ec); gcm_prefetch_l1(t + ec); gcm_prefetch_l1(q + ec);
+    if (pf_s) {
+      gcm_prefetch_l1(su + ejp); gcm_prefetch_l1(sv + ejp); gcm_prefetch_l1(st + ejp); gcm_prefetch_l1(sq + ejp);
+      gcm_prefetch_l1(spu + ejp); gcm_prefetch_l1(sd + ejp);
+    }
+    if (pf_n) {
+      gcm_prefetch_l1(su + ejm); gcm_prefetch_l1(sv + ejm); gcm_prefetch_l1(st + ejm); gcm_prefetch_l1(sq + ejm);
+    }
   };
   // pf2 > 0: the lines of this thread's own column (the ones that come from HBM) of layer k + pf2 are asked into L2
   // by two lanes per warp-row (one per 128-byte line)
@@ -600,6 +606,186 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// U, tiled: the same update with every operand staged in shared memory by 8-byte asynchronous copies (LDGSTS), three
+// layers in flight.  A CTA owns a 32 x 4 (i x j) tile; per layer it stages the 34 x 6 halo tile of su, sv, st, sq, spu,
+// sd (each thread its own column, 76 threads one halo-ring element each, periodic wrap resolved per element).  The
+// stencil reads of the k loop hit shared memory only: the HBM latency is carried by the copy queue instead of by
+// registers and resident warps; the six values a cell reads once (pgf, fv, u, v, t, q) come straight from global
+// memory.  Needs W % 32 == 0; one launch per row segment.
+// ---------------------------------------------------------------------------------------------------
+#define PFT_TI 32
+#define PFT_TJ 4
+#define PFT_ROW (PFT_TI + 2)
+#define PFT_TILE ((PFT_TJ + 2) * PFT_ROW)
+#define PFT_STAGE (6 * PFT_TILE)  // doubles per stage
+
+template <int L, int PFT_NS>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 4)
+pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
+                          size_t bstride2, size_t bstride3) {
+  GCM_DYN_SMEM(double, sm);
+  const int H = g.H, W = g.W, plane = H * W, wrap = g.wrap_j;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PFT_TI + tx;
+  const int i = blockIdx.x * PFT_TI + tx;
+  const int r = blockIdx.y * PFT_TJ + ty;
+  const bool active = r < seg.n1;
+  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile; rows past the segment still exist in memory
+  int j = j0 + ty;
+  if (wrap && j >= H) j -= H;
+  const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
+  const double* __restrict__ p = base.p + o2;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ pn = w.pn + o2;
+  // staged fields: 0..5 with halo (su, sv, st, sq, spu, sd), 6..11 own column only (pgf, fv, u, v, t, q)
+  const double* fld[12] = {star.u + o3, star.v + o3, star.t + o3, star.q + o3, w.spu + o3, w.sd + o3,
+                           w.pgf + o3,  w.fv + o3,   base.u + o3, base.v + o3, base.t + o3, base.q + o3};
+  double* __restrict__ ou = out.u + o3;
+  double* __restrict__ ov = out.v + o3;
+  double* __restrict__ ot = out.t + o3;
+  double* __restrict__ oq = out.q + o3;
+
+  const int jm = gcm_row(j, -1, H, wrap), jp = gcm_row(j, 1, H, wrap), jpp = gcm_row(jp, 1, H, wrap);
+  const int im = gcm_im(i, W), ip = gcm_ip(i, W);
+  const int e_c = j * W + i;
+  // halo ring of the tile: north row, south row, west column, east column -> (tile row, tile column, global offset)
+  int hr = 0, hc = 0, e_h = 0;
+  const bool has_halo = tid < 2 * PFT_ROW + 2 * PFT_TJ;
+  if (has_halo) {
+    int rr, cc;  // tile coordinates, -1 .. TJ and -1 .. TI
+    if (tid < PFT_ROW) { rr = -1; cc = tid - 1; }
+    else if (tid < 2 * PFT_ROW) { rr = PFT_TJ; cc = tid - PFT_ROW - 1; }
+    else if (tid < 2 * PFT_ROW + PFT_TJ) { rr = tid - 2 * PFT_ROW; cc = -1; }
+    else { rr = tid - 2 * PFT_ROW - PFT_TJ; cc = PFT_TI; }
+    int gj = j0 + rr, gi = blockIdx.x * PFT_TI + cc;
+    if (wrap) gj = gj < 0 ? gj + H : (gj >= H ? gj - H : gj);
+    gi = gi < 0 ? gi + W : (gi >= W ? gi - W : gi);
+    hr = rr + 1;
+    hc = cc + 1;
+    e_h = gj * W + gi;
+  }
+  const int t_c = (ty + 1) * PFT_ROW + (tx + 1);  // own position in a tile
+  const int t_h = hr * PFT_ROW + hc;
+
+  auto issue = [&](int k, int s) {  // stage layer k into stage s
+    double* st = sm + s * PFT_STAGE;
+    const int off = k * plane;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) gcm_cp_async8(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
+    if (has_halo) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) gcm_cp_async8(st + f * PFT_TILE + t_h, fld[f] + off + e_h);
+    }
+    gcm_cp_async_commit();
+  };
+  // layers 0 .. NS-2 are issued up front; iteration k then issues layer k + NS - 1 into the stage layer k - 1 left
+#pragma unroll
+  for (int k = 0; k < PFT_NS - 1; ++k)
+    if (k < L) issue(k, k);
+
+  // per-column (2-D) factors while the first layers are on their way
+  const double rdxj = g.rdx_j[j], rdxh = g.rdx_h[j], rdy = g.rdy;
+  const double p_c = p[e_c], p_ip = p[j * W + ip], p_jp = p[jp * W + i];
+  const double pn_c = pn[e_c], pn_ip = pn[j * W + ip], pn_jp = pn[jp * W + i];
+  const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                    // calc_pu / calc_pv
+  const double r_pnu = 1.0 / ((pn_c + pn_ip) * 0.5), r_pnv = 1.0 / ((pn_c + pn_jp) * 0.5);  // un_pu / un_pv
+  const double r_pn = 1.0 / pn_c;
+  const double sp_c = sp[e_c], sp_ip = sp[j * W + ip], sp_jp = sp[jp * W + i], sp_jm = sp[jm * W + i];
+  const double a_c = (sp_c + sp_jp) * 0.5;                     // jph(sp) at (j, i)
+  const double a_ip = (sp_ip + sp[jp * W + ip]) * 0.5;         // (j, i+1)
+  const double a_jm = (sp_jm + sp_c) * 0.5;                    // (j-1, i)
+  const double a_jm_ip = (sp[jm * W + ip] + sp_ip) * 0.5;      // (j-1, i+1)
+  const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;         // (j+1, i)
+  const bool zero_v = j == g.zero_v_row;
+  // layer L-1 pairs with layer 0 through the bottom of layer 0 (np.roll), times sd[0] = 0
+  const double u_top = fld[0][(L - 1) * plane + e_c], v_top = fld[1][(L - 1) * plane + e_c],
+               t_top = fld[2][(L - 1) * plane + e_c], q_top = fld[3][(L - 1) * plane + e_c];
+  (void)im;
+
+  gcm_cp_async_wait<PFT_NS - 3>();  // layers 0 and 1 have landed
+  __syncthreads();
+  if (PFT_NS - 1 < L) issue(PFT_NS - 1, PFT_NS - 1);
+  const double* s0 = sm;
+  double u_k = s0[0 * PFT_TILE + t_c], v_k = s0[1 * PFT_TILE + t_c], t_k = s0[2 * PFT_TILE + t_c],
+         q_k = s0[3 * PFT_TILE + t_c];
+  double sd_c = s0[5 * PFT_TILE + t_c], sd_ip = s0[5 * PFT_TILE + t_c + 1], sd_jp = s0[5 * PFT_TILE + t_c + PFT_ROW];
+  double fu = (u_k + u_top) * 0.5 * ((sd_c + sd_ip) * 0.5);
+  double fv_ = (v_k + v_top) * 0.5 * ((sd_c + sd_jp) * 0.5);
+  double ft = (t_k + t_top) * 0.5 * sd_c;
+  double fq = (q_k + q_top) * 0.5 * sd_c;
+  const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
+
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    if (k > 0) {  // layers k and k + 1 have landed; the stage of layer k - 1 is free for layer k + NS - 1
+      gcm_cp_async_wait<PFT_NS - 3>();
+      __syncthreads();
+      if (k + PFT_NS - 1 < L) issue(k + PFT_NS - 1, (k + PFT_NS - 1) % PFT_NS);
+      else gcm_cp_async_commit();  // keep one group per iteration so that the wait count stays exact
+    }
+    const double* sk = sm + (k % PFT_NS) * PFT_STAGE;
+    const double* sn = sm + ((k + 1) % PFT_NS) * PFT_STAGE;
+    // this cell's pgf, fv, u, v, t, q: read once, straight from global memory, consumed at the end of the layer
+    const int e = k * plane + e_c;
+    const double own_pgf = fld[6][e], own_fv = fld[7][e], own_u = fld[8][e], own_v = fld[9][e], own_t = fld[10][e],
+                 own_q = fld[11][e];
+    // fluxes through the top of layer k
+    double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
+    double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
+    if (k + 1 < L) {
+      u_kp = sn[0 * PFT_TILE + t_c]; v_kp = sn[1 * PFT_TILE + t_c]; t_kp = sn[2 * PFT_TILE + t_c];
+      q_kp = sn[3 * PFT_TILE + t_c];
+      sd_c = sn[5 * PFT_TILE + t_c]; sd_ip = sn[5 * PFT_TILE + t_c + 1]; sd_jp = sn[5 * PFT_TILE + t_c + PFT_ROW];
+      fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
+      fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
+      ft_n = (t_kp + t_k) * 0.5 * sd_c;
+      fq_n = (q_kp + q_k) * 0.5 * sd_c;
+    }
+    const double rds = g.c_rdsig[k];
+    const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;  // -(F_k - F_k+1) / dsig
+    const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
+
+    // horizontal neighbours from the tile
+    const double* su_ = sk + 0 * PFT_TILE + t_c;
+    const double* sv_ = sk + 1 * PFT_TILE + t_c;
+    const double* st_ = sk + 2 * PFT_TILE + t_c;
+    const double* sq_ = sk + 3 * PFT_TILE + t_c;
+    const double* pu_ = sk + 4 * PFT_TILE + t_c;
+    const double u_im = su_[-1], u_ip = su_[1], u_jp = su_[PFT_ROW], u_jm = su_[-PFT_ROW];
+    const double v_im = sv_[-1], v_ip = sv_[1], v_jp = sv_[PFT_ROW], v_jm = sv_[-PFT_ROW], v_jm_ip = sv_[1 - PFT_ROW];
+    const double pu_c = pu_[0], pu_im = pu_[-1], pu_ip = pu_[1], pu_jp = pu_[PFT_ROW], pu_jp_im = pu_[PFT_ROW - 1];
+    const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
+                 pv_jp = v_jp * a_jp;
+
+    // advec_m_pu (dynamics.py:55-108); (a/2)(b/2) = ab/4 exactly
+    const double puum = (u_k + u_im) * (pu_c + pu_im), puup = (u_ip + u_k) * (pu_ip + pu_c);
+    const double puvp = (pv_c + pv_ip) * (u_k + u_jp), puvm = (pv_jm + pv_jm_ip) * (u_jm + u_k);
+    const double dut = ((puum - puup) * rdxj + (puvm - puvp) * rdy) * 0.25;
+    const double pvvm = (v_k + v_jm) * (pv_c + pv_jm), pvvp = (v_jp + v_k) * (pv_jp + pv_c);
+    const double pvup = (v_k + v_ip) * (pu_c + pu_jp), pvum = (v_im + v_k) * (pu_im + pu_jp_im);
+    const double dvt = ((pvvm - pvvp) * rdy + (pvum - pvup) * rdxh) * 0.25;
+
+    const double pu_n = own_u * pu_fac - (dut + dus + own_pgf) * dt;  // dynamics.py:206
+    const double pv_n = own_v * pv_fac - (dvt + dvs + own_fv) * dt;   // dynamics.py:207
+    double v_n = pv_n * r_pnv;
+    if (zero_v) v_n *= 0.0;  // dynamics.py:222
+    // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
+    const double adv_t = ((pu_c * (t_k + st_[1]) - pu_im * (st_[-1] + t_k)) * rdxj +
+                          (pv_c * (t_k + st_[PFT_ROW]) - pv_jm * (st_[-PFT_ROW] + t_k)) * rdy) * 0.5;
+    const double adv_q = ((pu_c * (q_k + sq_[1]) - pu_im * (sq_[-1] + q_k)) * rdxj +
+                          (pv_c * (q_k + sq_[PFT_ROW]) - pv_jm * (sq_[-PFT_ROW] + q_k)) * rdy) * 0.5;
+    if (active) {
+      ou[e] = pu_n * r_pnu;
+      ov[e] = v_n;
+      ot[e] = (own_t * p_c - (adv_t + ads_t) * dt) * r_pn;
+      oq[e] = (own_q * p_c - (adv_q + ads_q) * dt) * r_pn;
+    }
+    fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
+    u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
+  }
+  if (active) out.p[o2 + e_c] = pn_c;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 int g_gcm_knob[16] = {0};
@@ -607,13 +793,16 @@ int g_gcm_knob[16] = {0};
 // tuning knobs of the fast path (bench.py --knob i=v; 0 = automatic):
 //   0  min resident blocks per SM of the update kernel (1..4: registers per thread vs resident warps)
 //   1  update-kernel tile width in i (threads.x, multiple of 32)      2  threads of the row kernel
-//   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the row kernel (RB)
+//   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the fused row kernel (RB);
+//                                                                       tiled update kernel: copy-pipeline stages (3..5)
 //   5  rows per warp task of the row kernel's column phase (RG)      6  packed rows per FFT pass (NBAT)
 //   7  register budget of the row kernel: 1 = 128 regs, 2 = 102 regs / five 128-thread CTAs per SM
 //   8  1 = one fused row kernel per half step, 2 = filter / column / filter as three launches
 //   9  threads of the filter kernel (three-launch form)
 //  10  update kernel: prefetch distance in layers + 1 (1 = off; default distance 1)
-//  14  update kernel: L2 prefetch distance in layers for the thread's own column (0 = off)
+//  14  update kernel: > 0: L2 prefetch distance in layers for the thread's own column; -1: L1 prefetch of the rows
+//      to the north / south only by the tile's edge rows (default 0: every thread prefetches all three rows)
+//  15  1 = update kernel with direct global loads (default: staged shared-memory tiles when W % 32 == 0)
 //  11  1 = the two chains of the row phase one after the other on the caller's stream (default: side by side)
 //  12  largest FFT radix the planner may use (set before the geometry is created; 0 = 16)
 //  13  1 = filter kernel with 168 registers per thread (three CTAs per SM)
@@ -799,12 +988,33 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
                            : dim3((W + tx - 1) / tx, (nrowsU + ty - 1) / ty, nbatch);
     const int pfd = g_gcm_knob[10] > 0 ? g_gcm_knob[10] - 1 : 1;  // prefetch distance in layers (knob: value + 1)
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
+    if (W % PFT_TI == 0 && g_gcm_knob[15] != 1) {  // staged tiles (knob 15 = 1: direct loads)
+      const int ns = g_gcm_knob[4] == 4 ? 4 : (g_gcm_knob[4] == 5 ? 5 : 3);  // knob 4: stages of the copy pipeline
+      const size_t smt = (size_t)ns * PFT_STAGE * sizeof(double);
+      // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every
+      // row, so a band stays bit-identical to the whole grid)
+      const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (parts[s2].n1 <= 0) continue;
+        const dim3 gridt(W / PFT_TI, (parts[s2].n1 + PFT_TJ - 1) / PFT_TJ, nbatch), blockt(PFT_TI, PFT_TJ);
+        if (ns == 4)
+          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 4>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        else if (ns == 5)
+          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        else
+          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 3>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        GCM_CHECK_LAUNCH();
+      }
+      return GCM_OK;
+    }
 #define PF_UPD(MINB, PF) \
   GCM_LAUNCH((pe25f_update_kernel<L, MINB, PF>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, g_gcm_knob[14], flatW, b2, b3)
     if (pfd > 0) {
       switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
         case 2: PF_UPD(2, true); break;
         case 3: PF_UPD(3, true); break;
+        case 5: PF_UPD(5, true); break;
+        case 6: PF_UPD(6, true); break;
         default: PF_UPD(4, true); break;
       }
     } else {

@@ -56,6 +56,17 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend):
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
+def test_band_with_tiled_update_is_bit_identical(backend):
+    """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too."""
+    geom, s = _case(H=16, W=32)
+    whole = dynamics.Stepper(geom, *s)
+    whole.step(450.0, 2)
+    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
+    band.step(450.0, 2)
+    for a, b in zip(band.gather(), whole.download()):
+        assert np.array_equal(a, b)
+
+
 def test_native_band_loop_single_rank(backend):
     """gcm_band_matsuno_step (csrc/comm.cu): the C++ loop with the ring closed on the band itself.  On the GPU this
     runs the overlapped schedule (side stream, interior rows first, two-segment launches next to the halos)."""

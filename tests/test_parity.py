@@ -257,6 +257,23 @@ def test_run25_golden(backend, name, H, W, L):
     check_state(one, tuple(g["%s_1" % k] for k in "puvtq") if "p_1" in g else O.matsuno_timestep(*s, dt, _ogeom(g, H, W, L)), 1e-12)
 
 
+@pytest.mark.parametrize("H,W,L,dt,n", [(10, 64, 9, 300.0, 3), (7, 32, 3, 300.0, 2), (12, 96, 9, 200.0, 2)])
+def test_run25_tiled_update_vs_oracle(backend, H, W, L, dt, n):
+    """Widths that are multiples of 32 take the shared-memory-tiled update kernel (asynchronous copies, halo ring with
+    periodic wrap); H not a multiple of the tile height leaves a partial tile."""
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    hm = 50.0 * np.random.default_rng(H).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    s = O.synthetic_state(og, seed=H * W)
+    ref = s
+    for _ in range(n):
+        ref = O.matsuno_timestep(*ref, dt, og)
+    st = dynamics.Stepper(geom, *s)
+    st.step(dt, n)
+    check_state(st.download(), ref, TOL_RUN)
+
+
 def _ogeom(g, H, W, L):
     og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
     og.ptop = float(g["ptop"]); og.heightmap = g["heightmap"]
