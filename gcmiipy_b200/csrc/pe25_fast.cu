@@ -987,8 +987,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const dim3 grid = flat ? dim3((nrowsU * W + tx * ty - 1) / (tx * ty), 1, nbatch)
                            : dim3((W + tx - 1) / tx, (nrowsU + ty - 1) / ty, nbatch);
     const int pfd = g_gcm_knob[10] > 0 ? g_gcm_knob[10] - 1 : 1;  // prefetch distance in layers (knob: value + 1)
-    GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
-    if (W % PFT_TI == 0 && g_gcm_knob[15] != 1) {  // staged tiles (knob 15 = 1: direct loads)
+    const bool tiled = W % PFT_TI == 0 && g_gcm_knob[15] != 1;  // staged tiles (knob 15 = 1: direct loads)
+    GcmProfScope ps(tiled ? GCM_K_UPDATE_TILED : GCM_K_UPDATE_FAST, stream);
+    if (tiled) {
       const int ns = g_gcm_knob[4] == 4 ? 4 : (g_gcm_knob[4] == 5 ? 5 : 3);  // knob 4: stages of the copy pipeline
       const size_t smt = (size_t)ns * PFT_STAGE * sizeof(double);
       // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every

@@ -14,7 +14,8 @@ enum GcmProfKind {
   GCM_K_COLUMN_F = 7,     // pe25f_hydro_kernel
   GCM_K_FILTER_B = 8,     // pe25f_filter_kernel<0>
   GCM_K_AFLUX_F = 9,      // pe25f_aflux_kernel
-  GCM_K_COUNT = 10
+  GCM_K_UPDATE_TILED = 10,  // pe25f_update_tiled_kernel
+  GCM_K_COUNT = 11
 };
 
 #ifdef GCM_EMU
