@@ -395,7 +395,7 @@ static int pe25_check_state(const gcm_state* s) {
 bool gcm_pe25_fast_supported(const gcm_geom* g);
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                             double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
-                            const int* seg_r, const int* seg_u, void* stream);
+                            double* pit, const int* seg_r, const int* seg_u, void* stream);
 
 static int g_pe25_path = 0;  // 0 = fused ALU-lean kernels when the geometry allows, 1 = always the 4-kernel path
 
@@ -408,8 +408,8 @@ extern "C" int gcm_pe25_select_path(int path) {
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
   if (g_pe25_path == 0 && gcm_pe25_fast_supported(g))
-    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, nullptr, nullptr,
-                                   stream);  // fv in the phi slot
+    return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, w.pit, nullptr,
+                                   nullptr, stream);  // fv in the phi slot
   const GcmGeomDev& d = g->d;
   const int H = d.H, W = d.W, L = d.L;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;  // member strides of the caller's arrays
@@ -502,7 +502,8 @@ extern "C" int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base,
   }
   Pe25Work w;
   pe25_carve(g, nbatch, ws, &w);
-  return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, seg_r, seg_u, stream);
+  return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, w.pit, seg_r, seg_u,
+                                 stream);
 }
 
 extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt,

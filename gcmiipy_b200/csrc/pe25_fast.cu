@@ -34,7 +34,7 @@ struct PfMut {
   double *p, *u, *v, *t, *q;
 };
 struct PfWork {
-  double *spu, *sd, *pgf, *fv, *pn;
+  double *spu, *sd, *pgf, *fv, *pn, *pit;
 };
 
 // hydrostatic geopotential at layer centres and density of one column (dynamics.py:111-142, :150-152);
@@ -235,6 +235,7 @@ pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWor
         sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
       }
       pn[c2] = p[c2] - pit * dt;
+      w.pit[o2 + c2] = pit;
     }
   }
 
@@ -356,7 +357,7 @@ pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* i
 }
 
 // aflux (dynamics.py:35-46) and p_n (:193-194): one thread per column of the rows of `seg`; needs the filtered spu.
-template <int L>
+template <int L, bool WRITE_SD>
 __global__ void __launch_bounds__(128)
 pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ sp_,
                    const double* __restrict__ sv_, PfWork w, double dt, GcmRowSeg seg, unsigned magicW, size_t bstride2,
@@ -385,12 +386,15 @@ pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __r
     conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
     pit += conv[k];
   }
-  double acc = 0.0;
+  if (WRITE_SD) {  // the tiled update kernel rebuilds sd from pit and the fluxes it already holds
+    double acc = 0.0;
 #pragma unroll
-  for (int k = L - 1; k >= 0; --k) {
-    acc += conv[k];
-    sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+    for (int k = L - 1; k >= 0; --k) {
+      acc += conv[k];
+      sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
+    }
   }
+  w.pit[o2 + c2] = pit;
   w.pn[o2 + c2] = p[o2 + c2] - pit * dt;
 }
 
@@ -617,10 +621,11 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 #define PFT_TJ 4
 #define PFT_ROW (PFT_TI + 2)
 #define PFT_TILE ((PFT_TJ + 2) * PFT_ROW)
-#define PFT_STAGE (6 * PFT_TILE)  // doubles per stage
+#define PFT_NF 5                    // staged fields: su, sv, st, sq, spu
+#define PFT_STAGE (PFT_NF * PFT_TILE)  // doubles per stage
 
-template <int L, int PFT_NS>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 4)
+template <int L, int PFT_NS, int MINB>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, MINB)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double, sm);
@@ -636,8 +641,9 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const double* __restrict__ p = base.p + o2;
   const double* __restrict__ sp = star.p + o2;
   const double* __restrict__ pn = w.pn + o2;
-  // staged fields: 0..5 with halo (su, sv, st, sq, spu, sd), 6..11 own column only (pgf, fv, u, v, t, q)
-  const double* fld[12] = {star.u + o3, star.v + o3, star.t + o3, star.q + o3, w.spu + o3, w.sd + o3,
+  const double* __restrict__ pit = w.pit + o2;
+  // fields 0..4 staged with halo (su, sv, st, sq, spu); 6..11 read once per cell (pgf, fv, u, v, t, q)
+  const double* fld[12] = {star.u + o3, star.v + o3, star.t + o3, star.q + o3, w.spu + o3, nullptr,
                            w.pgf + o3,  w.fv + o3,   base.u + o3, base.v + o3, base.t + o3, base.q + o3};
   double* __restrict__ ou = out.u + o3;
   double* __restrict__ ov = out.v + o3;
@@ -670,10 +676,10 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     double* st = sm + s * PFT_STAGE;
     const int off = k * plane;
 #pragma unroll
-    for (int f = 0; f < 6; ++f) gcm_cp_async8(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
+    for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
     if (has_halo) {
 #pragma unroll
-      for (int f = 0; f < 6; ++f) gcm_cp_async8(st + f * PFT_TILE + t_h, fld[f] + off + e_h);
+      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * PFT_TILE + t_h, fld[f] + off + e_h);
     }
     gcm_cp_async_commit();
   };
@@ -696,6 +702,12 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const double a_jm_ip = (sp[jm * W + ip] + sp_ip) * 0.5;      // (j-1, i+1)
   const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;         // (j+1, i)
   const bool zero_v = j == g.zero_v_row;
+  // sd (dynamics.py:42-44) of the three columns the vertical fluxes need -- (j, i), (j, i+1), (j+1, i) -- is rebuilt
+  // from pit and the running sums of conv, whose operands the horizontal advection loads anyway:
+  //   sd[k] = sum_{l >= k} conv[l] - pit sigb[k] = (pit - sum_{l < k} conv[l]) - pit sigb[k],   sd[0] = 0
+  const double pit_c = pit[e_c], pit_ip = pit[j * W + ip], pit_jp = pit[jp * W + i];
+  const double rdxj_jp = g.rdx_j[jp];
+  double pre_c = 0.0, pre_ip = 0.0, pre_jp = 0.0;
   // layer L-1 pairs with layer 0 through the bottom of layer 0 (np.roll), times sd[0] = 0
   const double u_top = fld[0][(L - 1) * plane + e_c], v_top = fld[1][(L - 1) * plane + e_c],
                t_top = fld[2][(L - 1) * plane + e_c], q_top = fld[3][(L - 1) * plane + e_c];
@@ -707,7 +719,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const double* s0 = sm;
   double u_k = s0[0 * PFT_TILE + t_c], v_k = s0[1 * PFT_TILE + t_c], t_k = s0[2 * PFT_TILE + t_c],
          q_k = s0[3 * PFT_TILE + t_c];
-  double sd_c = s0[5 * PFT_TILE + t_c], sd_ip = s0[5 * PFT_TILE + t_c + 1], sd_jp = s0[5 * PFT_TILE + t_c + PFT_ROW];
+  double sd_c = 0.0, sd_ip = 0.0, sd_jp = 0.0;  // level 0
   double fu = (u_k + u_top) * 0.5 * ((sd_c + sd_ip) * 0.5);
   double fv_ = (v_k + v_top) * 0.5 * ((sd_c + sd_jp) * 0.5);
   double ft = (t_k + t_top) * 0.5 * sd_c;
@@ -728,22 +740,6 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     const int e = k * plane + e_c;
     const double own_pgf = fld[6][e], own_fv = fld[7][e], own_u = fld[8][e], own_v = fld[9][e], own_t = fld[10][e],
                  own_q = fld[11][e];
-    // fluxes through the top of layer k
-    double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
-    double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
-    if (k + 1 < L) {
-      u_kp = sn[0 * PFT_TILE + t_c]; v_kp = sn[1 * PFT_TILE + t_c]; t_kp = sn[2 * PFT_TILE + t_c];
-      q_kp = sn[3 * PFT_TILE + t_c];
-      sd_c = sn[5 * PFT_TILE + t_c]; sd_ip = sn[5 * PFT_TILE + t_c + 1]; sd_jp = sn[5 * PFT_TILE + t_c + PFT_ROW];
-      fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
-      fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
-      ft_n = (t_kp + t_k) * 0.5 * sd_c;
-      fq_n = (q_kp + q_k) * 0.5 * sd_c;
-    }
-    const double rds = g.c_rdsig[k];
-    const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;  // -(F_k - F_k+1) / dsig
-    const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
-
     // horizontal neighbours from the tile
     const double* su_ = sk + 0 * PFT_TILE + t_c;
     const double* sv_ = sk + 1 * PFT_TILE + t_c;
@@ -755,6 +751,28 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     const double pu_c = pu_[0], pu_im = pu_[-1], pu_ip = pu_[1], pu_jp = pu_[PFT_ROW], pu_jp_im = pu_[PFT_ROW - 1];
     const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
                  pv_jp = v_jp * a_jp;
+
+    // fluxes through the top of layer k (advec_sig, dynamics.py:49-52) with sd at level k + 1
+    double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
+    double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
+    if (k + 1 < L) {
+      const double ds = g.c_dsig[k], sb = g.c_sigb[k + 1];
+      pre_c += ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * ds;           // conv of (j, i)      dynamics.py:39
+      pre_ip += ((pu_ip - pu_c) * rdxj + (pv_ip - pv_jm_ip) * rdy) * ds;      //         (j, i+1)
+      pre_jp += ((pu_jp - pu_jp_im) * rdxj_jp + (pv_jp - pv_c) * rdy) * ds;   //         (j+1, i)
+      sd_c = (pit_c - pre_c) - pit_c * sb;
+      sd_ip = (pit_ip - pre_ip) - pit_ip * sb;
+      sd_jp = (pit_jp - pre_jp) - pit_jp * sb;
+      u_kp = sn[0 * PFT_TILE + t_c]; v_kp = sn[1 * PFT_TILE + t_c]; t_kp = sn[2 * PFT_TILE + t_c];
+      q_kp = sn[3 * PFT_TILE + t_c];
+      fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
+      fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
+      ft_n = (t_kp + t_k) * 0.5 * sd_c;
+      fq_n = (q_kp + q_k) * 0.5 * sd_c;
+    }
+    const double rds = g.c_rdsig[k];
+    const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;  // -(F_k - F_k+1) / dsig
+    const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
 
     // advec_m_pu (dynamics.py:55-108); (a/2)(b/2) = ab/4 exactly
     const double puum = (u_k + u_im) * (pu_c + pu_im), puup = (u_ip + u_k) * (pu_ip + pu_c);
@@ -906,8 +924,12 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     {
       GcmProfScope ps(GCM_K_AFLUX_F, qa);
       const dim3 grida((nrowsR * W + 127) / 128, nbatch);
-      GCM_LAUNCH((pe25f_aflux_kernel<L>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR, magicW, b2,
-                 b3);
+      if (W % PFT_TI == 0 && g_gcm_knob[15] != 1)  // tiled update: pit and p_n only
+        GCM_LAUNCH((pe25f_aflux_kernel<L, false>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
+                   magicW, b2, b3);
+      else
+        GCM_LAUNCH((pe25f_aflux_kernel<L, true>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
+                   magicW, b2, b3);
     }
     GCM_CHECK_LAUNCH();
     {
@@ -998,12 +1020,13 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       for (int s2 = 0; s2 < 2; ++s2) {
         if (parts[s2].n1 <= 0) continue;
         const dim3 gridt(W / PFT_TI, (parts[s2].n1 + PFT_TJ - 1) / PFT_TJ, nbatch), blockt(PFT_TI, PFT_TJ);
-        if (ns == 4)
-          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 4>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
-        else if (ns == 5)
-          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
-        else
-          GCM_LAUNCH((pe25f_update_tiled_kernel<L, 3>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+#define PF_TILED(NS, MINB) \
+  GCM_LAUNCH((pe25f_update_tiled_kernel<L, NS, MINB>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3)
+        if (g_gcm_knob[0] == 3) PF_TILED(3, 3);       // knob 0 = 3: 168 registers, three CTAs per SM
+        else if (ns == 4) PF_TILED(4, 4);
+        else if (ns == 5) PF_TILED(5, 4);
+        else PF_TILED(3, 4);
+#undef PF_TILED
         GCM_CHECK_LAUNCH();
       }
       return GCM_OK;
@@ -1033,8 +1056,8 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
 
 int gcm_pe25_fast_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                             double dt, int nbatch, double* spu, double* sd, double* fv, double* pgf, double* pn,
-                            const int* seg_r, const int* seg_u, void* stream) {
-  const PfWork w{spu, sd, pgf, fv, pn};
+                            double* pit, const int* seg_r, const int* seg_u, void* stream) {
+  const PfWork w{spu, sd, pgf, fv, pn, pit};
   const GcmGeomDev& d = g->d;
   const int nrows = d.row_hi - d.row_lo;
   GcmRowSeg sr{d.row_lo, d.wrap_j ? nrows : nrows + 1, 0, 0};  // band: also the first halo row to the south
