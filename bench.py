@@ -28,6 +28,8 @@ WORKLOADS = {
     "c3": (180, 288, 9, 60.0, 1, "1x1.25deg 288x180x9 2.5-D Matsuno step (BASELINE configs[2])"),
     "c2": (46, 72, 9, 225.0, 1, "GISS 4x5deg 72x46x9 2.5-D Matsuno step (BASELINE configs[1])"),
     "c4": (24, 36, 9, 450.0, 1024, "ensemble of 1024 x 8x10deg 36x24x9 runs (BASELINE configs[3])"),
+    # tuning aid: the per-rank share of configs[4] on 8 GPUs as a stand-alone periodic grid (not a BASELINE config)
+    "c5b8": (90, 1440, 9, 10.0, 1, "1440x90x9: one of 8 latitude bands of configs[4], stepped alone (tuning aid)"),
 }
 METRIC = "cell_updates_per_sec"
 UNIT = "cell-updates/s"

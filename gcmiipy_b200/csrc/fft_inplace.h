@@ -9,9 +9,12 @@
 //              block length n = N / (r_0 .. r_{s-1})) combines the r elements q + t n/r of each block,
 //              multiplies output m by w_n^{q m} and stores it at q + m n/r.  After the last stage position
 //              p = m_0 N/r_0 + m_1 N/(r_0 r_1) + ... holds wavenumber k = m_0 + r_0 m_1 + r_0 r_1 m_2 + ...
-//   multiply = position p is scaled by table[min(k, N - k)], k = kperm[p] (folded into the last stage);
+//   multiply = position p is scaled by the table entry of wavenumber k = kperm[p]; the table is stored in
+//              transform order (GcmGeomDev::smmzp) and the multiply is folded between the last forward and the
+//              first inverse stage, which are one visit (gcm_mid_stage);
 //   inverse  = the exact mirror (decimation in time, stages in reverse order, conjugate twiddles): digit-
-//              reversed in, natural order out, scaled by N.
+//              reversed in, natural order out; numpy's 1/N is folded into the table.
+// The first forward stage is fed from global memory and the last inverse stage drains to it (gcm_filter_rows_io).
 // All batch rows go through a stage together, so a stage costs one __syncthreads for the whole batch.
 #pragma once
 #include "fft_rows.h"
@@ -212,38 +215,8 @@ __host__ __device__ inline bool gcm_plan_inplace_ok(const GcmFftPlan& plan) {
     default: CALL(16); break;      \
   }
 
-template <int NPJ>
-__device__ __forceinline__ void gcm_filter_rows_inplace(double2* z, int nrows, const GcmFftPlan& plan,
-                                                        const double2* __restrict__ tw,
-                                                        const double* __restrict__ table, const GcmRowSeg seg, int pr0,
-                                                        int tid, int nthr) {
-  if (plan.n == 1) return;  // low_pass.py:58-59
-  const int last = plan.npass - 1;
-  for (int p = 0; p < last; ++p) {
-    const GcmFftStage st = gcm_fft_stage(plan, p);
-#define GCM_CALL(R) gcm_dif_stage<R>(z, st, nrows, tw, tid, nthr)
-    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
-#undef GCM_CALL
-    __syncthreads();
-  }
-  {
-    const GcmFftStage st = gcm_fft_stage(plan, last);
-#define GCM_CALL(R) gcm_mid_stage<R, NPJ>(z, st, nrows, table, seg, pr0, tid, nthr)
-    GCM_RADIX_SWITCH(plan.radix[last], GCM_CALL)
-#undef GCM_CALL
-    __syncthreads();
-  }
-  for (int p = last - 1; p >= 0; --p) {
-    const GcmFftStage st = gcm_fft_stage(plan, p);
-#define GCM_CALL(R) gcm_dit_stage<R>(z, st, nrows, tw, tid, nthr)
-    GCM_RADIX_SWITCH(plan.radix[p], GCM_CALL)
-#undef GCM_CALL
-    __syncthreads();
-  }
-}
-
-// The same filter with the rows read from and written to global memory through `io` (see gcm_dif_stage_first).
-// z is only the inter-stage buffer; on exit it may be reused at once.
+// Filter `nrows` packed rows read from and written to global memory through `io` (see gcm_dif_stage_first).
+// z is only the inter-stage buffer (nrows * N complex); on exit it may be reused at once.
 template <int NPJ, class IO>
 __device__ __forceinline__ void gcm_filter_rows_io(double2* z, int nrows, const GcmFftPlan& plan,
                                                    const double2* __restrict__ tw, const double* __restrict__ table,

@@ -31,7 +31,6 @@ extern "C" const char* gcm_status_string(int s) {
 static const int kRadix[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
 static const double kRadixCost[] = {10.5, 16.5, 11.33, 12.4, 13.33, 7.0, 9.33, 8.0, 4.0, 5.33, 2.0};
 static const double kPassCost = 10.0;
-extern int g_gcm_knob[16];  // pe25_fast.cu
 
 static void plan_search(int m, int first, int* cur, int ncur, double cost, int* best, int* nbest, double* bestcost) {
   if (m == 1) {
@@ -44,7 +43,7 @@ static void plan_search(int m, int first, int* cur, int ncur, double cost, int* 
   }
   if (ncur >= 12 || cost >= *bestcost) return;
   for (int f = first; f < (int)(sizeof(kRadix) / sizeof(int)); ++f)
-    if (m % kRadix[f] == 0 && (g_gcm_knob[12] <= 0 || kRadix[f] <= g_gcm_knob[12])) {  // knob 12: largest radix
+    if (m % kRadix[f] == 0) {
       cur[ncur] = kRadix[f];
       plan_search(m / kRadix[f], f, cur, ncur + 1, cost + kRadixCost[f] + kPassCost, best, nbest, bestcost);
     }

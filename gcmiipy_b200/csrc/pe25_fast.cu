@@ -1,26 +1,24 @@
 // pe25_fast.cu -- fused kernels of the 2.5-D half step (reference dynamics.py:183-227).
 //
-// Two launches per half step, split at the only data dependences that span a whole latitude row (the zonal FFT
-// filter, low_pass.py:41-78) -- everything else is recomputed where it is needed instead of stored:
+// Five launches per half step, split at the only data dependences that span a whole latitude row (the zonal FFT
+// filter, low_pass.py:41-78) or a whole column (sums over k) -- everything else is recomputed where it is needed
+// instead of stored.  Two independent chains run side by side (caller's stream + the geometry's side stream):
 //
-//   R  pe25f_row_kernel     one CTA per block of RB latitude rows of one member, all layers.  Several CTAs share an
-//                           SM (small FFT buffer), so one CTA's barriers and loads hide behind another's math.
-//        FA   spu = arakawa_1977(su * iph(sp)): NBAT layer pairs per pass through a shared-memory buffer,
-//             in-place mixed-radix FFT (fft_inplace.h), spu -> HBM                              (dynamics.py:187-189)
-//        P2a  one thread per column: spu back from L1/L2; conv, pit, sd, p_n                   (:35-46, :193-194)
-//        P2b  one warp per 31 columns, marching south over the rows: hydrostatic phi and rho by column
-//             (:111-142, :150-152), east neighbour by warp shuffle, north row kept in registers:
-//             pgfu + phiu -> HBM (unfiltered, :159-165), fv = phiv + pgv -> HBM (:160, :167-169)
-//        FB   pgf = arakawa_1977(pgfu + phiu), in place in HBM through the same buffer          (:202)
-//   U  pe25f_update_kernel  one thread per column of a 32 x 4 (i x j) tile, k loop with the vertical neighbours and
-//        interface fluxes carried in registers: momentum and tracer update                     (:197-222)
+//   F1  pe25f_filter_kernel<1>   spu = arakawa_1977(su * iph(sp))                          (dynamics.py:187-189)
+//   A   pe25f_aflux_kernel       pit = sum_k conv, p_n = p - pit dt  (+ sd on the direct-load update path)  (:35-46, :194)
+//   H   pe25f_hydro_kernel       hydrostatic phi, rho by column in registers -> pgfu + phiu, fv = phiv + pgv (:111-171)
+//   F0  pe25f_filter_kernel<0>   pgf = arakawa_1977(pgfu + phiu), in place                 (:202)
+//   U   pe25f_update_tiled_kernel / pe25f_update_kernel   momentum and tracer update       (:197-222)
 //
-// Work fields in HBM between R and U: spu, sd, pgf, fv (3-D) and p_n (2-D).  phi and rho never leave the SM.
+// Work fields in HBM between the launches: spu, pgf, fv (3-D), pit, p_n (2-D).  phi and rho never leave the SM; sd is
+// rebuilt inside U.
 //   * divides by metric terms are multiplications by resident reciprocals (1/dx_j, 1/dx_h, 1/dy, 1/dsig), the
 //     divides by p_n averages are done once per column, the 1/W of the inverse transform is folded into the
 //     filter table, and when ptop = 0 (the reference's setting, geometry.py:147) the Exner factor
-//     ((sig p + ptop)/P0)^kappa factorises into sig^kappa (resident) x (p/P0)^kappa: one pow per column;
-//   * per-layer tables ride in the kernel parameters (constant bank), indices are 32-bit.
+//     ((sig p + ptop)/P0)^kappa factorises into sig^kappa (resident) x (p/P0)^kappa: one exp/log per column;
+//   * per-layer tables ride in the kernel parameters (constant bank), indices are 32-bit;
+//   * every kernel takes row segments (GcmRowSeg), so a latitude band can compute its interior rows while the halo
+//     exchange is in flight (comm.cu).
 // FMA contraction is on for this file.  Results agree with the reference within the stated fp64 tolerance
 // (tests/test_parity.py); the bit-exact operator kernels stay in pe25.cu.
 #include "fft_inplace.h"
@@ -77,39 +75,8 @@ __device__ __forceinline__ void pf_column(const GcmGeomDev& g, double sp_c, doub
 }
 
 // ---------------------------------------------------------------------------------------------------
-// R: one CTA per (block of RB rows, member)
+// hydrostatic columns
 // ---------------------------------------------------------------------------------------------------
-// flat index e = prl * W + i over the packed rows of an FFT pass, advanced by the block size without a division
-struct PfRowIdx {
-  int prl, i;
-  __device__ __forceinline__ PfRowIdx(int tid, unsigned magicW, int W) {
-    prl = gcm_fastdiv(tid, magicW);
-    i = tid - prl * W;
-  }
-  __device__ __forceinline__ void advance(int nthr, int W) {
-    i += nthr;
-    while (i >= W) {
-      i -= W;
-      ++prl;
-    }
-  }
-};
-
-// f(prl, i) for every element of `nb` rows of length W, spread over the block.  Rows at least as long as the block
-// take the nested form (row-invariant index math hoisted, four independent iterations in flight).
-template <class F>
-__device__ __forceinline__ void pf_foreach(int nb, int W, int tid, int nthr, unsigned magicW, F f) {
-  if (W >= nthr) {
-    for (int prl = 0; prl < nb; ++prl) {
-#pragma unroll 4
-      for (int i = tid; i < W; i += nthr) f(prl, i);
-    }
-  } else {
-    PfRowIdx x(tid, magicW, W);
-    for (int e = tid; e < nb * W; e += nthr, x.advance(nthr, W)) f(x.prl, x.i);
-  }
-}
-
 // Column phase of one row for one lane: phi and rho of column (j, i) into (phi, rho); if emit_pre, pgfu + phiu of
 // row j (dynamics.py:159, :162-165; east neighbour from lane + 1) -> pgf, unfiltered; if emit_fv, fv = phiv + pgv of
 // the row to the north (:160, :167-169) from (phi_n, rho_n, sp_n) -> fv at cn.  All lanes of the warp must call.
@@ -147,156 +114,10 @@ __device__ __forceinline__ double pf_row_step(const GcmGeomDev& g, const double*
   return sp_c;
 }
 
-template <int L, bool PTOP0, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-pe25f_row_kernel(GcmGeomDev g, const double* __restrict__ p, PfConst star, PfWork w, double dt, int ja, int jend, int RB,
-                 int RG, int NBAT, unsigned magicW, size_t bstride2, size_t bstride3) {
-  GCM_DYN_SMEM(double2, z);
-  constexpr int NP = (L + 1) / 2;
-  const int H = g.H, W = g.W, plane = H * W;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int j0 = ja + blockIdx.x * RB;
-  const int rb = jend - j0 < RB ? jend - j0 : RB;  // rows of this block
-  const int npr = rb * NP;                         // packed rows (layer pairs) of this block
-  const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
-  const double* __restrict__ sp = star.p + o2;
-  const double* __restrict__ su = star.u + o3;
-  const double* __restrict__ sv = star.v + o3;
-  const double* __restrict__ st = star.t + o3;
-  p += o2;
-  double* spu = w.spu + o3;  // written, then read back by other threads of the block: no __restrict__
-  double* pgf = w.pgf + o3;
-  double* __restrict__ sd = w.sd + o3;
-  double* __restrict__ fv = w.fv + o3;
-  double* __restrict__ pn = w.pn + o2;
-  const GcmRowSeg rseg{j0, rb, 0, 0};
-  const double rdy = g.rdy;
-
-  // start the rows of the column phases on their way to L2 while the first filter runs:
-  // sv rows j-1 .. j+rb-1 and st rows j .. j+rb of every layer, one request per 128-byte line
-  {
-    const int lines = (W * 8 + 127) / 128;
-    const int nrow = rb + 1;
-    for (int e = tid; e < L * nrow * lines; e += nthr) {
-      const int ln = e % lines, rk = e / lines, r = rk % nrow, k = rk / nrow;
-      const int jv = gcm_row(j0 + r, -1, H, g.wrap_j), jt = gcm_row(j0 + r - 1, 1, H, g.wrap_j);
-      gcm_prefetch_l2(sv + k * plane + jv * W + ln * 16);
-      gcm_prefetch_l2(st + k * plane + jt * W + ln * 16);
-    }
-  }
-
-  // FA. spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189), NBAT packed rows (two layers each) per pass
-  for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
-    const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
-    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-      const double* __restrict__ spr = sp + (j0 + r) * W;
-      const double* __restrict__ s0 = su + k0 * plane + (j0 + r) * W;
-      const double ph = (spr[i] + spr[gcm_ip(i, W)]) * 0.5;
-      const double x0 = s0[i] * ph;
-      const double x1 = k0 + 1 < L ? s0[plane + i] * ph : 0.0;
-      z[prl * W + i] = make_double2(x0, x1);
-    });
-    __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, rseg, pr0, tid, nthr);
-    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-      double* o = spu + k0 * plane + (j0 + r) * W;
-      const double2 v = z[prl * W + i];
-      o[i] = v.x;
-      if (k0 + 1 < L) o[plane + i] = v.y;
-    });
-    __syncthreads();  // the buffer is free for the next pass; spu of this block is visible to the block
-  }
-
-  // P2a. per column: aflux (dynamics.py:35-46), p_n (:194); spu comes back from L1/L2
-  {
-    PfRowIdx x(tid, magicW, W);
-    for (int e = tid; e < rb * W; e += nthr, x.advance(nthr, W)) {
-      const int i = x.i, j = j0 + x.prl;
-      const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
-      const int c2 = j * W + i, cim = j * W + gcm_im(i, W), cjm = jm * W + i;
-      const double sp_c = sp[c2];
-      const double pjh = (sp_c + sp[jp * W + i]) * 0.5, pjh_m = (sp[cjm] + sp_c) * 0.5;
-      const double rdxj = g.rdx_j[j];
-      double conv[L];
-      double pit = 0.0;
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        const double pu_c = spu[k * plane + c2], pu_im = spu[k * plane + cim];
-        const double pv_c = sv[k * plane + c2] * pjh, pv_jm = sv[k * plane + cjm] * pjh_m;
-        conv[k] = ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * g.c_dsig[k];
-        pit += conv[k];
-      }
-      double acc = 0.0;
-#pragma unroll
-      for (int k = L - 1; k >= 0; --k) {
-        acc += conv[k];
-        sd[k * plane + c2] = k == 0 ? 0.0 : acc - pit * g.c_sigb[k];  // dynamics.py:42-44
-      }
-      pn[c2] = p[c2] - pit * dt;
-      w.pit[o2 + c2] = pit;
-    }
-  }
-
-  // P2b. hydrostatic columns; a warp owns 31 columns (+ lane 31 = east neighbour of lane 30) and marches south,
-  // the two register sets (A, B) alternating between "this row" and "the row to the north"
-  {
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int nchunk = (W + 30) / 31, ngrp = (rb + RG - 1) / RG;
-    for (int task = warp; task < nchunk * ngrp; task += nwarp) {
-      const int grp = task / nchunk, c = task - grp * nchunk;
-      int i = c * 31 + lane;
-      const bool own = lane < 31 && i < W;
-      i = i % W;
-      const int r0 = grp * RG, r1 = r0 + RG < rb ? r0 + RG : rb;  // rows [r0, r1), row r1 only as the south neighbour
-      double phiA[L], rhoA[L], phiB[L], rhoB[L];
-      int jn = j0 + r0;  // r0 < rb: no wrap
-      double spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, jn * W + i, 0, jn, own, true, false, phiA, rhoA,
-                                         phiA, rhoA, 0.0);
-      double spB = 0.0;
-#pragma unroll 1
-      for (int r = r0 + 1; r <= r1; r += 2) {
-        int j = gcm_row(jn, 1, H, g.wrap_j);
-        spB = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r < r1, true, phiB, rhoB,
-                                    phiA, rhoA, spA);
-        jn = j;
-        if (r + 1 <= r1) {
-          j = gcm_row(jn, 1, H, g.wrap_j);
-          spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r + 1 < r1, true, phiA,
-                                      rhoA, phiB, rhoB, spB);
-          jn = j;
-        }
-      }
-    }
-  }
-  __syncthreads();  // pgfu + phiu of this block is visible to the block
-
-  // FB. pgf = arakawa_1977(pgfu + phiu) (dynamics.py:202), in place in HBM through the same buffer
-  for (int pr0 = 0; pr0 < npr; pr0 += NBAT) {
-    const int nb = npr - pr0 < NBAT ? npr - pr0 : NBAT;
-    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-      const double* o = pgf + k0 * plane + (j0 + r) * W;
-      z[prl * W + i] = make_double2(o[i], k0 + 1 < L ? o[plane + i] : 0.0);
-    });
-    __syncthreads();
-    gcm_filter_rows_inplace<NP>(z, nb, g.plan, g.tws, g.smmzp, rseg, pr0, tid, nthr);
-    pf_foreach(nb, W, tid, nthr, magicW, [&](int prl, int i) {
-      const int pr = pr0 + prl, r = pr / NP, k0 = 2 * (pr - r * NP);
-      double* o = pgf + k0 * plane + (j0 + r) * W;
-      const double2 v = z[prl * W + i];
-      o[i] = v.x;
-      if (k0 + 1 < L) o[plane + i] = v.y;
-    });
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// The same work as three launches (F: filter, C: columns, F: filter): every (row, layer pair) and every
-// (row group, column chunk) is its own unit of parallelism, so a latitude band of a few dozen rows (strong scaling
-// over GPUs) still fills the chip, and the column march can span RG rows (RG + 1 column evaluations per RG rows).
+// The row phase: every (row, layer pair) and every (row group, column chunk) is its own unit of parallelism, so a
+// latitude band of a few dozen rows (strong scaling over GPUs) still fills the chip, and the column march can span
+// RG rows (RG + 1 column evaluations per RG rows).
 // ---------------------------------------------------------------------------------------------------
 // MODE 1: spu = arakawa_1977(su * iph(sp)) (dynamics.py:187-189);  MODE 0: x = arakawa_1977(x) in place (:202).
 // One CTA per NBAT packed rows of the flattened (row, layer pair) list of the rows of `seg`.
@@ -340,10 +161,10 @@ struct PfFilterIO {
   }
 };
 
-template <int L, int MODE, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
+template <int L, int MODE>
+__global__ void __launch_bounds__(256, 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
-                    unsigned magicW, size_t bstride2, size_t bstride3) {
+                    size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double2, z);
   constexpr int NP = (L + 1) / 2;
   const int W = g.W;
@@ -353,7 +174,6 @@ pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* i
   PfFilterIO<L, MODE> io{sp + blockIdx.y * bstride2, in + blockIdx.y * bstride3, out + blockIdx.y * bstride3, seg, pr0, W,
                          g.H * W};
   gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
-  (void)magicW;
 }
 
 // aflux (dynamics.py:35-46) and p_n (:193-194): one thread per column of the rows of `seg`; needs the filtered spu.
@@ -441,12 +261,12 @@ pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// U: one thread per column, k loop
+// U, direct loads: one thread per column, k loop (widths that are not a multiple of 32; short rows run flat)
 // ---------------------------------------------------------------------------------------------------
-template <int L, int MINB, bool PF>
-__global__ void __launch_bounds__(128, MINB)
+template <int L>
+__global__ void __launch_bounds__(128, 4)
 pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg, int pfd,
-                    int pf2, unsigned flatW, size_t bstride2, size_t bstride3) {
+                    unsigned flatW, size_t bstride2, size_t bstride3) {
   const int H = g.H, W = g.W, plane = H * W;
   int i, r;
   if (flatW) {  // short rows: threads run over the (row, column) pairs of the launch in row-major order
@@ -516,42 +336,22 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
   }
   const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
 
-  // pfd > 0: ask for the lines of layer k + pfd while layer k is computed (no registers held, no scoreboard)
-  // the rows to the north / south are prefetched by the tile's own threads of those rows, except at the tile's edges
-  const bool pf_n = pf2 < 0 ? (threadIdx.y == 0 || flatW != 0) : true;
-  const bool pf_s = pf2 < 0 ? (threadIdx.y + 1 == blockDim.y || flatW != 0) : true;
+  // ask L1 for the lines of layer k + pfd while layer k is computed (no registers held, no scoreboard)
   auto prefetch_layer = [&](int ec, int ejp, int ejm) {
-    gcm_prefetch_l1(su + ec); gcm_prefetch_l1(sv + ec); gcm_prefetch_l1(st + ec); gcm_prefetch_l1(sq + ec);
-    gcm_prefetch_l1(spu + ec); gcm_prefetch_l1(sd + ec);
+    gcm_prefetch_l1(su + ec); gcm_prefetch_l1(su + ejp); gcm_prefetch_l1(su + ejm);
+    gcm_prefetch_l1(sv + ec); gcm_prefetch_l1(sv + ejp); gcm_prefetch_l1(sv + ejm);
+    gcm_prefetch_l1(st + ec); gcm_prefetch_l1(st + ejp); gcm_prefetch_l1(st + ejm);
+    gcm_prefetch_l1(sq + ec); gcm_prefetch_l1(sq + ejp); gcm_prefetch_l1(sq + ejm);
+    gcm_prefetch_l1(spu + ec); gcm_prefetch_l1(spu + ejp);
+    gcm_prefetch_l1(sd + ec); gcm_prefetch_l1(sd + ejp);
     gcm_prefetch_l1(pgf + ec); gcm_prefetch_l1(fv + ec);
     gcm_prefetch_l1(u + ec); gcm_prefetch_l1(v + ec); gcm_prefetch_l1(t + ec); gcm_prefetch_l1(q + ec);
-    if (pf_s) {
-      gcm_prefetch_l1(su + ejp); gcm_prefetch_l1(sv + ejp); gcm_prefetch_l1(st + ejp); gcm_prefetch_l1(sq + ejp);
-      gcm_prefetch_l1(spu + ejp); gcm_prefetch_l1(sd + ejp);
-    }
-    if (pf_n) {
-      gcm_prefetch_l1(su + ejm); gcm_prefetch_l1(sv + ejm); gcm_prefetch_l1(st + ejm); gcm_prefetch_l1(sq + ejm);
-    }
   };
-  // pf2 > 0: the lines of this thread's own column (the ones that come from HBM) of layer k + pf2 are asked into L2
-  // by two lanes per warp-row (one per 128-byte line)
-  const bool pf2_lane = PF && pf2 > 0 && (threadIdx.x & 15) == 0;
-  auto prefetch_l2_layer = [&](int ec) {
-    gcm_prefetch_l2(su + ec); gcm_prefetch_l2(sv + ec); gcm_prefetch_l2(st + ec); gcm_prefetch_l2(sq + ec);
-    gcm_prefetch_l2(spu + ec); gcm_prefetch_l2(sd + ec); gcm_prefetch_l2(pgf + ec); gcm_prefetch_l2(fv + ec);
-    gcm_prefetch_l2(u + ec); gcm_prefetch_l2(v + ec); gcm_prefetch_l2(t + ec); gcm_prefetch_l2(q + ec);
-  };
-  if (pf2_lane) {
-    for (int k = 0; k < pf2 && k < L; ++k) prefetch_l2_layer(e_c + k * plane);
-  }
-  if (PF) {
-    for (int k = 0; k < pfd && k < L; ++k) prefetch_layer(e_c + k * plane, e_jp + k * plane, e_jm + k * plane);
-  }
+  for (int k = 0; k < pfd && k < L; ++k) prefetch_layer(e_c + k * plane, e_jp + k * plane, e_jm + k * plane);
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
-    if (pf2_lane && k + pf2 < L) prefetch_l2_layer(e_c + pf2 * plane);
-    if (PF && k + pfd < L) prefetch_layer(e_c + pfd * plane, e_jp + pfd * plane, e_jm + pfd * plane);
+    if (pfd > 0 && k + pfd < L) prefetch_layer(e_c + pfd * plane, e_jp + pfd * plane, e_jm + pfd * plane);
     // fluxes through the top of layer k
     double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
     double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
@@ -619,13 +419,14 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 // ---------------------------------------------------------------------------------------------------
 #define PFT_TI 32
 #define PFT_TJ 4
+#define PFT_NS 3  // layers in flight
 #define PFT_ROW (PFT_TI + 2)
 #define PFT_TILE ((PFT_TJ + 2) * PFT_ROW)
 #define PFT_NF 5                    // staged fields: su, sv, st, sq, spu
 #define PFT_STAGE (PFT_NF * PFT_TILE)  // doubles per stage
 
-template <int L, int PFT_NS, int MINB>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, MINB)
+template <int L>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 4)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double, sm);
@@ -806,26 +607,15 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int g_gcm_knob[16] = {0};
+int g_gcm_knob[8] = {0};
 
-// tuning knobs of the fast path (bench.py --knob i=v; 0 = automatic):
-//   0  min resident blocks per SM of the update kernel (1..4: registers per thread vs resident warps)
-//   1  update-kernel tile width in i (threads.x, multiple of 32)      2  threads of the row kernel
-//   3  update-kernel tile height in j (threads.y)                     4  rows per CTA of the fused row kernel (RB);
-//                                                                       tiled update kernel: copy-pipeline stages (3..5)
-//   5  rows per warp task of the row kernel's column phase (RG)      6  packed rows per FFT pass (NBAT)
-//   7  register budget of the row kernel: 1 = 128 regs, 2 = 102 regs / five 128-thread CTAs per SM
-//   8  1 = one fused row kernel per half step, 2 = filter / column / filter as three launches
-//   9  threads of the filter kernel (three-launch form)
-//  10  update kernel: prefetch distance in layers + 1 (1 = off; default distance 1)
-//  14  update kernel: > 0: L2 prefetch distance in layers for the thread's own column; -1: L1 prefetch of the rows
-//      to the north / south only by the tile's edge rows (default 0: every thread prefetches all three rows)
-//  15  1 = update kernel with direct global loads (default: staged shared-memory tiles when W % 32 == 0)
-//  11  1 = the two chains of the row phase one after the other on the caller's stream (default: side by side)
-//  12  largest FFT radix the planner may use (set before the geometry is created; 0 = 16)
-//  13  1 = filter kernel with 168 registers per thread (three CTAs per SM)
+// tuning knobs (bench.py --knob i=v; 0 = automatic):
+//   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
+//   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream
+//   4  1 = update kernel with direct global loads even when W % 32 == 0
+//   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 extern "C" int gcm_tuning_knob(int idx, int value) {
-  GCM_REQUIRE(idx >= 0 && idx < 16, GCM_ESHAPE);
+  GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
   return GCM_OK;
 }
@@ -838,7 +628,7 @@ bool gcm_pe25_fast_supported(const gcm_geom* g) {
   return (size_t)d.W * sizeof(double2) <= 200 * 1024;
 }
 
-// One half step on the rows of `segR` (row phase: spu, sd, p_n, pgf, fv) and `segU` (update).  A whole grid or band
+// One half step on the rows of `segR` (row phase: spu, pit, p_n, pgf, fv) and `segU` (update).  A whole grid or band
 // is one segment each (segR = owned rows + the first halo row to the south in band mode); gcm_pe25_half_step_rows
 // passes two-segment launches for the rows next to the halos.
 template <int L>
@@ -855,16 +645,14 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
   const unsigned magicW = gcm_magic((unsigned)W);
-  const bool one_seg = segR.n2 == 0;
-  const int split = !one_seg || (g_gcm_knob[8] > 0 ? g_gcm_knob[8] == 2 : 1);
-  if (nrowsR > 0 && split) {
+  const bool tiled = W % PFT_TI == 0 && g_gcm_knob[4] != 1;  // update on staged shared-memory tiles
+  if (nrowsR > 0) {
     // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run
-    // side by side (caller's stream + the geometry's side stream): the filters are bound by shared memory and latency,
-    // the column kernels by HBM and FP64, so each fills the other's gaps.  Knob 11 = 1: one after the other.
+    // side by side (caller's stream + the geometry's side stream).
     cudaStream_t qa = (cudaStream_t)stream, qb = (cudaStream_t)stream;
 #ifndef GCM_EMU
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    const bool side = one_seg && g_gcm_knob[11] != 1;
+    const bool side = segR.n2 == 0 && g_gcm_knob[3] != 1;
     if (side) {
       void *q2, *e1, *e2;
       int st2 = gcm_geom_aux(g, &q2, &e1, &e2);
@@ -880,36 +668,28 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const int npr_total = nrowsR * NP;
     int nbf = 1440 / W < 1 ? 1 : 1440 / W;
     while (nbf > 1 && (size_t)((npr_total + nbf - 1) / nbf) * nbatch < 592) --nbf;
-    if (g_gcm_knob[6] > 0) nbf = g_gcm_knob[6];
+    if (g_gcm_knob[1] > 0) nbf = g_gcm_knob[1];
     int tf = (nbf * W / 12 + 31) / 32 * 32;
     tf = tf < 32 ? 32 : (tf > 256 ? 256 : tf);
-    if (g_gcm_knob[9] > 0) tf = g_gcm_knob[9];
+    if (g_gcm_knob[0] > 0) tf = g_gcm_knob[0] > 256 ? 256 : g_gcm_knob[0];
     const size_t smf = nbf * prsmem;
     const dim3 gridf((npr_total + nbf - 1) / nbf, nbatch);
-    const bool wide_regs = g_gcm_knob[13] == 1 && tf <= 128;  // knob 13 = 1: 168 registers, three CTAs per SM
 #ifndef GCM_EMU
     if (smf > 48 * 1024) {
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smf));
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smf));
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
     }
 #endif
     // hydro launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
     const int nchunk = (W + 30) / 31;
     int rg = 4;
     while (rg > 1 && (size_t)nchunk * ((nrowsR + rg - 1) / rg) * nbatch < 2368) rg /= 2;
-    if (g_gcm_knob[5] > 0) rg = g_gcm_knob[5];
-    if (!one_seg) rg = 1;  // a group of rows must be contiguous
+    if (g_gcm_knob[2] > 0) rg = g_gcm_knob[2];
+    if (segR.n2 > 0) rg = 1;  // a group of rows must be contiguous
     const int ntasks = nchunk * ((nrowsR + rg - 1) / rg);
     {
       GcmProfScope ps(GCM_K_FILTER_A, qa);
-      if (wide_regs)
-        GCM_LAUNCH((pe25f_filter_kernel<L, 1, 128, 3>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf,
-                   magicW, b2, b3);
-      else
-        GCM_LAUNCH((pe25f_filter_kernel<L, 1, 256, 2>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf,
-                   magicW, b2, b3);
+      GCM_LAUNCH((pe25f_filter_kernel<L, 1>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf, b2, b3);
     }
     GCM_CHECK_LAUNCH();
     {
@@ -924,7 +704,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     {
       GcmProfScope ps(GCM_K_AFLUX_F, qa);
       const dim3 grida((nrowsR * W + 127) / 128, nbatch);
-      if (W % PFT_TI == 0 && g_gcm_knob[15] != 1)  // tiled update: pit and p_n only
+      if (tiled)  // the tiled update rebuilds sd: pit and p_n only
         GCM_LAUNCH((pe25f_aflux_kernel<L, false>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
                    magicW, b2, b3);
       else
@@ -934,12 +714,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     GCM_CHECK_LAUNCH();
     {
       GcmProfScope ps(GCM_K_FILTER_B, qb);
-      if (wide_regs)
-        GCM_LAUNCH((pe25f_filter_kernel<L, 0, 128, 3>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf,
-                   magicW, b2, b3);
-      else
-        GCM_LAUNCH((pe25f_filter_kernel<L, 0, 256, 2>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf,
-                   magicW, b2, b3);
+      GCM_LAUNCH((pe25f_filter_kernel<L, 0>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf, b2, b3);
     }
     GCM_CHECK_LAUNCH();
 #ifndef GCM_EMU
@@ -948,109 +723,31 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GCM_CUDA(cudaStreamWaitEvent(qa, ev_join, 0));
     }
 #endif
-  } else if (nrowsR > 0) {
-    // one fused row kernel (tuning knob 8 = 1): rows per CTA for about 24 KB of packed rows, at least two waves
-    const int ja = segR.a;
-    int RB = (int)((24 * 1024) / (prsmem * NP));
-    RB = RB < 1 ? 1 : (RB > 8 ? 8 : RB);
-    while (RB > 1 && (size_t)((nrowsR + RB - 1) / RB) * nbatch < 296) --RB;
-    if (g_gcm_knob[4] > 0) RB = g_gcm_knob[4];
-    int RG = (RB + 3) / 4;
-    if (g_gcm_knob[5] > 0) RG = g_gcm_knob[5];
-    int NBAT = (int)((24 * 1024) / prsmem);
-    if (g_gcm_knob[6] > 0) NBAT = g_gcm_knob[6];
-    NBAT = NBAT < 1 ? 1 : (NBAT > RB * NP ? RB * NP : NBAT);
-    const size_t smem = NBAT * prsmem;
-    // threads per CTA (measured, profiles/r01h): few CTAs want wide CTAs; long rows run five 128-thread CTAs per SM
-    // on the 102-register build; many small CTAs want two warps each
-    const size_t nctas = (size_t)((nrowsR + RB - 1) / RB) * nbatch;
-    int variant = 0;
-    int tr = 64;
-    if (nctas < 296) tr = 192;
-    else if (W >= 512) { tr = 128; variant = 1; }
-    if (g_gcm_knob[2] > 0) tr = g_gcm_knob[2] > 256 ? 256 : g_gcm_knob[2];
-    if (g_gcm_knob[7] > 0) variant = g_gcm_knob[7] - 1;
-    if (variant == 1 && tr > 128) tr = 128;
-#ifdef GCM_EMU
-#define PF_ROW_SMEM(PT, MAXT, MINB)
-#else
-#define PF_ROW_SMEM(PT, MAXT, MINB)                                                                                    \
-  if (smem > 48 * 1024)                                                                                                \
-    GCM_CUDA(cudaFuncSetAttribute(pe25f_row_kernel<L, PT, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                  (int)smem));
-#endif
-#define PF_ROW_LAUNCH(PT, MAXT, MINB)                                                                                  \
-  do {                                                                                                                 \
-    PF_ROW_SMEM(PT, MAXT, MINB)                                                                                        \
-    GCM_LAUNCH((pe25f_row_kernel<L, PT, MAXT, MINB>), grid, dim3(tr), smem, stream, d, base->p, cs, w, dt, ja,         \
-               ja + nrowsR, RB, RG, NBAT, magicW, b2, b3);                                                             \
-  } while (0)
-    {
-      GcmProfScope ps(GCM_K_ROW, stream);
-      const dim3 grid((nrowsR + RB - 1) / RB, nbatch);
-      if (variant == 1) {
-        if (ptop0) PF_ROW_LAUNCH(true, 128, 5); else PF_ROW_LAUNCH(false, 128, 5);
-      } else {
-        if (ptop0) PF_ROW_LAUNCH(true, 256, 2); else PF_ROW_LAUNCH(false, 256, 2);
-      }
-    }
-#undef PF_ROW_LAUNCH
-#undef PF_ROW_SMEM
-    GCM_CHECK_LAUNCH();
   }
-  if (nrowsU > 0) {
-    // update: 32 x 4 (i x j) tiles; rows shorter than 128 that do not fill 32-wide tiles run flat over (row, column)
-    int tx = g_gcm_knob[1] > 0 ? g_gcm_knob[1] : 32;
-    int ty = g_gcm_knob[3] > 0 ? g_gcm_knob[3] : 4;
-    if (tx * ty > 128) ty = 128 / tx;
+  if (nrowsU > 0 && tiled) {
+    GcmProfScope ps(GCM_K_UPDATE_TILED, stream);
+    const size_t smt = (size_t)PFT_NS * PFT_STAGE * sizeof(double);
+    // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every
+    // row, so a band stays bit-identical to the whole grid)
+    const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (parts[s2].n1 <= 0) continue;
+      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + PFT_TJ - 1) / PFT_TJ, nbatch), blockt(PFT_TI, PFT_TJ);
+      GCM_LAUNCH((pe25f_update_tiled_kernel<L>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      GCM_CHECK_LAUNCH();
+    }
+  } else if (nrowsU > 0) {
+    // direct loads: 32 x 4 (i x j) tiles; rows shorter than 128 that do not fill 32-wide tiles run flat over
+    // (row, column)
+    GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
     const bool flat = W < 128 && W % 32 != 0 && (size_t)nrowsU * W < (1u << 22);
     const unsigned flatW = flat ? gcm_magic((unsigned)W) : 0u;
-    const dim3 block(tx, ty);
-    const dim3 grid = flat ? dim3((nrowsU * W + tx * ty - 1) / (tx * ty), 1, nbatch)
-                           : dim3((W + tx - 1) / tx, (nrowsU + ty - 1) / ty, nbatch);
-    const int pfd = g_gcm_knob[10] > 0 ? g_gcm_knob[10] - 1 : 1;  // prefetch distance in layers (knob: value + 1)
-    const bool tiled = W % PFT_TI == 0 && g_gcm_knob[15] != 1;  // staged tiles (knob 15 = 1: direct loads)
-    GcmProfScope ps(tiled ? GCM_K_UPDATE_TILED : GCM_K_UPDATE_FAST, stream);
-    if (tiled) {
-      const int ns = g_gcm_knob[4] == 4 ? 4 : (g_gcm_knob[4] == 5 ? 5 : 3);  // knob 4: stages of the copy pipeline
-      const size_t smt = (size_t)ns * PFT_STAGE * sizeof(double);
-      // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every
-      // row, so a band stays bit-identical to the whole grid)
-      const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
-      for (int s2 = 0; s2 < 2; ++s2) {
-        if (parts[s2].n1 <= 0) continue;
-        const dim3 gridt(W / PFT_TI, (parts[s2].n1 + PFT_TJ - 1) / PFT_TJ, nbatch), blockt(PFT_TI, PFT_TJ);
-#define PF_TILED(NS, MINB) \
-  GCM_LAUNCH((pe25f_update_tiled_kernel<L, NS, MINB>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3)
-        if (g_gcm_knob[0] == 3) PF_TILED(3, 3);       // knob 0 = 3: 168 registers, three CTAs per SM
-        else if (ns == 4) PF_TILED(4, 4);
-        else if (ns == 5) PF_TILED(5, 4);
-        else PF_TILED(3, 4);
-#undef PF_TILED
-        GCM_CHECK_LAUNCH();
-      }
-      return GCM_OK;
-    }
-#define PF_UPD(MINB, PF) \
-  GCM_LAUNCH((pe25f_update_kernel<L, MINB, PF>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, g_gcm_knob[14], flatW, b2, b3)
-    if (pfd > 0) {
-      switch (g_gcm_knob[0]) {  // registers per thread vs resident warps (tuning knob 0)
-        case 2: PF_UPD(2, true); break;
-        case 3: PF_UPD(3, true); break;
-        case 5: PF_UPD(5, true); break;
-        case 6: PF_UPD(6, true); break;
-        default: PF_UPD(4, true); break;
-      }
-    } else {
-      switch (g_gcm_knob[0]) {
-        case 3: PF_UPD(3, false); break;
-        case 4: PF_UPD(4, false); break;
-        default: PF_UPD(2, false); break;
-      }
-    }
-#undef PF_UPD
+    const dim3 block(32, 4);
+    const dim3 grid = flat ? dim3((nrowsU * W + 127) / 128, 1, nbatch) : dim3((W + 31) / 32, (nrowsU + 3) / 4, nbatch);
+    const int pfd = g_gcm_knob[5] > 0 ? g_gcm_knob[5] - 1 : 1;
+    GCM_LAUNCH((pe25f_update_kernel<L>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, flatW, b2, b3);
+    GCM_CHECK_LAUNCH();
   }
-  GCM_CHECK_LAUNCH();
   return GCM_OK;
 }
 

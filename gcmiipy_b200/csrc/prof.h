@@ -8,8 +8,8 @@ enum GcmProfKind {
   GCM_K_COLUMN = 1,       // pe25_column_kernel
   GCM_K_FILTER_PGF = 2,   // pe25_pgf_filter_kernel
   GCM_K_UPDATE = 3,       // pe25_update_kernel
-  GCM_K_ROW = 4,          // pe25f_row_kernel    (pe25_fast.cu)
-  GCM_K_UPDATE_FAST = 5,  // pe25f_update_kernel (pe25_fast.cu)
+  GCM_K_ROW = 4,          // (unused: the single-launch row kernel of rounds r01d-r01o)
+  GCM_K_UPDATE_FAST = 5,  // pe25f_update_kernel (pe25_fast.cu, direct loads)
   GCM_K_FILTER_A = 6,     // pe25f_filter_kernel<1>
   GCM_K_COLUMN_F = 7,     // pe25f_hydro_kernel
   GCM_K_FILTER_B = 8,     // pe25f_filter_kernel<0>

@@ -105,11 +105,11 @@ int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base, const gcm_
 int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt, int nsteps,
                           int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Kernel path of the half step: 0 (default) = the fused ALU-lean kernels of pe25_fast.cu whenever the
- * geometry allows (L in {3, 9}, W a product of 2, 3, 5, one row of all layers fits shared memory), else
- * the general 4-kernel path; 1 = always the general path (A/B comparisons, widths with other prime factors). */
+/* Kernel path of the half step: 0 (default) = the fused kernels of pe25_fast.cu whenever the geometry allows
+ * (L in {3, 9}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
+ * comparisons, widths with other prime factors). */
 int gcm_pe25_select_path(int path);
-/* launch-shape tuning knobs of the fused kernels (see pe25_fast.cu); 0 = automatic */
+/* launch-shape tuning knobs of the fused kernels (idx 0..7, see pe25_fast.cu); 0 = automatic */
 int gcm_tuning_knob(int idx, int value);
 
 /* the operators half_timestep is built from, each on the owned rows of one member */
