@@ -25,6 +25,7 @@ SOURCES = {
     "geom.cu": [],
     "prof.cu": [],
     "comm.cu": [],
+    "host_step.cu": [],
     "pe25.cu": ["-fmad=false"],
     "pe25_fast.cu": [],
     "sw2d.cu": ["-fmad=false"],

@@ -614,6 +614,7 @@ int g_gcm_knob[8] = {0};
 //   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream
 //   4  1 = update kernel with direct global loads even when W % 32 == 0
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
+//   6  latitude blocks of the host-resident step (host_step.cu)
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;

@@ -105,6 +105,16 @@ int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base, const gcm_
 int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt, int nsteps,
                           int nbatch, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* dynamics.matsuno_timestep once for a caller whose state lives in HOST memory (what the reference's callers have:
+ * numpy arrays in, numpy arrays out).  The grid is cut into latitude blocks that are copied in, stepped and copied
+ * out on three streams, so both directions of the PCIe link run at once and the kernels hide under the copies
+ * (csrc/host_step.cu); bit-identical to gcm_pe25_matsuno_step.  h_in / h_out: host states (pinned for full speed);
+ * d_cur, d_star, d_nxt: device scratch states of the grid's shape (d_nxt also ends up holding the new state).
+ * nblocks <= 0: automatic.  Whole-grid geometry, one member.  Stream-ordered: h_out is valid after the stream syncs. */
+int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_in, const gcm_state* h_out, const gcm_state* d_cur,
+                               const gcm_state* d_star, const gcm_state* d_nxt, double dt, int nblocks,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Kernel path of the half step: 0 (default) = the fused kernels of pe25_fast.cu whenever the geometry allows
  * (L in {3, 9}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
  * comparisons, widths with other prime factors). */

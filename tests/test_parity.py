@@ -339,6 +339,37 @@ def test_nonfinite_input_propagates_like_numpy(backend):
     assert np.isnan(out[1]).any()
 
 
+@pytest.mark.parametrize("H,W,L", [(64, 32, 3), (70, 36, 9), (24, 36, 9)])
+def test_step_host_is_bit_identical_to_resident_step(backend, H, W, L):
+    """Stepper.step_host -> gcm_pe25_matsuno_step_host: latitude blocks copied in, stepped (predictor rows recomputed
+    across block edges, two-segment launches across the periodic edge) and copied out on three streams; on the
+    emulator and for H < 64 the one-block form.  Must equal the device-resident step bit for bit."""
+    import torch
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    s = O.synthetic_state(og, seed=H + W)
+    ref = dynamics.Stepper(geom, *s)
+    ref.step(100.0, 2)
+    st = dynamics.Stepper(geom, *s)
+    from gcmiipy_b200 import _lib
+    _lib.lib().gcm_tuning_knob(6, 8 if H >= 64 else 0)       # small grids pipeline only on request
+    hin = [torch.from_numpy(np.ascontiguousarray(a)).clone() for a in s]
+    hout = [torch.empty_like(a) for a in hin]
+    if torch.cuda.is_available() and backend == "gpu":
+        hin = [a.pin_memory() for a in hin]
+        hout = [a.pin_memory() for a in hout]
+    for _ in range(2):
+        st.step_host(hin, hout, 100.0, 1)
+        if backend == "gpu":
+            torch.cuda.synchronize()
+        hin, hout = hout, hin
+    for a, b in zip(hin, ref.download()):
+        exact(a.numpy(), b)
+    _lib.lib().gcm_tuning_knob(6, 0)
+    for a, b in zip(st.download(), ref.download()):
+        exact(a, b)
+
+
 # ---- full-size properties (BASELINE sizes, no CPU reference needed) ---------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,L,dt", [(180, 288, 9, 60.0), (720, 1440, 9, 10.0)])
