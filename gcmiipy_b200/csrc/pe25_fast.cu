@@ -418,18 +418,16 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 // memory.  Needs W % 32 == 0; one launch per row segment.
 // ---------------------------------------------------------------------------------------------------
 #define PFT_TI 32
-#define PFT_TJ 4
 #define PFT_NS 3  // layers in flight
 #define PFT_ROW (PFT_TI + 2)
-#define PFT_TILE ((PFT_TJ + 2) * PFT_ROW)
-#define PFT_NF 5                    // staged fields: su, sv, st, sq, spu
-#define PFT_STAGE (PFT_NF * PFT_TILE)  // doubles per stage
+#define PFT_NF 5  // staged fields: su, sv, st, sq, spu
 
-template <int L>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 4)
+template <int L, int PFT_TJ>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
   GCM_DYN_SMEM(double, sm);
+  constexpr int PFT_TILE = (PFT_TJ + 2) * PFT_ROW, PFT_STAGE = PFT_NF * PFT_TILE;  // doubles per field tile / stage
   const int H = g.H, W = g.W, plane = H * W, wrap = g.wrap_j;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PFT_TI + tx;
   const int i = blockIdx.x * PFT_TI + tx;
@@ -683,7 +681,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
 #endif
     // hydro launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
     const int nchunk = (W + 30) / 31;
-    int rg = 4;
+    int rg = 8;
     while (rg > 1 && (size_t)nchunk * ((nrowsR + rg - 1) / rg) * nbatch < 2368) rg /= 2;
     if (g_gcm_knob[2] > 0) rg = g_gcm_knob[2];
     if (segR.n2 > 0) rg = 1;  // a group of rows must be contiguous
@@ -727,14 +725,15 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   }
   if (nrowsU > 0 && tiled) {
     GcmProfScope ps(GCM_K_UPDATE_TILED, stream);
-    const size_t smt = (size_t)PFT_NS * PFT_STAGE * sizeof(double);
     // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every
     // row, so a band stays bit-identical to the whole grid)
     const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
+    constexpr int tj = 4;  // tile height (8 measured slower on B200: r02a)
+    const size_t smt = (size_t)PFT_NS * PFT_NF * (tj + 2) * PFT_ROW * sizeof(double);
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
-      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + PFT_TJ - 1) / PFT_TJ, nbatch), blockt(PFT_TI, PFT_TJ);
-      GCM_LAUNCH((pe25f_update_tiled_kernel<L>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(PFT_TI, tj);
+      GCM_LAUNCH((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       GCM_CHECK_LAUNCH();
     }
   } else if (nrowsU > 0) {
