@@ -9,7 +9,8 @@ class GeomDesc(C.Structure):
     _fields_ = [("H", C.c_int), ("W", C.c_int), ("L", C.c_int), ("wrap_j", C.c_int), ("row_lo", C.c_int),
                 ("row_hi", C.c_int), ("zero_v_row", C.c_int), ("dy", C.c_double), ("ptop", C.c_double),
                 ("h_sig", C.c_void_p), ("h_dsig", C.c_void_p), ("h_sigb", C.c_void_p), ("h_sigt", C.c_void_p),
-                ("h_dx_j", C.c_void_p), ("h_dx_h", C.c_void_p), ("h_heightmap", C.c_void_p), ("h_smmz", C.c_void_p)]
+                ("h_dx_j", C.c_void_p), ("h_dx_h", C.c_void_p), ("h_heightmap", C.c_void_p), ("h_smmz", C.c_void_p),
+                ("zero_v_row2", C.c_int)]
 
 
 class State(C.Structure):

@@ -25,13 +25,22 @@ from .geometry import device_geom
 HALO_N, HALO_S = 1, 2
 
 
+def _wide_ok(geom):
+    """The one-exchange schedule needs the row-segment kernels (fused path: 3 or 9 layers, W a product of 2, 3, 5)."""
+    W = geom.width
+    for f in (2, 3, 5):
+        while W % f == 0:
+            W //= f
+    return geom.layers in (3, 9) and W == 1
+
+
 class BandStepper:
     """One rank's latitude band of the model state, advanced by `gcm_pe25_half_step` around halo exchanges.
 
     rank / world default to the initialised torch.distributed group (NCCL on GPUs).  world == 1 runs the same
     band code against itself (the ring closes on the rank's own rows)."""
 
-    def __init__(self, geom, p, u, v, t, q, rank=None, world=None, group=None, native=None):
+    def __init__(self, geom, p, u, v, t, q, rank=None, world=None, group=None, native=None, wide_halo=True):
         self.group = group
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -45,9 +54,15 @@ class BandStepper:
         if self.owned_rows < HALO_S:
             raise ValueError("a band needs at least %d rows" % HALO_S)
         self.j0, self.j1 = rank * self.owned_rows, (rank + 1) * self.owned_rows
-        self.dg = device_geom(geom, band=(self.j0, self.j1, HALO_N, HALO_S))
+        full0 = _host.dev(p)
+        if native is None:
+            native = full0.is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
+        # native ring: twice the halo (2 north, 4 south) buys ONE exchange per step (see csrc/comm.cu)
+        wide = bool(native) and wide_halo and self.owned_rows >= 2 * HALO_S and _wide_ok(geom)
+        self.halo_n, self.halo_s = (2 * HALO_N, 2 * HALO_S) if wide else (HALO_N, HALO_S)
+        self.dg = device_geom(geom, band=(self.j0, self.j1, self.halo_n, self.halo_s))
         self.family = _host.Family(p, u, v, t, q)
-        rows = torch.arange(self.j0 - HALO_N, self.j1 + HALO_S) % H
+        rows = torch.arange(self.j0 - self.halo_n, self.j1 + self.halo_s) % H
         full = [_host.dev(x) for x in (p, u, v, t, q)]
         rows = rows.to(full[0].device)
         self.cur = [x.index_select(x.dim() - 2, rows).contiguous() for x in full]
@@ -64,8 +79,6 @@ class BandStepper:
         self.nsteps_done = 0
         self.overlap = True
         self.comm = None
-        if native is None:
-            native = self.cur[0].is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
         if native:
             self._make_comm()
 

@@ -7,7 +7,9 @@
 //                 unpacks into the halo rows, then computes the three rows next to the halos
 //                 (gcm_pe25_half_step_rows, two-segment launches);
 //   main stream : meanwhile computes the interior rows (they read owned rows only) and joins the side stream.
-// The whole loop over steps runs here, so the host cost per step is a dozen launches and two NCCL groups.
+// With 2 + 4 halo rows the band exchanges ONCE per step and recomputes the three predictor rows its corrector reads
+// across the edges.  The whole loop over steps runs here, so the host cost per step is a dozen launches and one or
+// two NCCL groups.
 //
 // NCCL is bound at run time (dlopen of the libnccl the process already uses -- torch's -- else the system one): the
 // library has no link-time dependency on it, so single-GPU users and the CPU-side ABI check never need NCCL.
@@ -145,18 +147,18 @@ extern "C" int gcm_halo_pack(const gcm_geom*, const gcm_state*, int, int, double
 extern "C" int gcm_halo_unpack(const gcm_geom*, const gcm_state*, int, int, const double*, void*);
 extern "C" int gcm_halo_copy_rows(const gcm_geom*, const gcm_state*, int, const gcm_state*, int, int, void*);
 
-// fill the halo rows of `s` (1 north, 2 south) from the ring neighbours, on stream `q`
-static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, cudaStream_t q) {
+// fill the halo rows of `s` (hn north, hs south) from the ring neighbours, on stream `q`
+static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, cudaStream_t q) {
   const int lo = g->d.row_lo, hi = g->d.row_hi;
   int st;
   if (c->nranks == 1) {  // the ring closes on the band itself
-    if ((st = gcm_halo_copy_rows(g, s, lo, s, hi, GCM_HALO_S, q))) return st;
-    return gcm_halo_copy_rows(g, s, hi - GCM_HALO_N, s, lo - GCM_HALO_N, GCM_HALO_N, q);
+    if ((st = gcm_halo_copy_rows(g, s, lo, s, hi, hs, q))) return st;
+    return gcm_halo_copy_rows(g, s, hi - hn, s, lo - hn, hn, q);
   }
 #ifdef GCM_EMU
   return GCM_EUNSUP;
 #else
-  const size_t ns = gcm_halo_buffer_doubles(g, GCM_HALO_S), nn = gcm_halo_buffer_doubles(g, GCM_HALO_N);
+  const size_t ns = gcm_halo_buffer_doubles(g, hs), nn = gcm_halo_buffer_doubles(g, hn);
   if (c->buf_doubles < 2 * (ns + nn)) {
     if (c->buf) cudaFree(c->buf);
     c->buf = nullptr;
@@ -165,16 +167,16 @@ static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, cud
   }
   double *send_n = c->buf, *send_s = send_n + ns, *recv_s = send_s + nn, *recv_n = recv_s + ns;
   const int north = (c->rank + c->nranks - 1) % c->nranks, south = (c->rank + 1) % c->nranks;
-  if ((st = gcm_halo_pack(g, s, lo, GCM_HALO_S, send_n, q))) return st;               // -> north's south halo
-  if ((st = gcm_halo_pack(g, s, hi - GCM_HALO_N, GCM_HALO_N, send_s, q))) return st;  // -> south's north halo
+  if ((st = gcm_halo_pack(g, s, lo, hs, send_n, q))) return st;       // first owned rows -> north's south halo
+  if ((st = gcm_halo_pack(g, s, hi - hn, hn, send_s, q))) return st;  // last owned rows  -> south's north halo
   GCM_NCCL(g_nccl.GroupStart());
   GCM_NCCL(g_nccl.Send(send_n, ns, 8 /* ncclFloat64 */, north, c->comm, q));
   GCM_NCCL(g_nccl.Send(send_s, nn, 8, south, c->comm, q));
   GCM_NCCL(g_nccl.Recv(recv_s, ns, 8, south, c->comm, q));
   GCM_NCCL(g_nccl.Recv(recv_n, nn, 8, north, c->comm, q));
   GCM_NCCL(g_nccl.GroupEnd());
-  if ((st = gcm_halo_unpack(g, s, hi, GCM_HALO_S, recv_s, q))) return st;
-  return gcm_halo_unpack(g, s, lo - GCM_HALO_N, GCM_HALO_N, recv_n, q);
+  if ((st = gcm_halo_unpack(g, s, hi, hs, recv_s, q))) return st;
+  return gcm_halo_unpack(g, s, lo - hn, hn, recv_n, q);
 #endif
 }
 
@@ -192,7 +194,7 @@ static int band_half_step(const gcm_geom* g, gcm_comm* c, const gcm_state* base,
     const int rb[4] = {lo, 1, hi - 1, 2}, ub[4] = {lo, 1, hi - 2, 2};
     GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // `star` is complete on the main stream
     GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
-    if ((st = band_exchange(g, c, star, c->stream))) return st;
+    if ((st = band_exchange(g, c, star, GCM_HALO_N, GCM_HALO_S, c->stream))) return st;
     st = gcm_pe25_half_step_rows(g, base, star, out, dt, 1, ws, ws_bytes, ri, none, main);
     if (st == GCM_OK) {
       GCM_CUDA(cudaEventRecord(c->ev_rint, main));  // row phase of the interior is done
@@ -213,7 +215,7 @@ static int band_half_step(const gcm_geom* g, gcm_comm* c, const gcm_state* base,
   (void)overlap;
   (void)n;
 #endif
-  if ((st = band_exchange(g, c, star, main))) return st;
+  if ((st = band_exchange(g, c, star, GCM_HALO_N, GCM_HALO_S, main))) return st;
   return gcm_pe25_half_step(g, base, star, out, dt, 1, ws, ws_bytes, main);
 }
 
@@ -226,14 +228,27 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
   GCM_REQUIRE(g && c && cur && star && nxt && ws, GCM_ENULL);
   GCM_REQUIRE(nsteps > 0, GCM_ESHAPE);
   GCM_REQUIRE(!g->d.wrap_j, GCM_EUNSUP);
-  GCM_REQUIRE(g->d.row_lo == GCM_HALO_N && g->d.row_hi + GCM_HALO_S == g->d.H, GCM_ESHAPE);
-  GCM_REQUIRE(g->d.row_hi - g->d.row_lo >= GCM_HALO_S, GCM_ESHAPE);
+  const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi, lo = g->d.row_lo, n = g->d.row_hi - g->d.row_lo;
+  const bool wide = hn == 2 * GCM_HALO_N && hs == 2 * GCM_HALO_S;
+  GCM_REQUIRE(wide || (hn == GCM_HALO_N && hs == GCM_HALO_S), GCM_ESHAPE);
+  GCM_REQUIRE(n >= hs, GCM_ESHAPE);
   cudaStream_t main = (cudaStream_t)stream;
   const gcm_state *a = cur, *b = nxt;
   int st;
   for (int s = 0; s < nsteps; ++s) {
-    if ((st = band_half_step(g, c, a, a, star, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:231
-    if ((st = band_half_step(g, c, a, star, b, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:234
+    if (wide) {
+      // ONE exchange per step: with 2 + 4 halo rows of the base state the band computes the predictor also on the
+      // three rows its corrector reads across the band edges (the neighbours compute the same values from the same
+      // inputs with the same kernels), so the star state needs no exchange.  Halves the latency-bound messages.
+      if ((st = band_exchange(g, c, a, hn, hs, main))) return st;
+      const int rp[4] = {lo - 1, n + 4, 0, 0}, up[4] = {lo - 1, n + 3, 0, 0};
+      const int rc[4] = {lo, n + 1, 0, 0}, uc[4] = {lo, n, 0, 0};
+      if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;  // dynamics.py:231
+      if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, uc, main))) return st;  // dynamics.py:234
+    } else {
+      if ((st = band_half_step(g, c, a, a, star, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:231
+      if ((st = band_half_step(g, c, a, star, b, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:234
+    }
     const gcm_state* t = a;
     a = b;
     b = t;

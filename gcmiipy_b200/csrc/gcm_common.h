@@ -131,7 +131,7 @@ struct GcmGeomDev {
   int H, W, L;
   int wrap_j;
   int row_lo, row_hi;
-  int zero_v_row;
+  int zero_v_row, zero_v_row2;
   double dy, ptop;
   const double* sig;
   const double* dsig;

@@ -109,6 +109,7 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   // a band needs 1 halo row to the north and 2 to the south of its owned rows
   if (!d->wrap_j) GCM_REQUIRE(d->row_lo >= 1 && d->row_hi + 2 <= H, GCM_ESHAPE);
   GCM_REQUIRE(d->zero_v_row >= -1 && d->zero_v_row < H, GCM_ESHAPE);
+  GCM_REQUIRE(d->zero_v_row2 >= -1 && d->zero_v_row2 < H, GCM_ESHAPE);
 
   gcm_geom* g = (gcm_geom*)calloc(1, sizeof(gcm_geom));
   GCM_REQUIRE(g, (int)cudaErrorMemoryAllocation);
@@ -199,6 +200,7 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   g->d.wrap_j = d->wrap_j ? 1 : 0;
   g->d.row_lo = d->row_lo; g->d.row_hi = d->row_hi;
   g->d.zero_v_row = d->zero_v_row;
+  g->d.zero_v_row2 = d->zero_v_row2;
   g->d.dy = d->dy; g->d.ptop = d->ptop;
   g->d.sig = (const double*)(b + o_sig);
   g->d.dsig = (const double*)(b + o_dsig);

@@ -333,7 +333,7 @@ __global__ void pe25_update_kernel(GcmGeomDev g, GcmStateC base, GcmStateC star,
   const double pv_n = pv - (dvt + dvs + phiv + pgv) * dt;
   out.u[o3 + c] = pu_n / ((pn_c + pn_ip) / 2);
   double v_n = pv_n / ((pn_c + pn_jp) / 2);
-  if (j == g.zero_v_row) v_n *= 0.0;  // dynamics.py:222
+  if (j == g.zero_v_row || j == g.zero_v_row2) v_n *= 0.0;  // dynamics.py:222
   out.v[o3 + c] = v_n;
 
   const double adv_t = gcm_cell_advec_t(g, st, fpu, fpv, k, j, jm, jp, i, im, ip);

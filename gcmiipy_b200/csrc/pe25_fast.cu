@@ -320,7 +320,7 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
   const double a_jm = (sp_jm + sp_c) * 0.5;                  // (j-1, i)
   const double a_jm_ip = (sp[e_jm_ip] + sp_ip) * 0.5;        // (j-1, i+1)
   const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;       // (j+1, i)
-  const bool zero_v = j == g.zero_v_row;
+  const bool zero_v = j == g.zero_v_row || j == g.zero_v_row2;
 
   // vertical neighbours and interface fluxes carried in registers (advec_sig, dynamics.py:49-52)
   double u_k = su[e_c], v_k = sv[e_c], t_k = st[e_c], q_k = sq[e_c];
@@ -500,7 +500,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const double a_jm = (sp_jm + sp_c) * 0.5;                    // (j-1, i)
   const double a_jm_ip = (sp[jm * W + ip] + sp_ip) * 0.5;      // (j-1, i+1)
   const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;         // (j+1, i)
-  const bool zero_v = j == g.zero_v_row;
+  const bool zero_v = j == g.zero_v_row || j == g.zero_v_row2;
   // sd (dynamics.py:42-44) of the three columns the vertical fluxes need -- (j, i), (j, i+1), (j+1, i) -- is rebuilt
   // from pit and the running sums of conv, whose operands the horizontal advection loads anyway:
   //   sd[k] = sum_{l >= k} conv[l] - pit sigb[k] = (pit - sum_{l < k} conv[l]) - pit sigb[k],   sd[0] = 0

@@ -153,6 +153,7 @@ def device_geom(geom, band=None):
     dx_j, dx_h = _vec(geom.dx_j, H), _vec(geom.dx_h, H)
     hmap = np.ascontiguousarray(_host.magnitude(geom.heightmap), dtype=np.float64).reshape(H, W)
     smmz = polar_filter_table(geom, W) if W > 1 else None
+    zero_v2 = -1
     if band is None:
         Hs, row_lo, row_hi, wrap, zero_v = H, 0, H, 1, H - 1
     else:
@@ -161,11 +162,15 @@ def device_geom(geom, band=None):
         Hs, row_lo, row_hi, wrap = len(rows), hn, hn + (j1 - j0), 0
         dx_j, dx_h, hmap = dx_j[rows].copy(), dx_h[rows].copy(), np.ascontiguousarray(hmap[rows])
         smmz = np.ascontiguousarray(smmz[rows]) if smmz is not None else None
-        own = np.nonzero(rows[row_lo:row_hi] == H - 1)[0]
-        zero_v = int(row_lo + own[0]) if len(own) else -1
+        # stored rows that hold the global last row (the wall, dynamics.py:222): among the owned rows and, for the
+        # one-exchange schedule, among the halo rows whose predictor the band recomputes
+        lo_c, hi_c = max(row_lo - 1, 0), min(row_hi + 2, Hs)
+        wall = [int(lo_c + r) for r in np.nonzero(rows[lo_c:hi_c] == H - 1)[0]]
+        zero_v = wall[0] if wall else -1
+        zero_v2 = wall[1] if len(wall) > 1 else -1
     desc = _abi.GeomDesc(Hs, W, L, wrap, row_lo, row_hi, zero_v, _host.scalar(geom.dy), _host.scalar(geom.ptop),
                          _host.hptr(sig), _host.hptr(dsig), _host.hptr(sigb), _host.hptr(sigt), _host.hptr(dx_j),
-                         _host.hptr(dx_h), _host.hptr(hmap), _host.hptr(smmz))
+                         _host.hptr(dx_h), _host.hptr(hmap), _host.hptr(smmz), zero_v2)
     handle = ctypes.c_void_p()
     _lib.check(_lib.lib().gcm_geom_create(ctypes.byref(desc), ctypes.byref(handle)), "gcm_geom_create")
     obj = DeviceGeom(handle, Hs, W, L, row_lo, row_hi, wrap)

@@ -66,6 +66,8 @@ typedef struct {
   const double* h_dx_h;     /* [H]  geometry.py:137 */
   const double* h_heightmap;/* [H*W] geometry.py:149 (m); NULL = zeros */
   const double* h_smmz;     /* [H*(W/2+1)] polar-filter multipliers, low_pass.py:61-72; NULL iff W == 1 */
+  int zero_v_row2;  /* a second stored row holding the global last row (a band whose halo rows are recomputed by the
+                       one-exchange schedule of gcm_band_matsuno_step can hold it twice); -1 if absent */
 } gcm_geom_desc;
 
 int gcm_geom_create(const gcm_geom_desc* desc, gcm_geom** out);

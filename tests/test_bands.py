@@ -67,13 +67,15 @@ def test_band_with_tiled_update_is_bit_identical(backend):
         assert np.array_equal(a, b)
 
 
-def test_native_band_loop_single_rank(backend):
-    """gcm_band_matsuno_step (csrc/comm.cu): the C++ loop with the ring closed on the band itself.  On the GPU this
-    runs the overlapped schedule (side stream, interior rows first, two-segment launches next to the halos)."""
+@pytest.mark.parametrize("wide", [True, False])
+def test_native_band_loop_single_rank(backend, wide):
+    """gcm_band_matsuno_step (csrc/comm.cu): the C++ loop with the ring closed on the band itself.  wide: 2 + 4 halo
+    rows, one exchange per step, predictor recomputed on the rows across the band edges; else 1 + 2 halo rows, two
+    exchanges, and on the GPU the overlapped schedule (side stream, interior rows first, two-segment launches)."""
     geom, s = _case()
     whole = dynamics.Stepper(geom, *s)
-    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
-    assert band.comm is not None
+    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True, wide_halo=wide)
+    assert band.comm is not None and (band.halo_n, band.halo_s) == ((2, 4) if wide else (1, 2))
     for n in (3, 2):                                    # odd, then even: both buffer parities
         whole.step(450.0, n)
         band.step(450.0, n)

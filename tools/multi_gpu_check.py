@@ -39,8 +39,8 @@ def main():
     whole.step(dt, args.steps)
     ref = whole.download()
     ok = True
-    for native, overlap in ((True, True), (True, False), (False, False)):
-        b = bands.BandStepper(geom, *s0, native=native)
+    for native, overlap, wide in ((True, False, True), (True, True, False), (True, False, False), (False, False, False)):
+        b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
         b.overlap = overlap
         b.step(dt, args.steps)
         got = b.gather()
@@ -49,16 +49,16 @@ def main():
         flag = torch.tensor([int(same and finite)], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print("bitwise %s  native=%s overlap=%s  grid %dx%dx%d  ranks %d  steps %d" %
-                  ("OK" if flag.item() else "MISMATCH", native, overlap, W, H, L, world, args.steps), flush=True)
+            print("bitwise %s  native=%s overlap=%s one_exchange=%s  grid %dx%dx%d  ranks %d  steps %d" %
+                  ("OK" if flag.item() else "MISMATCH", native, overlap, wide, W, H, L, world, args.steps), flush=True)
         ok = ok and bool(flag.item())
         del b
     if args.time:
         H, W, L, dt = 720, 1440, 9, 10.0
         geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
         s0 = synthetic.synthetic_state(geom, seed=1234)
-        for native, overlap in ((True, True), (True, False), (False, False)):
-            b = bands.BandStepper(geom, *s0, native=native)
+        for native, overlap, wide in ((True, False, True), (True, True, False), (True, False, False), (False, False, False)):
+            b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
             b.overlap = overlap
             b.step(dt, 5)
             dist.barrier()
@@ -71,8 +71,8 @@ def main():
             t = torch.tensor([e0.elapsed_time(e1) / 30], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print("time native=%s overlap=%s: %.4f ms/step  (%.3e cell-updates/s on %d GPUs)" %
-                      (native, overlap, t.item(), H * W * L / (t.item() * 1e-3), world), flush=True)
+                print("time native=%s overlap=%s one_exchange=%s: %.4f ms/step  (%.3e cell-updates/s on %d GPUs)" %
+                      (native, overlap, wide, t.item(), H * W * L / (t.item() * 1e-3), world), flush=True)
             del b
     dist.barrier()
     dist.destroy_process_group()
