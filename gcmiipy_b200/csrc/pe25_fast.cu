@@ -433,9 +433,12 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const int i = blockIdx.x * PFT_TI + tx;
   const int r = blockIdx.y * PFT_TJ + ty;
   const bool active = r < seg.n1;
-  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile; rows past the segment still exist in memory
-  int j = j0 + ty;
-  if (wrap && j >= H) j -= H;
+  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile
+  // Stored row of a tile row: periodic on a whole grid; on a band clamped into the stored rows.  Rows an active
+  // thread reads are real rows by construction (the caller's halo contract); the clamp only keeps the unused corners
+  // of a partial tile inside the arrays.
+  auto rowc = [&](int x) { return wrap ? ((x % H) + H) % H : (x < 0 ? 0 : (x >= H ? H - 1 : x)); };
+  const int j = rowc(j0 + ty);
   const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
   const double* __restrict__ p = base.p + o2;
   const double* __restrict__ sp = star.p + o2;
@@ -449,7 +452,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   double* __restrict__ ot = out.t + o3;
   double* __restrict__ oq = out.q + o3;
 
-  const int jm = gcm_row(j, -1, H, wrap), jp = gcm_row(j, 1, H, wrap), jpp = gcm_row(jp, 1, H, wrap);
+  const int jm = rowc(j0 + ty - 1), jp = rowc(j0 + ty + 1), jpp = rowc(j0 + ty + 2);
   const int im = gcm_im(i, W), ip = gcm_ip(i, W);
   const int e_c = j * W + i;
   // halo ring of the tile: north row, south row, west column, east column -> (tile row, tile column, global offset)
@@ -461,8 +464,8 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     else if (tid < 2 * PFT_ROW) { rr = PFT_TJ; cc = tid - PFT_ROW - 1; }
     else if (tid < 2 * PFT_ROW + PFT_TJ) { rr = tid - 2 * PFT_ROW; cc = -1; }
     else { rr = tid - 2 * PFT_ROW - PFT_TJ; cc = PFT_TI; }
-    int gj = j0 + rr, gi = blockIdx.x * PFT_TI + cc;
-    if (wrap) gj = gj < 0 ? gj + H : (gj >= H ? gj - H : gj);
+    const int gj = rowc(j0 + rr);
+    int gi = blockIdx.x * PFT_TI + cc;
     gi = gi < 0 ? gi + W : (gi >= W ? gi - W : gi);
     hr = rr + 1;
     hc = cc + 1;

@@ -11,7 +11,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gcmiipy_b200", "csrc")
-OUT = os.path.join(HERE, "_build")
+# GCM_EMU_ASAN=1: AddressSanitizer build (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so) and
+# ASAN_OPTIONS=detect_leaks=0): an out-of-bounds read or write of any kernel shows up on the CPU -- the bounds
+# checker for the kernel sources (compute-sanitizer is not available on every GPU pool)
+ASAN = os.environ.get("GCM_EMU_ASAN") == "1"
+OUT = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libgcm_emu.so")
 
 
@@ -26,13 +30,15 @@ def build(force=False):
     objs, procs = [], []
     flags = ["-O2", "-std=c++17", "-fPIC", "-DGCM_EMU", "-ffp-contract=off", "-I", HERE, "-I", CSRC, "-I",
              os.path.join(ROOT, "include"), "-Wno-unused-value"]
+    if ASAN:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-O1"]
     for s in srcs + [os.path.join(HERE, "cuda_emu.cpp")]:
         o = os.path.join(OUT, os.path.basename(s) + ".o")
         objs.append(o)
         procs.append(subprocess.Popen(["g++"] + flags + ["-x", "c++", "-c", s, "-o", o]))
     if any(p.wait() != 0 for p in procs):
         raise RuntimeError("emu build failed")
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-lpthread"])
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-lpthread"] + (["-fsanitize=address"] if ASAN else []))
     return LIB
 
 

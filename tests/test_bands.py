@@ -34,17 +34,19 @@ def test_single_rank_band_is_bit_identical_to_whole_grid(backend):
         assert np.array_equal(a, b)
 
 
-def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend):
-    """Bands stepped one by one in this process with halo rows taken from the whole-grid state."""
-    geom, s = _case(H=24)
+@pytest.mark.parametrize("H,W,worlds", [(24, 36, (2, 3, 4)), (18, 32, (2, 3))])
+def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, H, W, worlds):
+    """Bands stepped one by one in this process with halo rows taken from the whole-grid state.  W = 32 with 9 and 6
+    owned rows: partial tiles of the shared-memory-tiled update kernel at the band's southern edge."""
+    geom, s = _case(H=H, W=W)
     whole = dynamics.Stepper(geom, *s)
     whole.step(450.0, 1)
     ref = whole.download()
     star = dynamics.half_timestep(*s, *s, 450.0, geom)
-    for world in (2, 3, 4):
+    for world in worlds:
         for rank in range(world):
-            b = bands.BandStepper(geom, *s, rank=rank, world=world)
-            rows = np.arange(b.j0 - 1, b.j1 + 2) % 24
+            b = bands.BandStepper(geom, *s, rank=rank, world=world, native=False)
+            rows = np.arange(b.j0 - 1, b.j1 + 2) % H
             b._half(b.cur, b.cur, b.star, 450.0)
             for got, want in zip(b.star, star):
                 got = got.cpu().numpy()

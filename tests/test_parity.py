@@ -257,7 +257,8 @@ def test_run25_golden(backend, name, H, W, L):
     check_state(one, tuple(g["%s_1" % k] for k in "puvtq") if "p_1" in g else O.matsuno_timestep(*s, dt, _ogeom(g, H, W, L)), 1e-12)
 
 
-@pytest.mark.parametrize("H,W,L,dt,n", [(10, 64, 9, 300.0, 3), (7, 32, 3, 300.0, 2), (12, 96, 9, 200.0, 2)])
+@pytest.mark.parametrize("H,W,L,dt,n", [(10, 64, 9, 300.0, 3), (7, 32, 3, 300.0, 2), (12, 96, 9, 200.0, 2),
+                                        (2, 32, 3, 100.0, 2), (3, 32, 9, 100.0, 1)])
 def test_run25_tiled_update_vs_oracle(backend, H, W, L, dt, n):
     """Widths that are multiples of 32 take the shared-memory-tiled update kernel (asynchronous copies, halo ring with
     periodic wrap); H not a multiple of the tile height leaves a partial tile."""
