@@ -113,6 +113,16 @@ __device__ __forceinline__ void gcm_cp_async8(double* smem_dst, const double* gm
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
+// 16-byte form (two doubles; both addresses 16-byte aligned)
+__device__ __forceinline__ void gcm_cp_async16(double* smem_dst, const double* gmem_src) {
+#ifdef GCM_EMU
+  smem_dst[0] = gmem_src[0];
+  smem_dst[1] = gmem_src[1];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
 __device__ __forceinline__ void gcm_cp_async_commit() {
 #ifndef GCM_EMU
   asm volatile("cp.async.commit_group;" ::: "memory");

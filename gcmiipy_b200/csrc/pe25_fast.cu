@@ -419,7 +419,7 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 // ---------------------------------------------------------------------------------------------------
 #define PFT_TI 32
 #define PFT_NS 3  // layers in flight
-#define PFT_ROW (PFT_TI + 2)
+#define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
 #define PFT_NF 5  // staged fields: su, sv, st, sq, spu
 
 template <int L, int PFT_TJ>
@@ -457,28 +457,31 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const int e_c = j * W + i;
   // halo ring of the tile: north row, south row, west column, east column -> (tile row, tile column, global offset)
   int hr = 0, hc = 0, e_h = 0;
-  const bool has_halo = tid < 2 * PFT_ROW + 2 * PFT_TJ;
+  constexpr int RING_ROW = PFT_TI + 2;  // a ring row spans columns -1 .. TI
+  const bool has_halo = tid < 2 * RING_ROW + 2 * PFT_TJ;
   if (has_halo) {
     int rr, cc;  // tile coordinates, -1 .. TJ and -1 .. TI
-    if (tid < PFT_ROW) { rr = -1; cc = tid - 1; }
-    else if (tid < 2 * PFT_ROW) { rr = PFT_TJ; cc = tid - PFT_ROW - 1; }
-    else if (tid < 2 * PFT_ROW + PFT_TJ) { rr = tid - 2 * PFT_ROW; cc = -1; }
-    else { rr = tid - 2 * PFT_ROW - PFT_TJ; cc = PFT_TI; }
+    if (tid < RING_ROW) { rr = -1; cc = tid - 1; }
+    else if (tid < 2 * RING_ROW) { rr = PFT_TJ; cc = tid - RING_ROW - 1; }
+    else if (tid < 2 * RING_ROW + PFT_TJ) { rr = tid - 2 * RING_ROW; cc = -1; }
+    else { rr = tid - 2 * RING_ROW - PFT_TJ; cc = PFT_TI; }
     const int gj = rowc(j0 + rr);
     int gi = blockIdx.x * PFT_TI + cc;
     gi = gi < 0 ? gi + W : (gi >= W ? gi - W : gi);
     hr = rr + 1;
-    hc = cc + 1;
+    hc = cc + 2;
     e_h = gj * W + gi;
   }
-  const int t_c = (ty + 1) * PFT_ROW + (tx + 1);  // own position in a tile
+  const int t_c = (ty + 1) * PFT_ROW + (tx + 2);  // own position in a tile
   const int t_h = hr * PFT_ROW + hc;
 
   auto issue = [&](int k, int s) {  // stage layer k into stage s
     double* st = sm + s * PFT_STAGE;
     const int off = k * plane;
+    if ((tx & 1) == 0) {  // two columns per copy: even columns are 16-byte aligned in the tile and in the field
 #pragma unroll
-    for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
+      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async16(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
+    }
     if (has_halo) {
 #pragma unroll
       for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * PFT_TILE + t_h, fld[f] + off + e_h);
