@@ -178,7 +178,16 @@ struct gcm_geom {
   void* aux_stream;
   void* ev_fork;
   void* ev_join;
+  // two consecutive Matsuno steps (ping-pong A -> B -> A) captured as a CUDA graph for multi-step calls (pe25.cu):
+  // a small cache keyed by the buffers, dt, member count and the tuning epoch
+  void* cap_stream;
+  struct {
+    unsigned long long key[20];
+    void* exec;
+  } graph[2];
+  int graph_next;
 };
+extern int g_gcm_tuning_epoch;  // bumped by gcm_tuning_knob / gcm_pe25_select_path: cached graphs go stale
 // lazily creates the side stream and events; returns a cudaError_t / GCM_OK
 int gcm_geom_aux(const gcm_geom* g, void** stream, void** ev_fork, void** ev_join);
 

@@ -8,6 +8,7 @@
 #include "gcm_common.h"
 
 extern "C" int gcm_version(void) { return 100; }
+int g_gcm_tuning_epoch = 0;
 
 extern "C" const char* gcm_status_string(int s) {
   switch (s) {
@@ -254,6 +255,9 @@ int gcm_geom_aux(const gcm_geom* cg, void** stream, void** ev_fork, void** ev_jo
 extern "C" int gcm_geom_destroy(gcm_geom* g) {
   if (!g) return GCM_OK;
 #ifndef GCM_EMU
+  for (int s = 0; s < 2; ++s)
+    if (g->graph[s].exec) cudaGraphExecDestroy((cudaGraphExec_t)g->graph[s].exec);
+  if (g->cap_stream) cudaStreamDestroy((cudaStream_t)g->cap_stream);
   if (g->aux_stream) cudaStreamDestroy((cudaStream_t)g->aux_stream);
   if (g->ev_fork) cudaEventDestroy((cudaEvent_t)g->ev_fork);
   if (g->ev_join) cudaEventDestroy((cudaEvent_t)g->ev_join);

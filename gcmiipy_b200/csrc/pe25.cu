@@ -8,6 +8,8 @@
 // Rows are periodic in j (np.roll) when the geometry stores the whole grid and plain neighbours when it
 // stores a latitude band with halo rows; kernels B (and A) also run on the first halo row south of the
 // band because row j of the update needs pit, sd, phi, rho and filtered spu at row j + 1.
+#include <string.h>
+
 #include "fft_rows.h"
 #include "gcm_common.h"
 #include "prof.h"
@@ -402,6 +404,7 @@ static int g_pe25_path = 0;  // 0 = fused ALU-lean kernels when the geometry all
 extern "C" int gcm_pe25_select_path(int path) {
   GCM_REQUIRE(path == 0 || path == 1, GCM_EUNSUP);
   g_pe25_path = path;
+  ++g_gcm_tuning_epoch;
   return GCM_OK;
 }
 
@@ -506,6 +509,71 @@ extern "C" int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base,
                                  stream);
 }
 
+#ifndef GCM_EMU
+// cached graph of two Matsuno steps a -> b -> a; *exec stays NULL when capture is not possible (the caller then
+// launches the kernels one by one)
+static int pe25_two_step_graph(const gcm_geom* cg, const gcm_state* a, const gcm_state* b, double dt, int nbatch,
+                               const Pe25Work& w, void* ws, cudaGraphExec_t* exec) {
+  gcm_geom* g = const_cast<gcm_geom*>(cg);
+  unsigned long long key[20] = {0};
+  const double* pa[5] = {a->p, a->u, a->v, a->t, a->q};
+  const double* pb[5] = {b->p, b->u, b->v, b->t, b->q};
+  for (int f = 0; f < 5; ++f) {
+    key[f] = (unsigned long long)(uintptr_t)pa[f];
+    key[5 + f] = (unsigned long long)(uintptr_t)pb[f];
+  }
+  key[10] = (unsigned long long)(uintptr_t)ws;
+  memcpy(&key[11], &dt, sizeof(double));
+  key[12] = (unsigned long long)nbatch;
+  key[13] = (unsigned long long)g_gcm_tuning_epoch;
+  for (int s = 0; s < 2; ++s)
+    if (g->graph[s].exec && memcmp(g->graph[s].key, key, sizeof(key)) == 0) {
+      *exec = (cudaGraphExec_t)g->graph[s].exec;
+      return GCM_OK;
+    }
+  if (!g->cap_stream) {
+    cudaStream_t q;
+    GCM_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    g->cap_stream = q;
+  }
+  cudaStream_t qc = (cudaStream_t)g->cap_stream;
+  {
+    void *q2, *e1, *e2;  // the side stream and its events exist before the capture starts
+    int st0 = gcm_geom_aux(cg, &q2, &e1, &e2);
+    if (st0) return st0;
+  }
+  if (cudaStreamBeginCapture(qc, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return GCM_OK;
+  }
+  int st = pe25_half_step_impl(cg, a, a, &w.star, dt, nbatch, w, qc);
+  if (!st) st = pe25_half_step_impl(cg, a, &w.star, b, dt, nbatch, w, qc);
+  if (!st) st = pe25_half_step_impl(cg, b, b, &w.star, dt, nbatch, w, qc);
+  if (!st) st = pe25_half_step_impl(cg, b, &w.star, a, dt, nbatch, w, qc);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(qc, &graph);
+  if (st || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return st > 0 || st == GCM_OK ? GCM_OK : st;  // a capture problem is not an error: fall back to plain launches
+  }
+  cudaGraphExec_t x = nullptr;
+  const cudaError_t e2 = cudaGraphInstantiate(&x, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) {
+    cudaGetLastError();
+    return GCM_OK;
+  }
+  const int slot = g->graph_next;
+  g->graph_next = (slot + 1) % 2;
+  if (g->graph[slot].exec) cudaGraphExecDestroy((cudaGraphExec_t)g->graph[slot].exec);
+  memcpy(g->graph[slot].key, key, sizeof(key));
+  g->graph[slot].exec = x;
+  *exec = x;
+  return GCM_OK;
+}
+#endif
+
 extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, const gcm_state* out, double dt,
                                      int nsteps, int nbatch, void* ws, size_t ws_bytes, void* stream) {
   GCM_REQUIRE(g && ws, GCM_ENULL);
@@ -521,6 +589,21 @@ extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, con
   const gcm_state* cur = in;
   for (int s = 0; s < nsteps; ++s) {
     const gcm_state* dst = ((nsteps - 1 - s) % 2 == 0) ? out : &w.tmp;
+#ifndef GCM_EMU
+    // From the second step on the state ping-pongs between `out` and a scratch state: two steps (A -> B -> A) are
+    // one CUDA graph, captured once per (buffers, dt, members) and replayed -- ten launches per step become one
+    // graph launch per two steps, which is what bounds the small grids.
+    if (s >= 1 && nsteps - s >= 4 && !g_gcm_prof_on) {
+      cudaGraphExec_t exec = nullptr;
+      if ((st = pe25_two_step_graph(g, cur, dst, dt, nbatch, w, ws, &exec))) return st;
+      if (exec) {
+        const int pairs = (nsteps - s) / 2;
+        for (int r = 0; r < pairs; ++r) GCM_CUDA(cudaGraphLaunch(exec, (cudaStream_t)stream));
+        s += 2 * pairs - 1;  // the state is back in `cur` after every pair
+        continue;
+      }
+    }
+#endif
     // dynamics.py:231: predictor with star = base; :234: corrector with the predicted star state
     if ((st = pe25_half_step_impl(g, cur, cur, &w.star, dt, nbatch, w, stream))) return st;
     if ((st = pe25_half_step_impl(g, cur, &w.star, dst, dt, nbatch, w, stream))) return st;

@@ -622,6 +622,7 @@ int g_gcm_knob[8] = {0};
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
+  ++g_gcm_tuning_epoch;
   return GCM_OK;
 }
 
