@@ -85,7 +85,12 @@ __device__ __forceinline__ double pf_row_step(const GcmGeomDev& g, const double*
                                               const double* __restrict__ st, double* pgf, double* __restrict__ fv,
                                               int plane, int c2, int cn, int j, bool own, bool emit_pre, bool emit_fv,
                                               double* phi, double* rho, const double* phi_n, const double* rho_n,
-                                              double sp_n) {
+                                              double sp_n, int c2_next = -1) {
+  if (c2_next >= 0) {  // the column of the next row of the march: ask L1 for it now
+    gcm_prefetch_l1(sp + c2_next);
+#pragma unroll
+    for (int k = 0; k < L; ++k) gcm_prefetch_l1(st + k * plane + c2_next);
+  }
   const double sp_c = sp[c2];
   pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
   if (emit_pre) {
@@ -242,20 +247,23 @@ pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, 
   const int rg = nrows - grp * RG < RG ? nrows - grp * RG : RG;
   double phiA[L], rhoA[L], phiB[L], rhoB[L];
   int jn = j0;
+  int j = gcm_row(jn, 1, H, g.wrap_j);
   double spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, jn * W + i, 0, jn, own, true, false, phiA, rhoA, phiA,
-                                     rhoA, 0.0);
+                                     rhoA, 0.0, j * W + i);
   double spB = 0.0;
 #pragma unroll 1
   for (int r = 1; r <= rg; r += 2) {
-    int j = gcm_row(jn, 1, H, g.wrap_j);
+    int jnext = gcm_row(j, 1, H, g.wrap_j);
     spB = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r < rg, true, phiB, rhoB, phiA,
-                                rhoA, spA);
+                                rhoA, spA, r + 1 <= rg ? jnext * W + i : -1);
     jn = j;
+    j = jnext;
     if (r + 1 <= rg) {
-      j = gcm_row(jn, 1, H, g.wrap_j);
+      jnext = gcm_row(j, 1, H, g.wrap_j);
       spA = pf_row_step<L, PTOP0>(g, sp, st, pgf, fv, plane, j * W + i, jn * W + i, j, own, r + 1 < rg, true, phiA, rhoA,
-                                  phiB, rhoB, spB);
+                                  phiB, rhoB, spB, r + 2 <= rg ? jnext * W + i : -1);
       jn = j;
+      j = jnext;
     }
   }
 }
