@@ -220,13 +220,18 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    stepper_initial = [x.clone() for x in stepper.tensors()]
+
     def reset():
         stepper.upload(*stepper_initial)
 
-    stepper_initial = [x.clone() for x in stepper.tensors()]
-
     # ---- device-resident throughput ("value") -------------------------------------------------------
     stepper.step(dt, args.warmup)
+    # two more untimed calls of the timed call's own shape: a multi-step call replays step pairs as a CUDA graph that
+    # is captured on first use, once for each of the two buffer parities (one-time cost, not steady state)
+    for _ in range(2):
+        stepper.step(dt, args.steps)
+    reset()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

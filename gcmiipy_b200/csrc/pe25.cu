@@ -593,7 +593,8 @@ extern "C" int gcm_pe25_matsuno_step(const gcm_geom* g, const gcm_state* in, con
     // From the second step on the state ping-pongs between `out` and a scratch state: two steps (A -> B -> A) are
     // one CUDA graph, captured once per (buffers, dt, members) and replayed -- ten launches per step become one
     // graph launch per two steps, which is what bounds the small grids.
-    if (s >= 1 && nsteps - s >= 4 && !g_gcm_prof_on) {
+    // Only where launches bound the step (small grids): on the large grids the kernels are long and replay buys nothing.
+    if (s >= 1 && nsteps - s >= 4 && !g_gcm_prof_on && pe25_n3(g) * (size_t)nbatch < 2000000) {
       cudaGraphExec_t exec = nullptr;
       if ((st = pe25_two_step_graph(g, cur, dst, dt, nbatch, w, ws, &exec))) return st;
       if (exec) {
