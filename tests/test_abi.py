@@ -65,3 +65,40 @@ def test_argument_errors_are_status_codes():
     desc = _abi.GeomDesc(H=4, W=3, L=2)
     h = ctypes.c_void_p()
     assert cdll.gcm_geom_create(ctypes.byref(desc), ctypes.byref(h)) == -1     # tables missing
+    # entry points added for the band / host-resident paths: NULL handles are argument errors, nothing is launched
+    assert cdll.gcm_pe25_half_step_rows(None, None, None, None, 1.0, 1, None, 0, None, None, None) == -1
+    assert cdll.gcm_band_matsuno_step(None, None, None, None, None, 1.0, 1, 0, None, 0, None) == -1
+    assert cdll.gcm_pe25_matsuno_step_host(None, None, None, None, None, None, 1.0, 0, None, 0, None) == -1
+    assert cdll.gcm_comm_create(0, 0, None, ctypes.byref(h)) == -2
+    assert cdll.gcm_comm_unique_id(None) == -1
+    assert cdll.gcm_tuning_knob(99, 1) == -2
+
+
+def test_band_entry_points_reject_bad_geometry(backend):
+    """gcm_band_matsuno_step wants a band geometry (wrap_j = 0), gcm_pe25_matsuno_step_host a whole grid, and
+    gcm_pe25_half_step_rows row segments inside the stored rows."""
+    import numpy as np
+    import torch
+    from gcmiipy_b200 import _host, _lib, bands, dynamics, geometry
+    from gcmiipy_b200.dynamics import _struct, _workspace
+    geom = geometry.gen_geometry(12, 16, 3, sig_func=geometry.manabe_sig)
+    s = [np.ones((12, 16))] + [np.ones((3, 12, 16)) for _ in range(4)]
+    st = dynamics.Stepper(geom, *s)
+    ws, need = _workspace(st.dg, 1)
+    sc, sn = _struct(st.cur), _struct(st.nxt)
+    lib = _lib.lib()
+    seg = lambda *v: (ctypes.c_int * 4)(*v)
+    rc = lib.gcm_pe25_half_step_rows(st.dg.handle, ctypes.byref(sc), ctypes.byref(sc), ctypes.byref(sn), 1.0, 1,
+                                     _host.ptr(ws), need, seg(0, 13, 0, 0), seg(0, 12, 0, 0), _lib.stream())
+    assert rc == -2                                                      # 13 rows from row 0 of a 12-row grid
+    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
+    rc = lib.gcm_band_matsuno_step(st.dg.handle, band.comm, ctypes.byref(sc), ctypes.byref(sc), ctypes.byref(sn), 1.0, 1,
+                                   0, _host.ptr(ws), need, _lib.stream())
+    assert rc == -4                                                      # whole-grid geometry: not a band
+    bc, bn = _struct(band.cur), _struct(band.nxt)
+    host = [torch.zeros_like(x, device="cpu") for x in band.cur]
+    hs = _struct(host)
+    wsb, needb = _workspace(band.dg, 1)
+    rc = lib.gcm_pe25_matsuno_step_host(band.dg.handle, ctypes.byref(hs), ctypes.byref(hs), ctypes.byref(bc),
+                                        ctypes.byref(bc), ctypes.byref(bn), 1.0, 0, _host.ptr(wsb), needb, _lib.stream())
+    assert rc == -4                                                      # band geometry: not a whole grid
