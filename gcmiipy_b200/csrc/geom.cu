@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "gcm_common.h"
+#include "fft_rows.h"
 
 extern "C" int gcm_version(void) { return 100; }
 int g_gcm_tuning_epoch = 0;
@@ -74,6 +75,24 @@ int gcm_fft_make_plan(int n, GcmFftPlan* plan) {
       best[nbest - 1] = odd;
       break;
     }
+  // tuning hook: GCM_FFT_PLAN="16,10,9" overrides the radix sequence of the smooth part (product must match)
+  if (const char* env = getenv("GCM_FFT_PLAN")) {
+    int over[16], no = 0, prod = 1;
+    for (const char* c = env; *c && no < 16;) {
+      const int r = atoi(c);
+      if (r < 2) break;
+      over[no++] = r;
+      prod *= r;
+      while (*c && *c != ',') ++c;
+      if (*c == ',') ++c;
+    }
+    bool ok = prod == smooth;
+    for (int a = 0; a < no; ++a) ok = ok && gcm_radix_unrolled(over[a]);
+    if (ok) {
+      nbest = no;
+      memcpy(best, over, no * sizeof(int));
+    }
+  }
   for (int a = 0; a < nbest; ++a) plan->radix[plan->npass++] = best[a];
   for (int p = 7; m > 1; p += 2)
     while (m % p == 0) {
