@@ -268,6 +268,81 @@ pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, 
   }
 }
 
+// Hydrostatic columns on narrow grids (W < 62, the ensemble members): a 31-column warp chunk would leave most lanes
+// idle, so a CTA takes G whole row groups (G * W threads, one column each) and the east neighbour comes through
+// shared memory instead of a shuffle.  Same arithmetic as pe25f_hydro_kernel.
+template <int L, bool PTOP0>
+__global__ void __launch_bounds__(256, 2)
+pe25f_hydro_narrow_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, int G, size_t bstride2,
+                          size_t bstride3) {
+  GCM_DYN_SMEM(double, xs);  // [2 parities][2 L + 1 values][blockDim.x]
+  const int H = g.H, W = g.W, plane = H * W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nrows = seg.n1 + seg.n2, ngrp = (nrows + RG - 1) / RG;
+  const int gl = tid / W, i = tid - gl * W;
+  const int grp = blockIdx.x * G + gl;
+  const bool valid = gl < G && grp < ngrp;
+  const size_t o2 = blockIdx.y * bstride2, o3 = blockIdx.y * bstride3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ st = star.t + o3;
+  double* pgf = w.pgf + o3;
+  double* __restrict__ fv = w.fv + o3;
+  const int te = i + 1 < W ? tid + 1 : tid - (W - 1);  // thread of the east neighbour (periodic within the row)
+  const int j0 = valid ? gcm_seg_row(seg, grp * RG) : 0;
+  const int rg = valid ? (nrows - grp * RG < RG ? nrows - grp * RG : RG) : 0;
+  double phi_n[L], rho_n[L];
+  double sp_n = 0.0;
+  int j = j0, jn = j0;
+  for (int r = 0; r <= RG; ++r) {  // the same trip count for every thread of the block: barriers inside
+    double* xr = xs + (r & 1) * (2 * L + 1) * nthr;
+    const bool row_ok = valid && r <= rg;
+    double phi[L], rho[L];
+    double sp_c = 1.0;
+    const int c2 = j * W + i;
+    if (row_ok) {
+      sp_c = sp[c2];
+      pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
+      xr[tid] = sp_c;
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        xr[(1 + k) * nthr + tid] = phi[k];
+        xr[(1 + L + k) * nthr + tid] = rho[k];
+      }
+    }
+    __syncthreads();
+    if (row_ok && r < rg) {  // pgfu + phiu of row j (dynamics.py:159, :162-165)
+      const double sp_e = xr[te];
+      const double rdxj = g.rdx_j[j];
+      const double psum = sp_c + sp_e, gradp = (sp_e - sp_c) * rdxj;
+      const double a_u = psum * gradp, b_u = psum * 0.5 * rdxj;
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const double phi_e = xr[(1 + k) * nthr + te], rho_e = xr[(1 + L + k) * nthr + te];
+        pgf[k * plane + c2] = g.c_sig[k] * a_u * gcm_rcp(rho[k] + rho_e) + b_u * (phi_e - phi[k]);
+      }
+    }
+    if (row_ok && r >= 1) {  // fv = phiv + pgv of the row to the north (dynamics.py:160, :167-169)
+      const int cn = jn * W + i;
+      const double rdy = g.rdy;
+      const double psum = sp_n + sp_c;
+      const double a_v = psum * ((sp_c - sp_n) * rdy), b_v = psum * 0.5 * rdy;
+#pragma unroll
+      for (int k = 0; k < L; ++k)
+        fv[k * plane + cn] = g.c_sig[k] * a_v * gcm_rcp(rho_n[k] + rho[k]) + b_v * (phi[k] - phi_n[k]);
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        phi_n[k] = phi[k];
+        rho_n[k] = rho[k];
+      }
+      sp_n = sp_c;
+      jn = j;
+      j = gcm_row(j, 1, H, g.wrap_j);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // U, direct loads: one thread per column, k loop (widths that are not a multiple of 32; short rows run flat)
 // ---------------------------------------------------------------------------------------------------
@@ -637,6 +712,7 @@ int g_gcm_knob[8] = {0};
 //   4  1 = update kernel with direct global loads even when W % 32 == 0
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
+//   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
@@ -716,7 +792,27 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GCM_LAUNCH((pe25f_filter_kernel<L, 1>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf, b2, b3);
     }
     GCM_CHECK_LAUNCH();
-    {
+    if (W < 62 && g_gcm_knob[7] != 1) {  // narrow rows: whole row groups per CTA, east neighbour through shared memory
+      GcmProfScope ps(GCM_K_COLUMN_F, qb);
+      const int ngrp = (nrowsR + rg - 1) / rg;
+      int G = 128 / W < 1 ? 1 : 128 / W;
+      if (G > ngrp) G = ngrp;
+      const int th = (G * W + 31) / 32 * 32;
+      const size_t smh = (size_t)2 * (2 * L + 1) * th * sizeof(double);
+      const dim3 gridn((ngrp + G - 1) / G, nbatch);
+#ifndef GCM_EMU
+      if (smh > 48 * 1024) {
+        GCM_CUDA(cudaFuncSetAttribute(pe25f_hydro_narrow_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smh));
+        GCM_CUDA(cudaFuncSetAttribute(pe25f_hydro_narrow_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smh));
+      }
+#endif
+      if (ptop0)
+        GCM_LAUNCH((pe25f_hydro_narrow_kernel<L, true>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
+      else
+        GCM_LAUNCH((pe25f_hydro_narrow_kernel<L, false>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
+    } else {
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
       if (ptop0)
