@@ -147,6 +147,29 @@ extern "C" int gcm_halo_pack(const gcm_geom*, const gcm_state*, int, int, double
 extern "C" int gcm_halo_unpack(const gcm_geom*, const gcm_state*, int, int, const double*, void*);
 extern "C" int gcm_halo_copy_rows(const gcm_geom*, const gcm_state*, int, const gcm_state*, int, int, void*);
 
+// both halo messages of a band in ONE launch: rows [a.row0, +a.nrows) <-> a.buf and rows [b.row0, +b.nrows) <-> b.buf
+// (unpack = 0: state -> buffers, 1: buffers -> state).  Buffer layout per job: [p rows][u][v][t][q], each [layer][row][i].
+struct GcmHaloJob {
+  int row0, nrows;
+  double* buf;
+};
+__global__ void band_halo2_kernel(gcm_state s, int H, int W, int L, GcmHaloJob a, GcmHaloJob b, int unpack) {
+  double* fld[5] = {s.p, s.u, s.v, s.t, s.q};
+  const size_t na = (size_t)a.nrows * W * (1 + 4 * (size_t)L), nb = (size_t)b.nrows * W * (1 + 4 * (size_t)L);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < na + nb; e += (size_t)gridDim.x * blockDim.x) {
+    const GcmHaloJob& jb = e < na ? a : b;
+    const size_t r0 = e < na ? e : e - na;
+    const size_t per_p = (size_t)jb.nrows * W, per_3 = (size_t)L * per_p;
+    int f;
+    size_t r;
+    if (r0 < per_p) { f = 0; r = r0; } else { f = 1 + (int)((r0 - per_p) / per_3); r = (r0 - per_p) % per_3; }
+    const int i = (int)(r % W), row = (int)((r / W) % jb.nrows), k = (int)(r / per_p);
+    const size_t in_state = ((size_t)k * H + jb.row0 + row) * W + i;
+    if (unpack) fld[f][in_state] = jb.buf[r0];
+    else jb.buf[r0] = fld[f][in_state];
+  }
+}
+
 // fill the halo rows of `s` (hn north, hs south) from the ring neighbours, on stream `q`
 static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, cudaStream_t q) {
   const int lo = g->d.row_lo, hi = g->d.row_hi;
@@ -167,16 +190,20 @@ static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int
   }
   double *send_n = c->buf, *send_s = send_n + ns, *recv_s = send_s + nn, *recv_n = recv_s + ns;
   const int north = (c->rank + c->nranks - 1) % c->nranks, south = (c->rank + 1) % c->nranks;
-  if ((st = gcm_halo_pack(g, s, lo, hs, send_n, q))) return st;       // first owned rows -> north's south halo
-  if ((st = gcm_halo_pack(g, s, hi - hn, hn, send_s, q))) return st;  // last owned rows  -> south's north halo
+  const int H = g->d.H, W = g->d.W, L = g->d.L;
+  const unsigned nblk = (unsigned)((ns + nn + 255) / 256 < 148 * 4 ? (ns + nn + 255) / 256 : 148 * 4);
+  // first owned rows -> north's south halo; last owned rows -> south's north halo
+  band_halo2_kernel<<<nblk, 256, 0, q>>>(*s, H, W, L, GcmHaloJob{lo, hs, send_n}, GcmHaloJob{hi - hn, hn, send_s}, 0);
+  GCM_CHECK_LAUNCH();
   GCM_NCCL(g_nccl.GroupStart());
   GCM_NCCL(g_nccl.Send(send_n, ns, 8 /* ncclFloat64 */, north, c->comm, q));
   GCM_NCCL(g_nccl.Send(send_s, nn, 8, south, c->comm, q));
   GCM_NCCL(g_nccl.Recv(recv_s, ns, 8, south, c->comm, q));
   GCM_NCCL(g_nccl.Recv(recv_n, nn, 8, north, c->comm, q));
   GCM_NCCL(g_nccl.GroupEnd());
-  if ((st = gcm_halo_unpack(g, s, hi, hs, recv_s, q))) return st;
-  return gcm_halo_unpack(g, s, lo - hn, hn, recv_n, q);
+  band_halo2_kernel<<<nblk, 256, 0, q>>>(*s, H, W, L, GcmHaloJob{hi, hs, recv_s}, GcmHaloJob{lo - hn, hn, recv_n}, 1);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
 #endif
 }
 
