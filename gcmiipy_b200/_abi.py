@@ -13,6 +13,11 @@ class GeomDesc(C.Structure):
                 ("zero_v_row2", C.c_int)]
 
 
+class Pe25Options(C.Structure):
+    _fields_ = [("coriolis", C.c_int), ("limit_q", C.c_int), ("limit_t", C.c_int), ("nu", C.c_double),
+                ("h_cor_u", C.c_void_p), ("h_cor_v", C.c_void_p)]
+
+
 class State(C.Structure):
     _fields_ = [("p", c_dp), ("u", c_dp), ("v", c_dp), ("t", c_dp), ("q", c_dp)]
 
@@ -37,6 +42,7 @@ SIGNATURES = {
     "gcm_comm_create": (_i, [_i, _i, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gcm_comm_destroy": (_i, [C.c_void_p]),
     "gcm_band_matsuno_step": (_i, [_geom, C.c_void_p, _st, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
+    "gcm_pe25_set_options": (_i, [_geom, C.POINTER(Pe25Options)]),
     "gcm_pe25_select_path": (_i, [_i]),
     "gcm_tuning_knob": (_i, [_i, _i]),
     "gcm_pe25_calc_pu": (_i, [_geom, c_dp, c_dp, c_dp, c_stream]),

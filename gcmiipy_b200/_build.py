@@ -28,6 +28,7 @@ SOURCES = {
     "host_step.cu": [],
     "pe25.cu": ["-fmad=false"],
     "pe25_fast.cu": [],
+    "pe25_extras.cu": [],
     "sw2d.cu": ["-fmad=false"],
     "pe2d.cu": ["-fmad=false"],
     "ops.cu": ["-fmad=false"],

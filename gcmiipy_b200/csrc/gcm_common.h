@@ -170,9 +170,19 @@ struct GcmGeomDev {
   GcmFftPlan plan;
 };
 
+// opt-in terms of the 2.5-D half step (pe25_extras.cu; gcm_pe25_set_options): all off by default
+struct GcmExtras {
+  int coriolis, limit_q, limit_t;
+  double nu;
+  const double* cor_u;  // [H] 2 sin(lat) w at the u rows (dynamics.py:91)
+  const double* cor_v;  // [H] at the v rows (dynamics.py:92)
+};
+
 struct gcm_geom {
   GcmGeomDev d;
   void* d_block;  // one device allocation holding every table
+  GcmExtras x;    // opt-in terms; x.cor_u / x.cor_v point into d_cor
+  void* d_cor;
   // side stream + fork/join events: the two independent kernel chains of a half step's row phase run side by side
   // (pe25_fast.cu); created on first use, one user thread per geometry
   void* aux_stream;
@@ -216,3 +226,10 @@ __host__ __device__ __forceinline__ int gcm_ip(int i, int W) { return i + 1 == W
 __host__ __device__ __forceinline__ int gcm_im(int i, int W) { return i == 0 ? W - 1 : i - 1; }
 
 int gcm_fft_make_plan(int n, GcmFftPlan* plan);
+
+static inline bool gcm_extras_on(const gcm_geom* g) {
+  return g->x.coriolis || g->x.limit_q || g->x.limit_t || g->x.nu != 0.0;
+}
+// pe25_extras.cu: adds the opt-in terms to the freshly written `out` of a half step (whole-grid geometry)
+int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu, double dt,
+                          int nbatch, void* stream);

@@ -282,6 +282,7 @@ extern "C" int gcm_geom_destroy(gcm_geom* g) {
   if (g->ev_join) cudaEventDestroy((cudaEvent_t)g->ev_join);
 #endif
   cudaFree(g->d_block);
+  if (g->d_cor) cudaFree(g->d_cor);
   free(g);
   return GCM_OK;
 }

@@ -408,7 +408,20 @@ extern "C" int gcm_pe25_select_path(int path) {
   return GCM_OK;
 }
 
+static int pe25_half_step_core(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                               double dt, int nbatch, const Pe25Work& w, void* stream);
+
+// the reference's half step, then (opt-in) the extra terms on the state it has just written
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
+                               double dt, int nbatch, const Pe25Work& w, void* stream) {
+  if (!gcm_extras_on(g)) return pe25_half_step_core(g, base, star, out, dt, nbatch, w, stream);
+  GCM_REQUIRE(g->d.wrap_j, GCM_EUNSUP);
+  int st = pe25_half_step_core(g, base, star, out, dt, nbatch, w, stream);
+  if (st) return st;
+  return gcm_pe25_extras_apply(g, star, out, w.spu, dt, nbatch, stream);
+}
+
+static int pe25_half_step_core(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
   if (g_pe25_path == 0 && gcm_pe25_fast_supported(g))
     return gcm_pe25_fast_half_step(g, base, star, out, dt, nbatch, w.spu, w.sd, w.phi, w.pgf, w.pn, w.pit, nullptr,
@@ -496,6 +509,7 @@ extern "C" int gcm_pe25_half_step_rows(const gcm_geom* g, const gcm_state* base,
   GCM_REQUIRE(gcm_aligned16(ws), GCM_EALIGN);
   GCM_REQUIRE(ws_bytes >= gcm_pe25_workspace_bytes(g, nbatch), GCM_EWORK);
   GCM_REQUIRE(gcm_pe25_fast_supported(g) && g_pe25_path == 0, GCM_EUNSUP);
+  GCM_REQUIRE(!gcm_extras_on(g), GCM_EUNSUP);  // the opt-in terms need whole rows j - 2 ... j + 2 of the star state
   const int H = g->d.H;
   for (int s2 = 0; s2 < 2; ++s2) {
     const int* sg = s2 ? seg_u : seg_r;

@@ -15,7 +15,8 @@ enum GcmProfKind {
   GCM_K_FILTER_B = 8,     // pe25f_filter_kernel<0>
   GCM_K_AFLUX_F = 9,      // pe25f_aflux_kernel
   GCM_K_UPDATE_TILED = 10,  // pe25f_update_tiled_kernel
-  GCM_K_COUNT = 11
+  GCM_K_EXTRAS = 11,        // pe25x_extras_kernel (pe25_extras.cu, opt-in terms)
+  GCM_K_COUNT = 12
 };
 
 #ifdef GCM_EMU

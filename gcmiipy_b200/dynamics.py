@@ -12,12 +12,41 @@ import ctypes
 import torch
 
 from . import _abi, _host, _lib
-from .geometry import device_geom
+from .geometry import _push_options, device_geom
 
 __all__ = ["calc_pu", "calc_pv", "un_pu", "un_pv", "aflux", "advec_sig", "advec_m_pu", "compute_geopotential",
-           "pgf", "advec_t", "half_timestep", "matsuno_timestep", "Stepper"]
+           "pgf", "advec_t", "half_timestep", "matsuno_timestep", "Stepper", "StepOptions", "configure"]
 
 _UNITS = ("pascal", "meter / second", "meter / second", "kelvin", "dimensionless")
+
+
+class StepOptions:
+    """Opt-in terms of the 2.5-D half step (include/gcm_b200.h gcm_pe25_options).
+    All off = the reference's step.  coriolis: dynamics.py:82-95 switched on; viscosity: kinematic horizontal
+    viscosity in m2/s (viscosity.py:12-25 on the lat-lon metric); limit_q / limit_t: van Leer flux-limited horizontal
+    advection of q / theta (flux_limiter.py:10-32 composed into advec_t, the TODO at dynamics.py:217-218)."""
+
+    def __init__(self, coriolis=False, viscosity=0.0, limit_q=False, limit_t=False):
+        self.coriolis, self.limit_q, self.limit_t = bool(coriolis), bool(limit_q), bool(limit_t)
+        self.viscosity = _host.scalar(viscosity)
+        if not self.viscosity >= 0.0:
+            raise ValueError("viscosity must be >= 0 (m2/s)")
+
+    def any(self):
+        return self.coriolis or self.limit_q or self.limit_t or self.viscosity != 0.0
+
+
+def configure(geom, coriolis=False, viscosity=0.0, limit_q=False, limit_t=False):
+    """Switch the opt-in terms of `half_timestep` / `matsuno_timestep` / `Stepper.step` on or off for `geom`
+    (whole-grid stepping only).  `configure(geom)` restores the reference's step.  Returns the StepOptions."""
+    opt = StepOptions(coriolis, viscosity, limit_q, limit_t)
+    geom.step_options = opt
+    for dg in list(geom._dev.values()):
+        if dg.wrap_j:
+            _push_options(geom, dg)
+        elif opt.any():
+            raise ValueError("the opt-in terms are not available on latitude bands")
+    return opt
 
 
 def _struct(ts):
@@ -81,7 +110,7 @@ class Stepper:
         new state into the five (pinned) host tensors `host_out`.  All asynchronous on the current stream.
         One step of one member goes through `gcm_pe25_matsuno_step_host`: latitude blocks copied in, stepped and
         copied out on three streams, so the PCIe link runs in both directions at once."""
-        if int(nsteps) == 1 and self.nbatch == 1 and self.cur[0].dim() == 2 and all(
+        if int(nsteps) == 1 and self.nbatch == 1 and self.cur[0].dim() == 2 and not self.dg.options_on and all(
                 not x.is_cuda and x.is_contiguous() and x.dtype == torch.float64 for x in list(host_in) + list(host_out)):
             if getattr(self, "_star", None) is None:
                 self._star = [torch.empty_like(x) for x in self.cur]

@@ -17,7 +17,8 @@ import numpy as np
 from . import _abi, _host, _lib
 from .constants import radius
 
-__all__ = ["Geom", "manabe_sig", "equal_sig", "gen_geometry", "gen_square_geometry", "device_geom", "polar_filter_table"]
+__all__ = ["Geom", "manabe_sig", "equal_sig", "gen_geometry", "gen_square_geometry", "device_geom", "polar_filter_table",
+           "coriolis_parameters"]
 
 
 class Geom:
@@ -35,6 +36,7 @@ class Geom:
         self.area = None
         self.ptop = 0.0
         self.heightmap = None
+        self.step_options = None      # opt-in terms of the 2.5-D step (dynamics.configure); None = the reference's step
         self._dev = {}
 
     def __getstate__(self):
@@ -111,12 +113,42 @@ def polar_filter_table(geom, im=None):
     return np.ascontiguousarray(np.insert(smmz, 0, 1, -1))
 
 
+def coriolis_parameters(geom):
+    """(cp_at_u, cp_at_v) of dynamics.py:89-92 as (H,) arrays: 2 sin(lat) w at the u rows and 2 sin(jph(lat)) w at the
+    v rows, w = 2 pi / day; zeros for a geometry without latitudes (gen_square_geometry, geometry.py:174)."""
+    w = 2 * math.pi / 86400.0
+    lat = np.asarray(_host.magnitude(geom.lat), dtype=np.float64)
+    if lat.ndim == 0:
+        z = np.zeros(geom.height)
+        return z, z.copy()
+    lat = lat.reshape(geom.height, -1)
+    cp_u = 2 * np.sin(lat) * w
+    cp_v = 2 * np.sin((lat + np.roll(lat, -1, -2)) / 2) * w
+    return np.ascontiguousarray(cp_u[:, 0]), np.ascontiguousarray(cp_v[:, 0])
+
+
+def _push_options(geom, dg):
+    """Hand geom.step_options to the device geometry (gcm_pe25_set_options)."""
+    opt = getattr(geom, "step_options", None)
+    if opt is None or not opt.any():
+        if dg.options_on:
+            _lib.check(_lib.lib().gcm_pe25_set_options(dg.handle, None), "gcm_pe25_set_options")
+            dg.options_on = False
+        return
+    cu, cv = coriolis_parameters(geom) if opt.coriolis else (None, None)
+    o = _abi.Pe25Options(int(opt.coriolis), int(opt.limit_q), int(opt.limit_t), float(opt.viscosity),
+                         _host.hptr(cu), _host.hptr(cv))
+    _lib.check(_lib.lib().gcm_pe25_set_options(dg.handle, ctypes.byref(o)), "gcm_pe25_set_options")
+    dg.options_on = True
+
+
 class DeviceGeom:
     """Owner of one `gcm_geom*` (include/gcm_b200.h)."""
 
     def __init__(self, handle, H, W, L, row_lo, row_hi, wrap_j):
         self.handle, self.H, self.W, self.L = handle, H, W, L
         self.row_lo, self.row_hi, self.wrap_j = row_lo, row_hi, wrap_j
+        self.options_on = False
 
     def __del__(self):
         try:
@@ -147,6 +179,8 @@ def device_geom(geom, band=None):
     key = _fingerprint(geom, band)
     if key in geom._dev:
         return geom._dev[key]
+    if band is not None and getattr(geom, "step_options", None) is not None and geom.step_options.any():
+        raise ValueError("the opt-in terms (dynamics.configure) are not available on latitude bands")
     H, W, L = geom.height, geom.width, geom.layers
     sig, dsig = _vec(geom.sig, L), _vec(geom.dsig, L)
     sigb, sigt = _vec(geom.sigb, L), _vec(geom.sigt, L)
@@ -177,4 +211,6 @@ def device_geom(geom, band=None):
     if len(geom._dev) >= 8:       # a caller that keeps editing the heightmap: drop the stale tables
         geom._dev.clear()
     geom._dev[key] = obj
+    if band is None:
+        _push_options(geom, obj)
     return obj

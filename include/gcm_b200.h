@@ -124,6 +124,30 @@ int gcm_pe25_select_path(int path);
 /* launch-shape tuning knobs of the fused kernels (idx 0..7, see pe25_fast.cu); 0 = automatic */
 int gcm_tuning_knob(int idx, int value);
 
+/* Opt-in terms of the 2.5-D half step.  All OFF by default: the step is then the
+ * reference's dynamics.half_timestep and nothing else.  The reference only sketches these terms -- the Coriolis
+ * block dynamics.py:82-95 is complete but sits behind `if False:`, tracer flux limiting is a TODO (dynamics.py:217-218)
+ * and viscosity.py is wired into the 2-D matsumo_temp.py only -- so they are composed from the reference's own
+ * building blocks:
+ *   coriolis  dynamics.py:86-95 as written (h_cor_u/h_cor_v = 2 sin(lat) w at the u / v rows, :91-92, [H] each);
+ *   nu        kinematic horizontal viscosity (m2/s): pi * nu * lap(u), lap = viscosity.py:12-19 with dx_j (dx_h for v) in i
+ *             and dy in j;
+ *   limit_q / limit_t  horizontal advection of q / theta (dynamics.py:174-181) with the edge value
+ *             upwind + 1/2 van_leer(r) * (downwind - upwind), r = flux_limiter.calc_r seen from the upwind cell
+ *             (flux_limiter.py:10-27); phi = 1 is the reference's centred flux, phi = 0 its donor cell.
+ * Applied by one extra launch per half step (csrc/pe25_extras.cu) inside gcm_pe25_half_step / gcm_pe25_matsuno_step.
+ * Whole-grid geometries only: with any option on, band geometries (wrap_j = 0), gcm_pe25_half_step_rows,
+ * gcm_pe25_matsuno_step_host and gcm_band_matsuno_step return GCM_EUNSUP.  opt = NULL switches everything off. */
+typedef struct {
+  int coriolis;
+  int limit_q;
+  int limit_t;
+  double nu;
+  const double* h_cor_u;   /* [H], required when coriolis != 0 */
+  const double* h_cor_v;   /* [H] */
+} gcm_pe25_options;
+int gcm_pe25_set_options(gcm_geom* g, const gcm_pe25_options* opt);
+
 /* the operators half_timestep is built from, each on the owned rows of one member */
 int gcm_pe25_calc_pu(const gcm_geom* g, const double* d_p, const double* d_u, double* d_pu, void* stream);   /* dynamics.py:15 */
 int gcm_pe25_calc_pv(const gcm_geom* g, const double* d_p, const double* d_v, double* d_pv, void* stream);   /* dynamics.py:20 */

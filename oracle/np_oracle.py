@@ -563,6 +563,111 @@ def mt_matsumo_scheme(u, v, p, t, dx, dt):
     return u_n, v_n, p_n, t_n
 
 
+# ---- opt-in terms of the 2.5-D half step ----------------------------------------
+# The reference only sketches these (dead Coriolis branch dynamics.py:82-95; "TODO might need to flux limit
+# this" dynamics.py:217-218; viscosity.py is wired into matsumo_temp.py only).  They are composed here from the
+# reference's own building blocks.  PINNING: the Coriolis term is pinned against the reference executed with its
+# `if False:` (dynamics.py:82) switched to `if True:` in memory (oracle/make_golden_ext.py ->
+# tests/golden/run25_24x36x9_coriolis.npz).  The limiter and viscosity compositions have no reference
+# counterpart: PARITY UNPINNED for those two; tests check them through their properties (conservation,
+# monotonicity, reduction to the reference's operators).
+class StepOptions:
+    """coriolis: add dynamics.py:86-95; nu: kinematic horizontal viscosity (m2/s) on u and v; limit_q / limit_t:
+    van Leer flux-limited horizontal advection of q / theta instead of the centred flux of advec_t."""
+
+    def __init__(self, coriolis=False, nu=0.0, limit_q=False, limit_t=False):
+        self.coriolis, self.nu, self.limit_q, self.limit_t = bool(coriolis), float(nu), bool(limit_q), bool(limit_t)
+
+    def any(self):
+        return self.coriolis or self.nu != 0.0 or self.limit_q or self.limit_t
+
+
+def coriolis_parameters(geom):
+    """(cp_at_u, cp_at_v) of dynamics.py:89-92, shapes (H, 1): 2 sin(lat) w at the u rows and at the v rows."""
+    w = 2 * math.pi / 86400.0                                   # dynamics.py:89 (units.day)
+    if np.ndim(geom.lat) == 0:                                  # gen_square_geometry: lat = 0 (geometry.py:174)
+        z = np.zeros((geom.height, 1))
+        return z, z
+    cp_at_u = 2 * np.sin(geom.lat) * w                          # :91
+    cp_at_v = 2 * np.sin(jph(geom.lat)) * w                     # :92
+    return cp_at_u, cp_at_v
+
+
+def coriolis_terms(pu, pv, geom):
+    """dynamics.py:86-95 with the branch enabled -> (coriolis_u, coriolis_v)."""
+    pu_at_pv = imh(jph(pu))                                     # :86
+    pv_at_pu = iph(jmh(pv))                                     # :87
+    cp_at_u, cp_at_v = coriolis_parameters(geom)
+    return cp_at_u * -pv_at_pu, cp_at_v * pu_at_pv              # :94-95
+
+
+def laplacian_h(q, dx, dy):
+    """viscosity.py:12-19 on the lat-lon metric: second differences in i over dx^2 and in j over dy^2
+    (identical to finite_laplacian_2d up to round-off when dx == dy)."""
+    return (ipj(q) + imj(q) - 2 * q) / (dx * dx) + (ijp(q) + ijm(q) - 2 * q) / (dy * dy)
+
+
+def limited_edge_value(q, flux, axis):
+    """Edge value of q at i+1/2 (along `axis`) for a flux-limited scheme built from flux_limiter.py: the donor
+    cell (:23-27, upwind by the sign of the flux) plus half the van Leer-limited (:10) downwind difference, the
+    slope ratio being calc_r's (:14-20, 0 where the denominator is 0) seen from the upwind cell.
+    phi = 1 gives the centred value iph(q) of advec_t, phi = 0 the donor cell."""
+    sh = lambda a, n: np.roll(a, n, axis)
+    b = sh(q, -1) - q                                                        # calc_r's b: q[i+1] - q[i]
+    a = q - sh(q, 1)                                                         # calc_r's a: q[i] - q[i-1]
+    r_up = np.divide(a, b, out=np.zeros_like(b), where=(b != 0))             # upwind cell i    (flux > 0)
+    r_dn = np.divide(sh(b, -1), b, out=np.zeros_like(b), where=(b != 0))     # upwind cell i+1  (flux <= 0)
+    return np.where(flux > 0, q + 0.5 * van_leer(r_up) * b, sh(q, -1) - 0.5 * van_leer(r_dn) * b)
+
+
+def advec_t_limited(pu, pv, t, geom):
+    """advec_t (dynamics.py:174-181) with iph(t), jph(t) replaced by the limited edge values."""
+    tpu = pu * limited_edge_value(t, pu, -1)
+    tpv = pv * limited_edge_value(t, pv, -2)
+    return (tpu - imj(tpu)) / geom.dx_j + (tpv - ijm(tpv)) / geom.dy
+
+
+def half_timestep_ext(p, u, v, t, q, sp, su, sv, st, sq, dt, geom, opt):
+    """half_timestep (dynamics.py:183-227) with the opt-in terms; opt all off == half_timestep bit for bit."""
+    pu = calc_pu(p, u)
+    spu_orig = calc_pu(sp, su)
+    spu = arakawa_1977(spu_orig, geom)
+    pv = calc_pv(p, v)
+    spv = calc_pv(sp, sv)
+    pit, sd = aflux(spu, spv, geom)
+    p_n = p - pit * dt
+    dut, dvt = advec_m_pu(sp, su, sv, spu, spv, geom)
+    if opt.coriolis:
+        cu, cv = coriolis_terms(spu, spv, geom)
+        dut = dut + cu                                                       # dynamics.py:100-101
+        dvt = dvt + cv
+    pgu, pgv, phiu, phiv = pgf(sp, st, geom)
+    dus = advec_sig(iph(sd), su, geom)
+    dvs = advec_sig(jph(sd), sv, geom)
+    pgfu = arakawa_1977(pgu + phiu, geom)
+    fu = dut + dus + pgfu
+    fv = dvt + dvs + phiv + pgv
+    if opt.nu != 0.0:     # pi * nu * lap(u): the mass-weighted form of matsumo_temp.py:55-59's mu * lap(u) / rho
+        fu = fu - iph(sp) * (opt.nu * laplacian_h(su, geom.dx_j, geom.dy))
+        fv = fv - jph(sp) * (opt.nu * laplacian_h(sv, geom.dx_h, geom.dy))
+    pu_n = pu - fu * dt
+    pv_n = pv - fv * dt
+    u_n = un_pu(pu_n, p_n)
+    v_n = un_pv(pv_n, p_n)
+    adv_t = advec_t_limited if opt.limit_t else advec_t
+    adv_q = advec_t_limited if opt.limit_q else advec_t
+    t_n = (t * p - (adv_t(spu, spv, st, geom) + advec_sig(sd, st, geom)) * dt) / p_n
+    q_n = (q * p - (adv_q(spu, spv, sq, geom) + advec_sig(sd, sq, geom)) * dt) / p_n
+    v_n[:, -1, :] *= 0
+    return p_n, u_n, v_n, t_n, q_n
+
+
+def matsuno_timestep_ext(p, u, v, t, q, dt, geom, opt):
+    """matsuno_timestep (dynamics.py:230-237) over half_timestep_ext."""
+    s = half_timestep_ext(p, u, v, t, q, p, u, v, t, q, dt, geom, opt)
+    return half_timestep_ext(p, u, v, t, q, *s, dt, geom, opt)
+
+
 # ---- synthetic initial states shared by tests and bench (SURVEY.md section 8d) ---------------
 def synthetic_state(geom, seed=1234, amp_u=1.0, amp_p=50.0, amp_t=0.5):
     """Reference ICs (run_model_ic) plus a smooth seeded band-limited perturbation so that no
