@@ -2,6 +2,7 @@
 """Benchmark of the Matsuno C-grid hot path (BASELINE.json: cell-updates/s, fraction of the HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c3|c2|c4] [--impl native|reference]
+                    [--options coriolis,limit_q,limit_t,viscosity=NU]
 
 One "step" = one full Matsuno step (predictor + corrector, dynamics.py:230-237) of the 2.5-D model over the
 whole grid.  Default workload: the 0.25 deg grid 1440 x 720 x 9 (BASELINE.json configs[4], the grid the metric
@@ -113,24 +114,39 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_step_rate(H, W, L, dt, nsteps, seed=1234):
+def parse_options(text):
+    """--options coriolis,limit_q,limit_t,viscosity=1e5 -> kwargs of dynamics.configure (opt-in terms)."""
+    kw = {}
+    for item in filter(None, (text or "").split(",")):
+        k, _, v = item.partition("=")
+        if k not in ("coriolis", "limit_q", "limit_t", "viscosity"):
+            raise SystemExit("unknown option %r" % k)
+        kw[k] = float(v) if k == "viscosity" else True
+    return kw
+
+
+def cpu_oracle_step_rate(H, W, L, dt, nsteps, seed=1234, options=None):
     """Time the CPU restatement of the reference (oracle/np_oracle.py) on an H x W x L grid; returns seconds."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import np_oracle as O
     geom = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
     s = O.synthetic_state(geom, seed=seed)
+    opt = None
+    if options:
+        opt = O.StepOptions(options.get("coriolis", False), options.get("viscosity", 0.0), options.get("limit_q", False),
+                            options.get("limit_t", False))
     t0 = time.perf_counter()
     for _ in range(nsteps):
-        s = O.matsuno_timestep(*s, dt, geom)
+        s = O.matsuno_timestep_ext(*s, dt, geom, opt) if opt else O.matsuno_timestep(*s, dt, geom)
     return time.perf_counter() - t0
 
 
 def _ref_worker(args):
-    H, W, L, dt, warmup, steps = args
+    H, W, L, dt, warmup, steps, options = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     if warmup:
-        cpu_oracle_step_rate(H, W, L, dt, warmup)
-    return cpu_oracle_step_rate(H, W, L, dt, steps)
+        cpu_oracle_step_rate(H, W, L, dt, warmup, options=options)
+    return cpu_oracle_step_rate(H, W, L, dt, steps, options=options)
 
 
 def run_reference(args):
@@ -142,6 +158,9 @@ def run_reference(args):
         return
     import multiprocessing as mp
     H, W, L, dt, members, desc = WORKLOADS[args.workload]
+    options = parse_options(args.options)
+    if options:
+        desc += " + opt-in terms"
     cores = os.cpu_count() or 1
     full_step_s = 1.7e-6 * H * W * L * (members if members > 1 else 1)       # ~0.6 M cell-updates/s/core
     budget = 120.0
@@ -150,12 +169,12 @@ def run_reference(args):
         rows, nmem = H, max(1, int(members * frac))
         sample = "%d of %d members per process" % (nmem, members)
         cells = H * W * L * nmem
-        work = (H, W, L, dt, args.warmup * nmem, args.steps * nmem)
+        work = (H, W, L, dt, args.warmup * nmem, args.steps * nmem, options)
     else:
         rows = max(8, int(H * frac) // 2 * 2)
         sample = "%d x %d x %d rows-subset grid per process (of %d rows)" % (W, rows, L, H)
         cells = rows * W * L
-        work = (rows, W, L, dt, args.warmup, args.steps)
+        work = (rows, W, L, dt, args.warmup, args.steps, options)
     with mp.get_context("fork").Pool(cores) as pool:
         times = pool.map(_ref_worker, [work] * cores)
     tmax = max(times)
@@ -164,7 +183,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "grid": [H, W, L], "dt_s": dt, "members": members},
+        "config": {"workload": desc, "grid": [H, W, L], "dt_s": dt, "members": members, "options": options or None},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; numpy oracle pinned bit-exactly to the reference's outputs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,6 +209,11 @@ def run_native(args):
 
     H, W, L, dt, members, desc = WORKLOADS[args.workload]
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    options = parse_options(args.options)
+    if options:
+        assert world == 1, "the opt-in terms run on whole-grid geometries (one GPU)"
+        dynamics.configure(geom, **options)
+        desc += " + opt-in terms"
     _lib.lib().gcm_pe25_select_path(args.path)
     for kv in args.knob:
         i, v = kv.split("=")
@@ -312,13 +336,13 @@ def run_native(args):
     if world == 1 and not args.no_cpu_baseline:
         if members > 1:
             nmem = 64
-            t = cpu_oracle_step_rate(H, W, L, dt, nmem)
+            t = cpu_oracle_step_rate(H, W, L, dt, nmem, options=options)
             cpu = {"value": H * W * L * nmem / t, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "%d member-steps of the %dx%dx%d grid, numpy oracle, 1 thread" % (nmem, W, H, L)}
         else:
             rows = H if H * W * L <= 2_000_000 else 180
             nst = max(1, int(2_000_000 // (rows * W * L)))
-            t = cpu_oracle_step_rate(rows, W, L, dt, nst)
+            t = cpu_oracle_step_rate(rows, W, L, dt, nst, options=options)
             cpu = {"value": rows * W * L * nst / t, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "%d Matsuno step(s) of a %dx%dx%d grid, numpy oracle, 1 thread" % (nst, W, rows, L)}
 
@@ -326,7 +350,7 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "grid": [H, W, L], "dt_s": dt, "members": members,
+        "config": {"workload": desc, "grid": [H, W, L], "dt_s": dt, "members": members, "options": options or None,
                    "parallelism": "lat-bands x%d" % world if members == 1 else "members split x%d" % world,
                    "l2_policy": "state %.0f MB > 126 MB L2: inputs larger than L2, no flush" % (total_cells * b_alg(L) / 2e6 / world)
                    if total_cells * b_alg(L) / 2 / world > 126e6 else "state fits L2 (latency/ALU-bound config); no flush"},
@@ -350,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 = fused kernels (default), 1 = general 4-kernel path")
+    ap.add_argument("--options", default="", help="opt-in terms of the step: coriolis,limit_q,limit_t,viscosity=NU "
+                    "(BASELINE configs[1] names flux limiter + viscosity: --workload c2 --options limit_q,limit_t,viscosity=1e5)")
     ap.add_argument("--knob", action="append", default=[], help="tuning knob i=v (gcm_tuning_knob)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

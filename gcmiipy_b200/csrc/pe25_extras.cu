@@ -11,6 +11,9 @@
 // workspace:
 //   u_n += -dt (cor_u - visc_u) / iph(p_n)        v_n += -dt (cor_v - visc_v) / jph(p_n)
 //   q_n += -dt div(G) / p_n,   G = mass flux * (limited edge value - centred edge value)
+// One thread per column (i, k) marches PX_RJ rows south: the tracer column j-2 ... j+2 and the flux through the north
+// edge ride in registers, so a row costs one new load per tracer in j and three limiter evaluations instead of four.
+// Divides are reciprocals (metric tables, gcm_rcp): fp64 division is a ~30-instruction software sequence.
 // The default path (no option set) launches nothing from this file and stays bit-identical to the reference step.
 // Whole-grid geometries only (rows periodic in j): the limiter reads j - 2 ... j + 2.
 #include <math.h>
@@ -21,43 +24,25 @@
 #define IDX3(k, j, i) (((size_t)(k) * H + (size_t)(j)) * W + (size_t)(i))
 #define IDX2(j, i) ((size_t)(j) * W + (size_t)(i))
 
-// flux_limiter.py:10
-__device__ __forceinline__ double px_van_leer(double r) { return (r + fabs(r)) / (1 + fabs(r)); }
-
-// limited edge value minus the centred one at the edge between q0 and q1 (qm, q0 | q1, q2), upwind by the sign
-// of the mass flux (flux_limiter.py:23-27); slope ratio as calc_r (:14-20): 0 where the denominator is 0
+// Limited edge value minus the centred one at the edge between q0 and q1 (qm, q0 | q1, q2), upwind by the sign of the
+// mass flux (flux_limiter.py:23-27).  With r = a / b the slope ratio of calc_r (:14-20; 0 where b == 0) seen from the
+// upwind cell, van_leer(r) * b (:10) = 2 a b / (a + b) where a and b have the same sign and 0 elsewhere -- the
+// harmonic-mean form of the same limiter: one reciprocal instead of two divides, and no r to overflow.
 __device__ __forceinline__ double px_edge_excess(double qm, double q0, double q1, double q2, double flux) {
   const double b = q1 - q0;
-  double e;
-  if (flux > 0) {
-    const double a = q0 - qm;
-    const double r = b != 0 ? a / b : 0.0;
-    e = q0 + 0.5 * px_van_leer(r) * b;
-  } else {
-    const double c = q2 - q1;
-    const double r = b != 0 ? c / b : 0.0;
-    e = q1 - 0.5 * px_van_leer(r) * b;
-  }
-  return e - (q0 + q1) / 2;
+  const double a = flux > 0 ? q0 - qm : q2 - q1;
+  const double ab = a * b;
+  const double lim = ab > 0 ? 2 * ab * gcm_rcp(a + b) : 0.0;
+  return flux > 0 ? 0.5 * (lim - b) : 0.5 * (b - lim);   // (q0 + lim/2) - (q0+q1)/2   |   (q1 - lim/2) - (q0+q1)/2
 }
 
-// divergence of the correction flux G of one tracer at (k, j, i)
-__device__ __forceinline__ double px_limiter_div(const double* __restrict__ f, const double* __restrict__ spu,
-                                                 double spv_c, double spv_n, int k, int j, int jm1, int jm2, int jp1,
-                                                 int jp2, int i, int im1, int im2, int ip1, int ip2, int H, int W,
-                                                 double dx, double dy) {
-  const double f0 = f[IDX3(k, j, i)];
-  const double fw1 = f[IDX3(k, j, im1)], fw2 = f[IDX3(k, j, im2)];
-  const double fe1 = f[IDX3(k, j, ip1)], fe2 = f[IDX3(k, j, ip2)];
-  const double fn1 = f[IDX3(k, jm1, i)], fn2 = f[IDX3(k, jm2, i)];
-  const double fs1 = f[IDX3(k, jp1, i)], fs2 = f[IDX3(k, jp2, i)];
-  const double pu_c = spu[IDX3(k, j, i)], pu_w = spu[IDX3(k, j, im1)];
-  const double gi_c = pu_c * px_edge_excess(fw1, f0, fe1, fe2, pu_c);    // edge i + 1/2
-  const double gi_w = pu_w * px_edge_excess(fw2, fw1, f0, fe1, pu_w);    // edge i - 1/2
-  const double gj_c = spv_c * px_edge_excess(fn1, f0, fs1, fs2, spv_c);  // edge j + 1/2
-  const double gj_n = spv_n * px_edge_excess(fn2, fn1, f0, fs1, spv_n);  // edge j - 1/2
-  return (gi_c - gi_w) / dx + (gj_c - gj_n) / dy;
-}
+// column i of one tracer while the thread marches south: the five rows j-2 ... j+2 and the correction flux through
+// the north edge of row j (the south edge of the row before)
+struct PxColumn {
+  double m2, m1, c, p1, p2, gj_n;
+};
+
+#define PX_RJ 8  // rows a thread marches over
 
 __global__ void __launch_bounds__(128)
 pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, const double* __restrict__ su,
@@ -68,58 +53,99 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
   const int H = g.H, W = g.W, L = g.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W) return;
-  const int j = g.row_lo + blockIdx.y;
+  const int j0 = g.row_lo + blockIdx.y * PX_RJ;
+  const int j1 = j0 + PX_RJ < g.row_hi ? j0 + PX_RJ : g.row_hi;
   const int k = blockIdx.z % L, b = blockIdx.z / L;
   sp += b * b2; pn += b * b2;
   su += b * b3; sv += b * b3; st += b * b3; sq += b * b3; spu += b * b3;
   u += b * b3; v += b * b3; t += b * b3; q += b * b3;
 
   const int ip1 = gcm_ip(i, W), im1 = gcm_im(i, W), ip2 = gcm_ip(ip1, W), im2 = gcm_im(im1, W);
-  const int jp1 = gcm_row(j, 1, H, 1), jm1 = gcm_row(j, -1, H, 1);
-  const int jp2 = gcm_row(jp1, 1, H, 1), jm2 = gcm_row(jm1, -1, H, 1);
-  const size_t c = IDX3(k, j, i);
-  const double dy = g.dy, dxj = g.dx_j[j], dxh = g.dx_h[j];
+  const double rdy = g.rdy;
+  const bool momentum = x.coriolis || x.nu != 0.0;
+  const double* const trc_in[2] = {sq, st};
+  double* const trc_out[2] = {q, t};
+  const bool trc_on[2] = {x.limit_q != 0, x.limit_t != 0};
 
-  const double sp_c = sp[IDX2(j, i)], sp_e = sp[IDX2(j, ip1)], sp_s = sp[IDX2(jp1, i)], sp_n = sp[IDX2(jm1, i)];
-  const double pn_c = pn[IDX2(j, i)];
-  // star mass flux in j (dynamics.py:191): spv = sv * jph(sp)
-  const double spv_c = sv[c] * ((sp_c + sp_s) / 2);
-  const double spv_n = sv[IDX3(k, jm1, i)] * ((sp_n + sp_c) / 2);
-
-  if (x.coriolis || x.nu != 0.0) {
-    double fu = 0.0, fv = 0.0;  // what is added to dut + dus + pgfu and to dvt + dvs + phiv + pgv
-    if (x.coriolis) {
-      const double sp_se = sp[IDX2(jp1, ip1)], sp_ne = sp[IDX2(jm1, ip1)];
-      const double spv_e = sv[IDX3(k, j, ip1)] * ((sp_e + sp_se) / 2);
-      const double spv_ne = sv[IDX3(k, jm1, ip1)] * ((sp_ne + sp_e) / 2);
-      const double pv_at_pu = ((spv_c + spv_n) / 2 + (spv_e + spv_ne) / 2) / 2;  // iph(jmh(pv)), dynamics.py:87
-      const double pu_at_pv = ((spu[c] + spu[IDX3(k, jp1, i)]) / 2 +
-                               (spu[IDX3(k, j, im1)] + spu[IDX3(k, jp1, im1)]) / 2) / 2;  // imh(jph(pu)), :86
-      fu += x.cor_u[j] * -pv_at_pu;  // :94
-      fv += x.cor_v[j] * pu_at_pv;   // :95
+  // state carried from row to row
+  int jm1 = gcm_row(j0, -1, H, 1), jm2 = gcm_row(jm1, -1, H, 1), jp1 = gcm_row(j0, 1, H, 1);
+  double sp_n = sp[IDX2(jm1, i)], sp_c = sp[IDX2(j0, i)], sp_s = sp[IDX2(jp1, i)];
+  double spv_n = sv[IDX3(k, jm1, i)] * ((sp_n + sp_c) / 2);  // star mass flux in j (dynamics.py:191) through the north edge
+  PxColumn col[2];
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+    if (trc_on[f]) {
+      const double* __restrict__ a = trc_in[f];
+      const int jp2 = gcm_row(jp1, 1, H, 1);
+      col[f].m2 = a[IDX3(k, jm2, i)]; col[f].m1 = a[IDX3(k, jm1, i)]; col[f].c = a[IDX3(k, j0, i)];
+      col[f].p1 = a[IDX3(k, jp1, i)]; col[f].p2 = a[IDX3(k, jp2, i)];
+      col[f].gj_n = spv_n * px_edge_excess(col[f].m2, col[f].m1, col[f].c, col[f].p1, spv_n);
     }
-    const bool wall = (j == g.zero_v_row || j == g.zero_v_row2);  // v_n[:, -1, :] stays 0 (dynamics.py:222)
-    if (x.nu != 0.0) {
-      const double u0 = su[c];
-      const double lap_u = (su[IDX3(k, j, ip1)] + su[IDX3(k, j, im1)] - 2 * u0) / (dxj * dxj) +
-                           (su[IDX3(k, jp1, i)] + su[IDX3(k, jm1, i)] - 2 * u0) / (dy * dy);
-      fu -= (sp_c + sp_e) / 2 * (x.nu * lap_u);
-      if (!wall) {
-        const double v0 = sv[c];
-        const double lap_v = (sv[IDX3(k, j, ip1)] + sv[IDX3(k, j, im1)] - 2 * v0) / (dxh * dxh) +
-                             (sv[IDX3(k, jp1, i)] + sv[IDX3(k, jm1, i)] - 2 * v0) / (dy * dy);
-        fv -= (sp_c + sp_s) / 2 * (x.nu * lap_v);
+
+  for (int j = j0; j < j1; ++j) {
+    jm1 = gcm_row(j, -1, H, 1);
+    jp1 = gcm_row(j, 1, H, 1);
+    const size_t c = IDX3(k, j, i);
+    const double rdxj = g.rdx_j[j];
+    const double pn_c = pn[IDX2(j, i)];
+    const double sv_c = sv[c];
+    const double spv_c = sv_c * ((sp_c + sp_s) / 2);
+
+    if (momentum) {
+      double fu = 0.0, fv = 0.0;  // what is added to dut + dus + pgfu and to dvt + dvs + phiv + pgv
+      const double sp_e = sp[IDX2(j, ip1)];
+      if (x.coriolis) {
+        const double sp_se = sp[IDX2(jp1, ip1)], sp_ne = sp[IDX2(jm1, ip1)];
+        const double spv_e = sv[IDX3(k, j, ip1)] * ((sp_e + sp_se) / 2);
+        const double spv_ne = sv[IDX3(k, jm1, ip1)] * ((sp_ne + sp_e) / 2);
+        const double pv_at_pu = ((spv_c + spv_n) / 2 + (spv_e + spv_ne) / 2) / 2;  // iph(jmh(pv)), dynamics.py:87
+        const double pu_at_pv = ((spu[c] + spu[IDX3(k, jp1, i)]) / 2 +
+                                 (spu[IDX3(k, j, im1)] + spu[IDX3(k, jp1, im1)]) / 2) / 2;  // imh(jph(pu)), :86
+        fu += x.cor_u[j] * -pv_at_pu;  // :94
+        fv += x.cor_v[j] * pu_at_pv;   // :95
       }
+      const bool wall = (j == g.zero_v_row || j == g.zero_v_row2);  // v_n[:, -1, :] stays 0 (dynamics.py:222)
+      if (x.nu != 0.0) {
+        const double u0 = su[c];
+        const double lap_u = (su[IDX3(k, j, ip1)] + su[IDX3(k, j, im1)] - 2 * u0) * (rdxj * rdxj) +
+                             (su[IDX3(k, jp1, i)] + su[IDX3(k, jm1, i)] - 2 * u0) * (rdy * rdy);
+        fu -= (sp_c + sp_e) / 2 * (x.nu * lap_u);
+        if (!wall) {
+          const double rdxh = g.rdx_h[j];
+          const double lap_v = (sv[IDX3(k, j, ip1)] + sv[IDX3(k, j, im1)] - 2 * sv_c) * (rdxh * rdxh) +
+                               (sv[IDX3(k, jp1, i)] + sv[IDX3(k, jm1, i)] - 2 * sv_c) * (rdy * rdy);
+          fv -= (sp_c + sp_s) / 2 * (x.nu * lap_v);
+        }
+      }
+      u[c] -= (fu * dt) * gcm_rcp((pn_c + pn[IDX2(j, ip1)]) / 2);
+      if (!wall) v[c] -= (fv * dt) * gcm_rcp((pn_c + pn[IDX2(jp1, i)]) / 2);
     }
-    u[c] += -(fu * dt) / ((pn_c + pn[IDX2(j, ip1)]) / 2);
-    if (!wall) v[c] += -(fv * dt) / ((pn_c + pn[IDX2(jp1, i)]) / 2);
+
+    if (trc_on[0] || trc_on[1]) {
+      const double pu_c = spu[c], pu_w = spu[IDX3(k, j, im1)];
+      const double rpn = gcm_rcp(pn_c);
+      const int jp3 = gcm_row(gcm_row(jp1, 1, H, 1), 1, H, 1);
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+        if (trc_on[f]) {
+          const double* __restrict__ a = trc_in[f];
+          PxColumn& cl = col[f];
+          const double fw1 = a[IDX3(k, j, im1)], fw2 = a[IDX3(k, j, im2)];
+          const double fe1 = a[IDX3(k, j, ip1)], fe2 = a[IDX3(k, j, ip2)];
+          const double gi_c = pu_c * px_edge_excess(fw1, cl.c, fe1, fe2, pu_c);          // edge i + 1/2
+          const double gi_w = pu_w * px_edge_excess(fw2, fw1, cl.c, fe1, pu_w);          // edge i - 1/2
+          const double gj_c = spv_c * px_edge_excess(cl.m1, cl.c, cl.p1, cl.p2, spv_c);  // edge j + 1/2
+          const double div = (gi_c - gi_w) * rdxj + (gj_c - cl.gj_n) * rdy;
+          trc_out[f][c] -= (div * dt) * rpn;
+          cl.m2 = cl.m1; cl.m1 = cl.c; cl.c = cl.p1; cl.p1 = cl.p2;
+          if (j + 1 < j1) cl.p2 = a[IDX3(k, jp3, i)];
+          cl.gj_n = gj_c;
+        }
+    }
+    spv_n = spv_c;
+    sp_n = sp_c; sp_c = sp_s;
+    if (j + 1 < j1) sp_s = sp[IDX2(gcm_row(jp1, 1, H, 1), i)];
   }
-  if (x.limit_q)
-    q[c] += -(px_limiter_div(sq, spu, spv_c, spv_n, k, j, jm1, jm2, jp1, jp2, i, im1, im2, ip1, ip2, H, W, dxj, dy) *
-              dt) / pn_c;
-  if (x.limit_t)
-    t[c] += -(px_limiter_div(st, spu, spv_c, spv_n, k, j, jm1, jm2, jp1, jp2, i, im1, im2, ip1, ip2, H, W, dxj, dy) *
-              dt) / pn_c;
 }
 
 int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu, double dt,
@@ -129,11 +155,11 @@ int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_st
   const int H = d.H, W = d.W, L = d.L;
   const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
   const unsigned gx = (unsigned)((W + tc - 1) / tc);
+  const unsigned gy = (unsigned)((d.row_hi - d.row_lo + PX_RJ - 1) / PX_RJ);
   {
     GcmProfScope ps(GCM_K_EXTRAS, stream);
-    GCM_LAUNCH(pe25x_extras_kernel, dim3(gx, d.row_hi - d.row_lo, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p,
-               star->u, star->v, star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, (size_t)H * W,
-               (size_t)L * H * W);
+    GCM_LAUNCH(pe25x_extras_kernel, dim3(gx, gy, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p, star->u, star->v,
+               star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, (size_t)H * W, (size_t)L * H * W);
   }
   GCM_CHECK_LAUNCH();
   return GCM_OK;
