@@ -15,10 +15,10 @@ import math
 import numpy as np
 
 from . import _abi, _host, _lib
-from .constants import radius
+from .constants import G, Md, R, radius
 
 __all__ = ["Geom", "manabe_sig", "equal_sig", "gen_geometry", "gen_square_geometry", "device_geom", "polar_filter_table",
-           "coriolis_parameters"]
+           "coriolis_parameters", "pressure_from_heightmap"]
 
 
 class Geom:
@@ -100,6 +100,14 @@ def gen_square_geometry(height, width, layers, dx, dy, sig_func=equal_sig):
     geom.dy = _host.scalar(dy)
     geom.heightmap = np.zeros((height, width))
     return geom
+
+
+def pressure_from_heightmap(height, sea_level_pressure, sea_level_temp):
+    """geometry.py:185-231: isothermal barometric formula p = p0 exp(-G Md h / (R T0)) -- the surface pressure that
+    goes with a `geom.heightmap` (host side, once; the reference's prints and abandoned attempts are dropped)."""
+    h = np.asarray(_host.magnitude(height), dtype=np.float64)
+    p0, t0 = _host.magnitude(sea_level_pressure), _host.magnitude(sea_level_temp)
+    return p0 * np.exp((-G * Md * h) / (R * t0))
 
 
 def polar_filter_table(geom, im=None):

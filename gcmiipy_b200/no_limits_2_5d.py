@@ -109,6 +109,42 @@ def run_model(height, width, layers, dt, timesteps, callback, stats=True):
     return p, u, v, t, q, g, geom
 
 
+def save_checkpoint(path, p, u, v, t, q, g=None, utc=0.0, nsteps=0):
+    """Checkpoint of a run (the reference has none: a run_model that dies starts over): the five
+    prognostics as float64 SI magnitudes, the ground variables, the model time, the step count and the STATS
+    diagnostics collected so far, in one .npz.  `p ... q` may be host arrays, Quantities or device tensors (e.g.
+    `Stepper.tensors()`); restoring and stepping on gives bit for bit the run that was never interrupted."""
+    def host(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().cpu().numpy()
+        return np.asarray(_host.magnitude(x), dtype=np.float64)
+    arrs = {k: host(x) for k, x in zip("puvtq", (p, u, v, t, q))}
+    if g is not None:
+        for k, x in zip(GroundVars._fields, g):
+            arrs["g_" + k] = host(x)
+    for k, vals in STATS.items():
+        arrs["stats_" + k] = np.asarray(vals, dtype=np.float64)
+    arrs["utc"] = np.float64(_host.scalar(utc))
+    arrs["nsteps"] = np.int64(nsteps)
+    with open(path, "wb") as f:
+        np.savez(f, **arrs)
+
+
+def load_checkpoint(path, restore_stats=True):
+    """-> (p, u, v, t, q, g, utc, nsteps) as written by save_checkpoint (g is None if none was saved); STATS is
+    restored to what it was at the checkpoint unless restore_stats=False."""
+    with np.load(path) as z:
+        state = tuple(z[k] for k in "puvtq")
+        g = GroundVars(*(z["g_" + k] for k in GroundVars._fields)) if "g_gt" in z.files else None
+        if restore_stats:
+            STATS.clear()
+            for k in z.files:
+                if k.startswith("stats_"):
+                    a = z[k]
+                    STATS[k[6:]] = [tuple(r) for r in a] if a.ndim == 2 else [float(x) for x in a]
+        return state + (g, float(z["utc"]), int(z["nsteps"]))
+
+
 def main():
     """no_limits_2_5d.py:256-270 at a stable time step (the reference's 1800 s diverges)."""
     p, u, v, t, q, g, geom = run_model(8, 8, 3, 450.0, 200, None)

@@ -57,5 +57,16 @@ def main():
          hs_p=hs[0], hs_u=hs[1], hs_v=hs[2], hs_t=hs[3], hs_q=hs[4], **out)
 
 
+def barometric():
+    """geometry.pressure_from_heightmap (geometry.py:185-231) on a few heights."""
+    const, geometry = ref_loader.load("constants", "geometry")
+    U = const.units
+    h = np.array([[0.0, 100.0, 1000.0], [2500.0, 5000.0, 8848.0]])
+    with ref_loader.quiet():
+        p = geometry.pressure_from_heightmap(h * U.m, 101325.0 * U.Pa, 288.15 * U.K)
+    save("barometric", height=h, p0=101325.0, t0=288.15, p=p)
+
+
 if __name__ == "__main__":
+    barometric()
     main()

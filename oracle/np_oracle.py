@@ -135,6 +135,12 @@ def gen_square_geometry(height, width, layers, dx, dy, sig_func=equal_sig):
     return geom
 
 
+def pressure_from_heightmap(height, sea_level_pressure, sea_level_temp):
+    """geometry.py:185-231 (returns `wiki_val`, :227): R = 8.3145 J/(K mol), Md = 28.97 g/mol (constants.py:10,13)."""
+    R, Md = 8.3145, 28.97e-3
+    return sea_level_pressure * np.exp((-G * Md * height) / (R * sea_level_temp))
+
+
 # ---- low_pass.py:14-78 -----------------------------------------------------------------------
 def polar_filter_table(geom, im):
     """smmz[..., n] of low_pass.py:61-72: 1 for n = 0, min(1, (dx_j/dy)/sin(pi n/im)) for n >= 1."""

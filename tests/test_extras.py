@@ -240,6 +240,39 @@ def test_options_are_refused_where_they_do_not_apply(backend):
     check_state(tuple(a.numpy() for a in hout), ref, TOL_CALL)
 
 
+def test_pressure_from_heightmap_golden():
+    """geometry.pressure_from_heightmap (geometry.py:185-231), host-side initial-condition helper."""
+    g = load_golden("barometric")
+    assert np.array_equal(O.pressure_from_heightmap(g["height"], float(g["p0"]), float(g["t0"])), g["p"])
+    assert rel(geometry.pressure_from_heightmap(g["height"], float(g["p0"]), float(g["t0"])), g["p"]) < 1e-15
+
+
+def test_checkpoint_resume_is_bit_identical(backend, tmp_path):
+    """6 steps straight == 3 steps, checkpoint, fresh Stepper from the file, 3 steps."""
+    from gcmiipy_b200 import no_limits_2_5d as nl
+    geom, og, s = _case(24, 36, 9, seed=21)
+    dynamics.configure(geom, coriolis=True, limit_q=True)
+    a = dynamics.Stepper(geom, *s)
+    a.step(450.0, 6)
+    b = dynamics.Stepper(geom, *s)
+    b.step(450.0, 3)
+    nl.STATS.clear()
+    nl.STATS["u_max"].append(1.5)
+    nl.STATS["ke"].append((1.0, 2.0, 3.0, 6.0))
+    ground = nl.gen_initial_conditions(geom)[5]
+    path = str(tmp_path / "ck.npz")
+    nl.save_checkpoint(path, *b.tensors(), g=ground, utc=3 * 450.0, nsteps=3)
+    nl.STATS.clear()
+    p, u, v, t, q, g2, utc, n = nl.load_checkpoint(path)
+    assert (utc, n) == (1350.0, 3) and nl.STATS["u_max"] == [1.5] and nl.STATS["ke"] == [(1.0, 2.0, 3.0, 6.0)]
+    assert np.array_equal(g2.gt, ground.gt)
+    c = dynamics.Stepper(geom, p, u, v, t, q)
+    c.step(450.0, 3)
+    for x, y in zip(a.download(), c.download()):
+        assert np.array_equal(x, y)
+    nl.STATS.clear()
+
+
 @pytest.mark.gpu
 def test_options_full_size_properties():
     """1 x 1.25 deg grid (BASELINE configs[2]): with the limiter on q only, surface pressure, winds and theta are
