@@ -265,3 +265,52 @@ __device__ __forceinline__ void gcm_filter_rows_io(double2* z, int nrows, const 
   }
   __syncthreads();
 }
+
+// ---- plans known at compile time ---------------------------------------------------------------------------------
+// gcm_filter_rows_io picks every stage's butterfly with a runtime switch over eleven radices: the kernel image holds
+// 5 x 11 unrolled stage bodies (~20 000 SASS instructions, 330 KB) of which one plan executes ~2 200, scattered over
+// the image -- ncu shows `no_instruction` (instruction fetch) as the first stall reason of the filter kernels (r02m).
+// For the plans of the grids BASELINE.json names the radices are template constants, so the image of a filter kernel
+// is the five stage bodies it runs and nothing else (fits the 32 KB L1.5 instruction cache).
+template <int PLAN>
+struct GcmFixedPlan;
+template <> struct GcmFixedPlan<1> { static constexpr int n = 3, r0 = 12, r1 = 8, rl = 15; };  // W = 1440
+template <> struct GcmFixedPlan<2> { static constexpr int n = 3, r0 = 12, r1 = 8, rl = 3; };   // W = 288
+template <> struct GcmFixedPlan<3> { static constexpr int n = 2, r0 = 8, r1 = 0, rl = 9; };    // W = 72
+template <> struct GcmFixedPlan<4> { static constexpr int n = 2, r0 = 12, r1 = 0, rl = 3; };   // W = 36
+#define GCM_FIXED_PLANS 4
+
+// 0 = no compile-time twin of this plan (take the runtime switch)
+__host__ inline int gcm_fixed_plan_id(const GcmFftPlan& p) {
+  auto is = [&](int n, int a, int b, int c) {
+    return p.npass == n && p.radix[0] == a && p.radix[1] == b && (n == 2 || p.radix[2] == c);
+  };
+  if (is(3, 12, 8, 15)) return 1;
+  if (is(3, 12, 8, 3)) return 2;
+  if (is(2, 8, 9, 0)) return 3;
+  if (is(2, 12, 3, 0)) return 4;
+  return 0;
+}
+
+template <int NPJ, int PLAN, class IO>
+__device__ __forceinline__ void gcm_filter_rows_io_fixed(double2* z, int nrows, const GcmFftPlan& plan,
+                                                         const double2* __restrict__ tw,
+                                                         const double* __restrict__ table, const GcmRowSeg seg, int pr0,
+                                                         IO& io, int tid, int nthr) {
+  using P = GcmFixedPlan<PLAN>;
+  constexpr int last = P::n - 1;
+  gcm_dif_stage_first<P::r0>(z, gcm_fft_stage(plan, 0), nrows, tw, io, tid, nthr);
+  __syncthreads();
+  if constexpr (P::n == 3) {
+    gcm_dif_stage<(P::r1 > 0 ? P::r1 : 2)>(z, gcm_fft_stage(plan, 1), nrows, tw, tid, nthr);
+    __syncthreads();
+  }
+  gcm_mid_stage<P::rl, NPJ>(z, gcm_fft_stage(plan, last), nrows, table, seg, pr0, tid, nthr);
+  __syncthreads();
+  if constexpr (P::n == 3) {
+    gcm_dit_stage<(P::r1 > 0 ? P::r1 : 2)>(z, gcm_fft_stage(plan, 1), nrows, tw, tid, nthr);
+    __syncthreads();
+  }
+  gcm_dit_stage_last<P::r0>(z, gcm_fft_stage(plan, 0), nrows, tw, io, tid, nthr);
+  __syncthreads();
+}

@@ -166,7 +166,8 @@ struct PfFilterIO {
   }
 };
 
-template <int L, int MODE>
+// PLAN > 0: the radices of the plan are compile-time constants (GcmFixedPlan); 0: runtime switch, any plan
+template <int L, int MODE, int PLAN>
 __global__ void __launch_bounds__(256, 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
                     size_t bstride2, size_t bstride3) {
@@ -178,7 +179,36 @@ pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* i
   const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
   PfFilterIO<L, MODE> io{sp + blockIdx.y * bstride2, in + blockIdx.y * bstride3, out + blockIdx.y * bstride3, seg, pr0, W,
                          g.H * W};
-  gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
+  if constexpr (PLAN > 0)
+    gcm_filter_rows_io_fixed<NP, PLAN>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
+  else
+    gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
+}
+
+// launch of the filter kernel whose image matches the plan
+template <int L, int MODE, int PLAN>
+static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream, const double* sp,
+                                 const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3) {
+#ifndef GCM_EMU
+  if (smem > 48 * 1024)
+    GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+#endif
+  GCM_LAUNCH((pe25f_filter_kernel<L, MODE, PLAN>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, b2, b3);
+  GCM_CHECK_LAUNCH();
+  return GCM_OK;
+}
+template <int L, int MODE>
+static int pf_filter_launch(int plan_id, const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream,
+                            const double* sp, const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2,
+                            size_t b3) {
+  switch (plan_id) {
+    case 1: return pf_filter_launch_plan<L, MODE, 1>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+    case 2: return pf_filter_launch_plan<L, MODE, 2>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+    case 3: return pf_filter_launch_plan<L, MODE, 3>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+    case 4: return pf_filter_launch_plan<L, MODE, 4>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+    default: return pf_filter_launch_plan<L, MODE, 0>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+  }
 }
 
 // aflux (dynamics.py:35-46) and p_n (:193-194): one thread per column of the rows of `seg`; needs the filtered spu.
@@ -704,7 +734,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int g_gcm_knob[8] = {0};
+int g_gcm_knob[10] = {0};
 
 // tuning knobs (bench.py --knob i=v; 0 = automatic):
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
@@ -713,8 +743,9 @@ int g_gcm_knob[8] = {0};
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
+//   8  1 = filter kernel with the runtime radix switch even when the plan has a compile-time twin (GcmFixedPlan)
 extern "C" int gcm_tuning_knob(int idx, int value) {
-  GCM_REQUIRE(idx >= 0 && idx < 8, GCM_ESHAPE);
+  GCM_REQUIRE(idx >= 0 && idx < 10, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
   ++g_gcm_tuning_epoch;
   return GCM_OK;
@@ -774,12 +805,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     if (g_gcm_knob[0] > 0) tf = g_gcm_knob[0] > 256 ? 256 : g_gcm_knob[0];
     const size_t smf = nbf * prsmem;
     const dim3 gridf((npr_total + nbf - 1) / nbf, nbatch);
-#ifndef GCM_EMU
-    if (smf > 48 * 1024) {
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-    }
-#endif
+    const int plan_id = g_gcm_knob[8] == 1 ? 0 : gcm_fixed_plan_id(d.plan);  // compile-time radices when known
     // hydro launch: warp tasks of RG rows x 31 columns; shrink RG until there are about 16 warps per SM
     const int nchunk = (W + 30) / 31;
     int rg = 8;
@@ -789,9 +815,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const int ntasks = nchunk * ((nrowsR + rg - 1) / rg);
     {
       GcmProfScope ps(GCM_K_FILTER_A, qa);
-      GCM_LAUNCH((pe25f_filter_kernel<L, 1>), gridf, dim3(tf), smf, qa, d, star->p, star->u, w.spu, segR, nbf, b2, b3);
+      int stf = pf_filter_launch<L, 1>(plan_id, d, gridf, tf, smf, qa, star->p, star->u, w.spu, segR, nbf, b2, b3);
+      if (stf) return stf;
     }
-    GCM_CHECK_LAUNCH();
     if (W < 62 && g_gcm_knob[7] != 1) {  // narrow rows: whole row groups per CTA, east neighbour through shared memory
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const int ngrp = (nrowsR + rg - 1) / rg;
@@ -834,9 +860,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     GCM_CHECK_LAUNCH();
     {
       GcmProfScope ps(GCM_K_FILTER_B, qb);
-      GCM_LAUNCH((pe25f_filter_kernel<L, 0>), gridf, dim3(tf), smf, qb, d, star->p, w.pgf, w.pgf, segR, nbf, b2, b3);
+      int stf = pf_filter_launch<L, 0>(plan_id, d, gridf, tf, smf, qb, star->p, w.pgf, w.pgf, segR, nbf, b2, b3);
+      if (stf) return stf;
     }
-    GCM_CHECK_LAUNCH();
 #ifndef GCM_EMU
     if (side) {
       GCM_CUDA(cudaEventRecord(ev_join, qb));

@@ -121,7 +121,7 @@ int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_in, const g
  * (L in {3, 9}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
  * comparisons, widths with other prime factors). */
 int gcm_pe25_select_path(int path);
-/* launch-shape tuning knobs of the fused kernels (idx 0..7, see pe25_fast.cu); 0 = automatic */
+/* launch-shape tuning knobs of the fused kernels (idx 0..9, see pe25_fast.cu); 0 = automatic */
 int gcm_tuning_knob(int idx, int value);
 
 /* Opt-in terms of the 2.5-D half step.  All OFF by default: the step is then the
