@@ -21,8 +21,6 @@
 #include "gcm_common.h"
 #include "prof.h"
 
-#define IDX3(k, j, i) (((size_t)(k) * H + (size_t)(j)) * W + (size_t)(i))
-#define IDX2(j, i) ((size_t)(j) * W + (size_t)(i))
 
 // Limited edge value minus the centred one at the edge between q0 and q1 (qm, q0 | q1, q2), upwind by the sign of the
 // mass flux (flux_limiter.py:23-27).  With r = a / b the slope ratio of calc_r (:14-20; 0 where b == 0) seen from the
@@ -42,23 +40,26 @@ struct PxColumn {
   double m2, m1, c, p1, p2, gj_n;
 };
 
-#define PX_RJ 8  // rows a thread marches over
+// rows a thread marches over: 8 on large grids, fewer when the launch would not fill the chip
+#define PX_RJ_MAX 8
 
 __global__ void __launch_bounds__(128)
 pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, const double* __restrict__ su,
                     const double* __restrict__ sv, const double* __restrict__ st, const double* __restrict__ sq,
                     const double* __restrict__ spu, const double* __restrict__ pn, double* __restrict__ u,
-                    double* __restrict__ v, double* __restrict__ t, double* __restrict__ q, double dt, size_t b2,
-                    size_t b3) {
+                    double* __restrict__ v, double* __restrict__ t, double* __restrict__ q, double dt, int rj,
+                    size_t b2, size_t b3) {
   const int H = g.H, W = g.W, L = g.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W) return;
-  const int j0 = g.row_lo + blockIdx.y * PX_RJ;
-  const int j1 = j0 + PX_RJ < g.row_hi ? j0 + PX_RJ : g.row_hi;
+  const int j0 = g.row_lo + blockIdx.y * rj;
+  const int j1 = j0 + rj < g.row_hi ? j0 + rj : g.row_hi;
   const int k = blockIdx.z % L, b = blockIdx.z / L;
+  // member and layer folded into the pointers: every access below is pointer + 32-bit (row * W + column)
+  const size_t o3 = b * b3 + (size_t)k * H * W;
   sp += b * b2; pn += b * b2;
-  su += b * b3; sv += b * b3; st += b * b3; sq += b * b3; spu += b * b3;
-  u += b * b3; v += b * b3; t += b * b3; q += b * b3;
+  su += o3; sv += o3; st += o3; sq += o3; spu += o3;
+  u += o3; v += o3; t += o3; q += o3;
 
   const int ip1 = gcm_ip(i, W), im1 = gcm_im(i, W), ip2 = gcm_ip(ip1, W), im2 = gcm_im(im1, W);
   const double rdy = g.rdy;
@@ -67,84 +68,86 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
   double* const trc_out[2] = {q, t};
   const bool trc_on[2] = {x.limit_q != 0, x.limit_t != 0};
 
-  // state carried from row to row
-  int jm1 = gcm_row(j0, -1, H, 1), jm2 = gcm_row(jm1, -1, H, 1), jp1 = gcm_row(j0, 1, H, 1);
-  double sp_n = sp[IDX2(jm1, i)], sp_c = sp[IDX2(j0, i)], sp_s = sp[IDX2(jp1, i)];
-  double spv_n = sv[IDX3(k, jm1, i)] * ((sp_n + sp_c) / 2);  // star mass flux in j (dynamics.py:191) through the north edge
+  // state carried from row to row (row offsets r* = row * W)
+  int jm1 = gcm_row(j0, -1, H, 1), jp1 = gcm_row(j0, 1, H, 1);
+  int rn = jm1 * W, rc = j0 * W, rs = jp1 * W;
+  double sp_n = sp[rn + i], sp_c = sp[rc + i], sp_s = sp[rs + i];
+  double spv_n = sv[rn + i] * ((sp_n + sp_c) / 2);  // star mass flux in j (dynamics.py:191) through the north edge
   PxColumn col[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f)
     if (trc_on[f]) {
       const double* __restrict__ a = trc_in[f];
-      const int jp2 = gcm_row(jp1, 1, H, 1);
-      col[f].m2 = a[IDX3(k, jm2, i)]; col[f].m1 = a[IDX3(k, jm1, i)]; col[f].c = a[IDX3(k, j0, i)];
-      col[f].p1 = a[IDX3(k, jp1, i)]; col[f].p2 = a[IDX3(k, jp2, i)];
+      const int rn2 = gcm_row(jm1, -1, H, 1) * W, rs2 = gcm_row(jp1, 1, H, 1) * W;
+      col[f].m2 = a[rn2 + i]; col[f].m1 = a[rn + i]; col[f].c = a[rc + i];
+      col[f].p1 = a[rs + i]; col[f].p2 = a[rs2 + i];
       col[f].gj_n = spv_n * px_edge_excess(col[f].m2, col[f].m1, col[f].c, col[f].p1, spv_n);
     }
 
   for (int j = j0; j < j1; ++j) {
-    jm1 = gcm_row(j, -1, H, 1);
-    jp1 = gcm_row(j, 1, H, 1);
-    const size_t c = IDX3(k, j, i);
+    const int jp2 = gcm_row(jp1, 1, H, 1);
+    const int rs2 = jp2 * W;
+    const int c = rc + i;
     const double rdxj = g.rdx_j[j];
-    const double pn_c = pn[IDX2(j, i)];
+    const double pn_c = pn[c];
     const double sv_c = sv[c];
     const double spv_c = sv_c * ((sp_c + sp_s) / 2);
 
     if (momentum) {
       double fu = 0.0, fv = 0.0;  // what is added to dut + dus + pgfu and to dvt + dvs + phiv + pgv
-      const double sp_e = sp[IDX2(j, ip1)];
+      const double sp_e = sp[rc + ip1];
       if (x.coriolis) {
-        const double sp_se = sp[IDX2(jp1, ip1)], sp_ne = sp[IDX2(jm1, ip1)];
-        const double spv_e = sv[IDX3(k, j, ip1)] * ((sp_e + sp_se) / 2);
-        const double spv_ne = sv[IDX3(k, jm1, ip1)] * ((sp_ne + sp_e) / 2);
+        const double sp_se = sp[rs + ip1], sp_ne = sp[rn + ip1];
+        const double spv_e = sv[rc + ip1] * ((sp_e + sp_se) / 2);
+        const double spv_ne = sv[rn + ip1] * ((sp_ne + sp_e) / 2);
         const double pv_at_pu = ((spv_c + spv_n) / 2 + (spv_e + spv_ne) / 2) / 2;  // iph(jmh(pv)), dynamics.py:87
-        const double pu_at_pv = ((spu[c] + spu[IDX3(k, jp1, i)]) / 2 +
-                                 (spu[IDX3(k, j, im1)] + spu[IDX3(k, jp1, im1)]) / 2) / 2;  // imh(jph(pu)), :86
+        const double pu_at_pv = ((spu[c] + spu[rs + i]) / 2 + (spu[rc + im1] + spu[rs + im1]) / 2) / 2;  // imh(jph(pu)), :86
         fu += x.cor_u[j] * -pv_at_pu;  // :94
         fv += x.cor_v[j] * pu_at_pv;   // :95
       }
       const bool wall = (j == g.zero_v_row || j == g.zero_v_row2);  // v_n[:, -1, :] stays 0 (dynamics.py:222)
       if (x.nu != 0.0) {
         const double u0 = su[c];
-        const double lap_u = (su[IDX3(k, j, ip1)] + su[IDX3(k, j, im1)] - 2 * u0) * (rdxj * rdxj) +
-                             (su[IDX3(k, jp1, i)] + su[IDX3(k, jm1, i)] - 2 * u0) * (rdy * rdy);
+        const double lap_u = (su[rc + ip1] + su[rc + im1] - 2 * u0) * (rdxj * rdxj) +
+                             (su[rs + i] + su[rn + i] - 2 * u0) * (rdy * rdy);
         fu -= (sp_c + sp_e) / 2 * (x.nu * lap_u);
         if (!wall) {
           const double rdxh = g.rdx_h[j];
-          const double lap_v = (sv[IDX3(k, j, ip1)] + sv[IDX3(k, j, im1)] - 2 * sv_c) * (rdxh * rdxh) +
-                               (sv[IDX3(k, jp1, i)] + sv[IDX3(k, jm1, i)] - 2 * sv_c) * (rdy * rdy);
+          const double lap_v = (sv[rc + ip1] + sv[rc + im1] - 2 * sv_c) * (rdxh * rdxh) +
+                               (sv[rs + i] + sv[rn + i] - 2 * sv_c) * (rdy * rdy);
           fv -= (sp_c + sp_s) / 2 * (x.nu * lap_v);
         }
       }
-      u[c] -= (fu * dt) * gcm_rcp((pn_c + pn[IDX2(j, ip1)]) / 2);
-      if (!wall) v[c] -= (fv * dt) * gcm_rcp((pn_c + pn[IDX2(jp1, i)]) / 2);
+      u[c] -= (fu * dt) * gcm_rcp((pn_c + pn[rc + ip1]) / 2);
+      if (!wall) v[c] -= (fv * dt) * gcm_rcp((pn_c + pn[rs + i]) / 2);
     }
 
     if (trc_on[0] || trc_on[1]) {
-      const double pu_c = spu[c], pu_w = spu[IDX3(k, j, im1)];
+      const double pu_c = spu[c], pu_w = spu[rc + im1];
       const double rpn = gcm_rcp(pn_c);
-      const int jp3 = gcm_row(gcm_row(jp1, 1, H, 1), 1, H, 1);
+      const int rs3 = gcm_row(jp2, 1, H, 1) * W;
 #pragma unroll
       for (int f = 0; f < 2; ++f)
         if (trc_on[f]) {
           const double* __restrict__ a = trc_in[f];
           PxColumn& cl = col[f];
-          const double fw1 = a[IDX3(k, j, im1)], fw2 = a[IDX3(k, j, im2)];
-          const double fe1 = a[IDX3(k, j, ip1)], fe2 = a[IDX3(k, j, ip2)];
+          const double fw1 = a[rc + im1], fw2 = a[rc + im2];
+          const double fe1 = a[rc + ip1], fe2 = a[rc + ip2];
           const double gi_c = pu_c * px_edge_excess(fw1, cl.c, fe1, fe2, pu_c);          // edge i + 1/2
           const double gi_w = pu_w * px_edge_excess(fw2, fw1, cl.c, fe1, pu_w);          // edge i - 1/2
           const double gj_c = spv_c * px_edge_excess(cl.m1, cl.c, cl.p1, cl.p2, spv_c);  // edge j + 1/2
           const double div = (gi_c - gi_w) * rdxj + (gj_c - cl.gj_n) * rdy;
           trc_out[f][c] -= (div * dt) * rpn;
           cl.m2 = cl.m1; cl.m1 = cl.c; cl.c = cl.p1; cl.p1 = cl.p2;
-          if (j + 1 < j1) cl.p2 = a[IDX3(k, jp3, i)];
+          if (j + 1 < j1) cl.p2 = a[rs3 + i];
           cl.gj_n = gj_c;
         }
     }
     spv_n = spv_c;
     sp_n = sp_c; sp_c = sp_s;
-    if (j + 1 < j1) sp_s = sp[IDX2(gcm_row(jp1, 1, H, 1), i)];
+    if (j + 1 < j1) sp_s = sp[rs2 + i];
+    rn = rc; rc = rs; rs = rs2;
+    jp1 = jp2;
   }
 }
 
@@ -152,14 +155,18 @@ int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_st
                           int nbatch, void* stream) {
   const GcmGeomDev& d = g->d;
   GCM_REQUIRE(d.wrap_j, GCM_EUNSUP);
-  const int H = d.H, W = d.W, L = d.L;
+  GCM_REQUIRE((double)d.H * d.W < 2147483648.0, GCM_EUNSUP);  // 32-bit offsets within a layer
+  const int H = d.H, W = d.W, L = d.L, nrows = d.row_hi - d.row_lo;
   const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
   const unsigned gx = (unsigned)((W + tc - 1) / tc);
-  const unsigned gy = (unsigned)((d.row_hi - d.row_lo + PX_RJ - 1) / PX_RJ);
+  int rj = PX_RJ_MAX;  // shorter marches until the launch has about four CTAs per SM
+  while (rj > 1 && (size_t)gx * ((nrows + rj - 1) / rj) * L * nbatch < 592) rj /= 2;
+  const unsigned gy = (unsigned)((nrows + rj - 1) / rj);
   {
     GcmProfScope ps(GCM_K_EXTRAS, stream);
     GCM_LAUNCH(pe25x_extras_kernel, dim3(gx, gy, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p, star->u, star->v,
-               star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, (size_t)H * W, (size_t)L * H * W);
+               star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, rj, (size_t)H * W,
+               (size_t)L * H * W);
   }
   GCM_CHECK_LAUNCH();
   return GCM_OK;
