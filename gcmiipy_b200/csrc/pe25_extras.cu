@@ -13,7 +13,8 @@
 //   q_n += -dt div(G) / p_n,   G = mass flux * (limited edge value - centred edge value)
 // One thread per column (i, k) marches PX_RJ rows south: the tracer column j-2 ... j+2 and the flux through the north
 // edge ride in registers, so a row costs one new load per tracer in j and three limiter evaluations instead of four.
-// Divides are reciprocals (metric tables, gcm_rcp): fp64 division is a ~30-instruction software sequence.
+// Divides are reciprocals (metric tables, gcm_rcp): fp64 division is a ~30-instruction software sequence.  The march is
+// bound by load latency (ncu r03c: long-scoreboard 12.9 cycles per issue), so each row asks the next row's lines into L1.
 // The default path (no option set) launches nothing from this file and stays bit-identical to the reference step.
 // Whole-grid geometries only (rows periodic in j): the limiter reads j - 2 ... j + 2.
 #include <math.h>
@@ -88,6 +89,23 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
     const int jp2 = gcm_row(jp1, 1, H, 1);
     const int rs2 = jp2 * W;
     const int c = rc + i;
+    if (j + 1 < j1) {  // the next row's lines into L1 while this row is computed (the march is load-latency bound)
+      const int cn = rs + i;
+      gcm_prefetch_l1(pn + cn);
+      gcm_prefetch_l1(spu + cn);
+      if (momentum) {
+        gcm_prefetch_l1(u + cn);
+        gcm_prefetch_l1(v + cn);
+        gcm_prefetch_l1(su + rs2 + i);
+        gcm_prefetch_l1(sv + rs2 + i);
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+        if (trc_on[f]) {
+          gcm_prefetch_l1(trc_out[f] + cn);
+          gcm_prefetch_l1(trc_in[f] + gcm_row(jp2, 1, H, 1) * W + i);
+        }
+    }
     const double rdxj = g.rdx_j[j];
     const double pn_c = pn[c];
     const double sv_c = sv[c];
