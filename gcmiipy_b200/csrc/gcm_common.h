@@ -19,6 +19,30 @@
   type* name = reinterpret_cast<type*>(gcm_dyn_smem_)
 #endif
 
+#ifdef GCM_EMU
+#define GCM_LAUNCH_DEP GCM_LAUNCH
+#else
+// launch with the programmatic-stream-serialization attribute when `pdl` is set (see gcm_pdl_wait), else like <<<>>>
+template <class... KArgs, class... Args>
+static inline void gcm_launch_dep(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+extern int g_gcm_knob[10];
+#define GCM_LAUNCH_DEP(kern, grid, block, smem, stream, ...) \
+  gcm_launch_dep(g_gcm_knob[9] > 0, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
+#endif
+
 #define GCM_CHECK_LAUNCH()                        \
   do {                                            \
     cudaError_t e_ = cudaGetLastError();          \
@@ -136,6 +160,21 @@ __device__ __forceinline__ void gcm_cp_async_wait() {
 #endif
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// be scheduled before its predecessor in the stream has drained; gcm_pdl_wait() blocks until every prerequisite grid
+// has completed and its writes are visible, so it must precede the first global access of a kernel; both are no-ops in
+// a kernel launched the ordinary way.  gcm_pdl_trigger() lets the dependents of THIS grid start being scheduled.
+__device__ __forceinline__ void gcm_pdl_wait() {
+#ifndef GCM_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void gcm_pdl_trigger() {
+#ifndef GCM_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // device-resident geometry tables, passed to kernels by value
 struct GcmGeomDev {
   int H, W, L;
@@ -164,6 +203,7 @@ struct GcmGeomDev {
   const double2* tws;   // per-stage twiddles of the in-place transform, contiguous in the butterfly index:
                         //         tws[twoff[s] + (m-1) stride_s + q] = exp(-2 pi i q m / n_s)
   double rdy;           // 1 / dy
+  int pdl_early;        // 1 = kernels trigger their dependents at entry (set per launch from tuning knob 9)
   // per-layer tables by value (kernel parameters live in the constant bank: no load instruction) when L <= 16
   double c_sig[GCM_MAXLC], c_dsig[GCM_MAXLC], c_sigb[GCM_MAXLC], c_sigt[GCM_MAXLC], c_rdsig[GCM_MAXLC],
       c_sigkap[GCM_MAXLC];

@@ -171,6 +171,8 @@ template <int L, int MODE, int PLAN>
 __global__ void __launch_bounds__(256, 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
                     size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   GCM_DYN_SMEM(double2, z);
   constexpr int NP = (L + 1) / 2;
   const int W = g.W;
@@ -194,7 +196,7 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
     GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
 #endif
-  GCM_LAUNCH((pe25f_filter_kernel<L, MODE, PLAN>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, b2, b3);
+  GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, b2, b3);
   GCM_CHECK_LAUNCH();
   return GCM_OK;
 }
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(128)
 pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __restrict__ sp_,
                    const double* __restrict__ sv_, PfWork w, double dt, GcmRowSeg seg, unsigned magicW, size_t bstride2,
                    size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   const int H = g.H, W = g.W, plane = H * W;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gcm_fastdiv(t, magicW), i = t - r * W;
@@ -258,6 +262,8 @@ pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __r
 template <int L, bool PTOP0>
 __global__ void __launch_bounds__(128, 4)
 pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   const int H = g.H, W = g.W, plane = H * W;
   const int lane = threadIdx.x & 31;
   const int nchunk = (W + 30) / 31, nrows = seg.n1 + seg.n2, ngrp = (nrows + RG - 1) / RG;
@@ -305,6 +311,8 @@ template <int L, bool PTOP0>
 __global__ void __launch_bounds__(256, 2)
 pe25f_hydro_narrow_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, int G, size_t bstride2,
                           size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   GCM_DYN_SMEM(double, xs);  // [2 parities][2 L + 1 values][blockDim.x]
   const int H = g.H, W = g.W, plane = H * W;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -380,6 +388,8 @@ template <int L>
 __global__ void __launch_bounds__(128, 4)
 pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg, int pfd,
                     unsigned flatW, size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   const int H = g.H, W = g.W, plane = H * W;
   int i, r;
   if (flatW) {  // short rows: threads run over the (row, column) pairs of the launch in row-major order
@@ -539,6 +549,8 @@ template <int L, int PFT_TJ>
 __global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
   constexpr int pfd = 2;  // L1 prefetch distance (layers) of the once-read fields: 1..3 measured alike, off costs 14 %
   GCM_DYN_SMEM(double, sm);
   constexpr int PFT_TILE = (PFT_TJ + 2) * PFT_ROW, PFT_STAGE = PFT_NF * PFT_TILE;  // doubles per field tile / stage
@@ -744,6 +756,8 @@ int g_gcm_knob[10] = {0};
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
 //   8  1 = filter kernel with the runtime radix switch even when the plan has a compile-time twin (GcmFixedPlan)
+//   9  programmatic dependent launch of the half-step kernels: 0 = off, 1 = on (a kernel's launch overlaps the drain
+//      of its predecessor), 2 = on + every kernel triggers its dependents at entry
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 10, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
@@ -765,7 +779,8 @@ bool gcm_pe25_fast_supported(const gcm_geom* g) {
 template <int L>
 static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out, double dt,
                         int nbatch, const PfWork& w, GcmRowSeg segR, GcmRowSeg segU, void* stream) {
-  const GcmGeomDev& d = g->d;
+  GcmGeomDev d = g->d;
+  d.pdl_early = g_gcm_knob[9] == 2;
   const int H = d.H, W = d.W;
   const size_t b2 = (size_t)H * W, b3 = (size_t)L * H * W;
   const int nrowsR = segR.n1 + segR.n2, nrowsU = segU.n1 + segU.n2;
@@ -835,26 +850,26 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       }
 #endif
       if (ptop0)
-        GCM_LAUNCH((pe25f_hydro_narrow_kernel<L, true>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
+        GCM_LAUNCH_DEP((pe25f_hydro_narrow_kernel<L, true>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
       else
-        GCM_LAUNCH((pe25f_hydro_narrow_kernel<L, false>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
+        GCM_LAUNCH_DEP((pe25f_hydro_narrow_kernel<L, false>), gridn, dim3(th), smh, qb, d, cs, w, segR, rg, G, b2, b3);
     } else {
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
       if (ptop0)
-        GCM_LAUNCH((pe25f_hydro_kernel<L, true>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+        GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
       else
-        GCM_LAUNCH((pe25f_hydro_kernel<L, false>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+        GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, false>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
     }
     GCM_CHECK_LAUNCH();
     {
       GcmProfScope ps(GCM_K_AFLUX_F, qa);
       const dim3 grida((nrowsR * W + 127) / 128, nbatch);
       if (tiled)  // the tiled update rebuilds sd: pit and p_n only
-        GCM_LAUNCH((pe25f_aflux_kernel<L, false>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
+        GCM_LAUNCH_DEP((pe25f_aflux_kernel<L, false>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
                    magicW, b2, b3);
       else
-        GCM_LAUNCH((pe25f_aflux_kernel<L, true>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
+        GCM_LAUNCH_DEP((pe25f_aflux_kernel<L, true>), grida, dim3(128), 0, qa, d, base->p, star->p, star->v, w, dt, segR,
                    magicW, b2, b3);
     }
     GCM_CHECK_LAUNCH();
@@ -880,7 +895,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
       const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(PFT_TI, tj);
-      GCM_LAUNCH((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       GCM_CHECK_LAUNCH();
     }
   } else if (nrowsU > 0) {
@@ -892,7 +907,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const dim3 block(32, 4);
     const dim3 grid = flat ? dim3((nrowsU * W + 127) / 128, 1, nbatch) : dim3((W + 31) / 32, (nrowsU + 3) / 4, nbatch);
     const int pfd = g_gcm_knob[5] > 0 ? g_gcm_knob[5] - 1 : 1;
-    GCM_LAUNCH((pe25f_update_kernel<L>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, flatW, b2, b3);
+    GCM_LAUNCH_DEP((pe25f_update_kernel<L>), grid, block, 0, stream, d, cb, cs, mo, w, dt, segU, pfd, flatW, b2, b3);
     GCM_CHECK_LAUNCH();
   }
   return GCM_OK;
