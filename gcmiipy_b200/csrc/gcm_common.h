@@ -40,7 +40,7 @@ static inline void gcm_launch_dep(bool pdl, void (*kern)(KArgs...), dim3 grid, d
 }
 extern int g_gcm_knob[10];
 #define GCM_LAUNCH_DEP(kern, grid, block, smem, stream, ...) \
-  gcm_launch_dep(g_gcm_knob[9] > 0, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
+  gcm_launch_dep(g_gcm_knob[9] != 3, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
 #define GCM_CHECK_LAUNCH()                        \

@@ -756,8 +756,9 @@ int g_gcm_knob[10] = {0};
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
 //   8  1 = filter kernel with the runtime radix switch even when the plan has a compile-time twin (GcmFixedPlan)
-//   9  programmatic dependent launch of the half-step kernels: 0 = off, 1 = on (a kernel's launch overlaps the drain
-//      of its predecessor), 2 = on + every kernel triggers its dependents at entry
+//   9  programmatic dependent launch of the half-step kernels: 0 / 1 = on (a kernel's launch overlaps the drain of its
+//      predecessor in the stream: -3 ... -5 % per step, r03e), 2 = on + every kernel triggers its dependents at entry
+//      (waiting CTAs then hold SM slots the running kernel could use: slower on most grids), 3 = off
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < 10, GCM_ESHAPE);
   g_gcm_knob[idx] = value;

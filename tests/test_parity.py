@@ -402,10 +402,10 @@ def test_full_size_properties(H, W, L, dt):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,L", [(46, 72, 9), (20, 64, 9), (24, 36, 9), (180, 288, 9)])
 def test_programmatic_dependent_launch_is_bit_identical(H, W, L):
-    """Tuning knob 9: the half-step kernels launched with the programmatic-stream-serialization attribute (1) and with
-    an early trigger of their dependents (2) must give the bits of the ordinary launches, single steps and the
-    replayed step-pair graph alike (a kernel that read or overwrote a field before its predecessor had finished would
-    show up here)."""
+    """Tuning knob 9: the half-step kernels launched with the programmatic-stream-serialization attribute (0 / 1, the
+    default) and with an early trigger of their dependents (2) must give the bits of the ordinary launches (3), single
+    steps and the replayed step-pair graph alike (a kernel that read or overwrote a field before its predecessor had
+    finished would show up here)."""
     import torch
     from gcmiipy_b200 import _lib
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
@@ -413,7 +413,7 @@ def test_programmatic_dependent_launch_is_bit_identical(H, W, L):
     s = O.synthetic_state(og, seed=H + W)
     res = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (3, 1, 2):
             assert _lib.lib().gcm_tuning_knob(9, mode) == 0
             st = dynamics.Stepper(geom, *s)
             for _ in range(3):
@@ -424,5 +424,5 @@ def test_programmatic_dependent_launch_is_bit_identical(H, W, L):
     finally:
         _lib.lib().gcm_tuning_knob(9, 0)
     for mode in (1, 2):
-        for a, b in zip(res[0], res[mode]):
+        for a, b in zip(res[3], res[mode]):
             exact(b, a)
