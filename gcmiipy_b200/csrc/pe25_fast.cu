@@ -533,6 +533,127 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// U, one thread per CELL: the direct-load update for launches too small to fill the chip with one thread per column
+// (the 72 x 46 grid is 26 CTAs of columns marching nine layers one after the other: a chain of nine dependent load
+// round trips on 26 of 148 SMs).  Every (k, j, i) is its own thread and evaluates the two sigma-interface fluxes of its
+// layer itself instead of carrying them up the column: the same expressions, operand for operand, as
+// pe25f_update_kernel, 9 x the threads, a ninth of the chain.  Flat over (row, column); blockIdx.y = layer.
+// ---------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(128)
+pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
+                         unsigned flatW, size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
+  const int H = g.H, W = g.W, plane = H * W;
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gcm_fastdiv(tt, flatW), i = tt - r * W;
+  if (r >= seg.n1 + seg.n2) return;
+  const int k = blockIdx.y;
+  const int j = gcm_seg_row(seg, r);
+  const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
+  const double* __restrict__ p = base.p + o2;
+  const double* __restrict__ u = base.u + o3;
+  const double* __restrict__ v = base.v + o3;
+  const double* __restrict__ t = base.t + o3;
+  const double* __restrict__ q = base.q + o3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ su = star.u + o3;
+  const double* __restrict__ sv = star.v + o3;
+  const double* __restrict__ st = star.t + o3;
+  const double* __restrict__ sq = star.q + o3;
+  const double* __restrict__ spu = w.spu + o3;
+  const double* __restrict__ sd = w.sd + o3;
+  const double* __restrict__ pgf = w.pgf + o3;
+  const double* __restrict__ fv = w.fv + o3;
+  const double* __restrict__ pn = w.pn + o2;
+
+  const int wrap = g.wrap_j;
+  const int jm = gcm_row(j, -1, H, wrap), jp = gcm_row(j, 1, H, wrap), jpp = gcm_row(jp, 1, H, wrap);
+  const int im = gcm_im(i, W), ip = gcm_ip(i, W);
+  const double rdxj = g.rdx_j[j], rdxh = g.rdx_h[j], rdy = g.rdy;
+  const int c2 = j * W + i, c2_ip = j * W + ip, c2_jp = jp * W + i, c2_jm = jm * W + i;
+  const int kd = k * plane;
+  const int e_c = kd + c2, e_im = kd + j * W + im, e_ip = kd + c2_ip, e_jp = kd + c2_jp, e_jm = kd + c2_jm,
+            e_jp_im = kd + jp * W + im, e_jm_ip = kd + jm * W + ip;
+
+  // per-column (2-D) factors
+  const double p_c = p[c2], p_ip = p[c2_ip], p_jp = p[c2_jp];
+  const double pn_c = pn[c2], pn_ip = pn[c2_ip], pn_jp = pn[c2_jp];
+  const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                    // calc_pu / calc_pv
+  const double r_pnu = 1.0 / ((pn_c + pn_ip) * 0.5), r_pnv = 1.0 / ((pn_c + pn_jp) * 0.5);  // un_pu / un_pv
+  const double r_pn = 1.0 / pn_c;
+  const double sp_c = sp[c2], sp_ip = sp[c2_ip], sp_jp = sp[c2_jp], sp_jm = sp[c2_jm];
+  const double a_c = (sp_c + sp_jp) * 0.5;                   // jph(sp) at (j, i)
+  const double a_ip = (sp_ip + sp[jp * W + ip]) * 0.5;       // (j, i+1)
+  const double a_jm = (sp_jm + sp_c) * 0.5;                  // (j-1, i)
+  const double a_jm_ip = (sp[jm * W + ip] + sp_ip) * 0.5;    // (j-1, i+1)
+  const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;       // (j+1, i)
+  const bool zero_v = j == g.zero_v_row || j == g.zero_v_row2;
+
+  // advec_sig (dynamics.py:49-52): flux through the bottom of layer k pairs it with layer k - 1 (layer 0 with L - 1,
+  // np.roll, times sd[0] = 0), flux through its top pairs layer k + 1 with it (the top of layer L - 1 is the bottom of
+  // layer 0 again)
+  const int kb = (k == 0 ? L - 1 : k - 1) * plane, kn = (k + 1 < L ? k + 1 : 0) * plane;
+  const double u_k = su[e_c], v_k = sv[e_c], t_k = st[e_c], q_k = sq[e_c];
+  double fu, fv_, ft, fq, fu_n, fv_n, ft_n, fq_n;
+  {
+    const double sd_c = sd[e_c], sd_ip = sd[e_ip], sd_jp = sd[e_jp];
+    fu = (u_k + su[kb + c2]) * 0.5 * ((sd_c + sd_ip) * 0.5);
+    fv_ = (v_k + sv[kb + c2]) * 0.5 * ((sd_c + sd_jp) * 0.5);
+    ft = (t_k + st[kb + c2]) * 0.5 * sd_c;
+    fq = (q_k + sq[kb + c2]) * 0.5 * sd_c;
+  }
+  {
+    const double sd_c = sd[kn + c2], sd_ip = sd[kn + c2_ip], sd_jp = sd[kn + c2_jp];
+    fu_n = (su[kn + c2] + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
+    fv_n = (sv[kn + c2] + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
+    ft_n = (st[kn + c2] + t_k) * 0.5 * sd_c;
+    fq_n = (sq[kn + c2] + q_k) * 0.5 * sd_c;
+  }
+  const double rds = g.rdsig[k];
+  const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;      // -(F_k - F_k+1) / dsig
+  const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
+
+  // horizontal neighbours
+  const double u_im = su[e_im], u_ip = su[e_ip], u_jp = su[e_jp], u_jm = su[e_jm];
+  const double v_im = sv[e_im], v_ip = sv[e_ip], v_jp = sv[e_jp], v_jm = sv[e_jm], v_jm_ip = sv[e_jm_ip];
+  const double pu_c = spu[e_c], pu_im = spu[e_im], pu_ip = spu[e_ip], pu_jp = spu[e_jp], pu_jp_im = spu[e_jp_im];
+  const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
+               pv_jp = v_jp * a_jp;
+
+  // advec_m_pu (dynamics.py:55-108); (a/2)(b/2) = ab/4 exactly
+  const double puum = (u_k + u_im) * (pu_c + pu_im), puup = (u_ip + u_k) * (pu_ip + pu_c);
+  const double puvp = (pv_c + pv_ip) * (u_k + u_jp), puvm = (pv_jm + pv_jm_ip) * (u_jm + u_k);
+  const double dut = ((puum - puup) * rdxj + (puvm - puvp) * rdy) * 0.25;
+  const double pvvm = (v_k + v_jm) * (pv_c + pv_jm), pvvp = (v_jp + v_k) * (pv_jp + pv_c);
+  const double pvup = (v_k + v_ip) * (pu_c + pu_jp), pvum = (v_im + v_k) * (pu_im + pu_jp_im);
+  const double dvt = ((pvvm - pvvp) * rdy + (pvum - pvup) * rdxh) * 0.25;
+
+  const double pu_n = u[e_c] * pu_fac - (dut + dus + pgf[e_c]) * dt;   // dynamics.py:206
+  const double pv_n = v[e_c] * pv_fac - (dvt + dvs + fv[e_c]) * dt;    // dynamics.py:207
+  out.u[o3 + e_c] = pu_n * r_pnu;
+  double v_n = pv_n * r_pnv;
+  if (zero_v) v_n *= 0.0;  // dynamics.py:222
+  out.v[o3 + e_c] = v_n;
+
+  // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
+  {
+    const double x_ip = st[e_ip], x_im = st[e_im], x_jp = st[e_jp], x_jm = st[e_jm];
+    const double adv = ((pu_c * (t_k + x_ip) - pu_im * (x_im + t_k)) * rdxj +
+                        (pv_c * (t_k + x_jp) - pv_jm * (x_jm + t_k)) * rdy) * 0.5;
+    out.t[o3 + e_c] = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
+  }
+  {
+    const double x_ip = sq[e_ip], x_im = sq[e_im], x_jp = sq[e_jp], x_jm = sq[e_jm];
+    const double adv = ((pu_c * (q_k + x_ip) - pu_im * (x_im + q_k)) * rdxj +
+                        (pv_c * (q_k + x_jp) - pv_jm * (x_jm + q_k)) * rdy) * 0.5;
+    out.q[o3 + e_c] = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
+  }
+  if (k == 0) out.p[o2 + c2] = pn_c;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // U, tiled: the same update with every operand staged in shared memory by 8-byte asynchronous copies (LDGSTS), three
 // layers in flight.  A CTA owns a 32 x 4 (i x j) tile; per layer it stages the 34 x 6 halo tile of su, sv, st, sq, spu,
 // sd (each thread its own column, 76 threads one halo-ring element each, periodic wrap resolved per element).  The
@@ -751,7 +872,7 @@ int g_gcm_knob[10] = {0};
 // tuning knobs (bench.py --knob i=v; 0 = automatic):
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
 //   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream
-//   4  1 = update kernel with direct global loads even when W % 32 == 0
+//   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
@@ -903,6 +1024,17 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     // direct loads: 32 x 4 (i x j) tiles; rows shorter than 128 that do not fill 32-wide tiles run flat over
     // (row, column)
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
+    // narrow single grids (the 72 x 46 and 36 x 24 grids, not their ensembles): one thread per cell.  The choice
+    // depends on the width and the member count only, never on the rows of the launch, so a latitude band takes the
+    // same kernel as the whole grid.
+    const bool cells = (size_t)W * nbatch <= 1024 && (size_t)nrowsU * W < (1u << 22) && g_gcm_knob[4] != 2;
+    if (cells) {
+      const dim3 gridc((nrowsU * W + 127) / 128, L, nbatch);
+      GCM_LAUNCH_DEP((pe25f_update_cell_kernel<L>), gridc, dim3(128), 0, stream, d, cb, cs, mo, w, dt, segU,
+                     gcm_magic((unsigned)W), b2, b3);
+      GCM_CHECK_LAUNCH();
+      return GCM_OK;
+    }
     const bool flat = W < 128 && W % 32 != 0 && (size_t)nrowsU * W < (1u << 22);
     const unsigned flatW = flat ? gcm_magic((unsigned)W) : 0u;
     const dim3 block(32, 4);

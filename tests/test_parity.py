@@ -426,3 +426,30 @@ def test_programmatic_dependent_launch_is_bit_identical(H, W, L):
     for mode in (1, 2):
         for a, b in zip(res[3], res[mode]):
             exact(b, a)
+
+
+@pytest.mark.parametrize("H,W,L", [(46, 72, 9), (24, 36, 9), (5, 18, 3), (1, 6, 9)])
+def test_cell_update_kernel_matches_column_march(backend, H, W, L):
+    """Narrow single grids take the one-thread-per-cell update (pe25f_update_cell_kernel); knob 4 = 2 forces the
+    column march (pe25f_update_kernel).  Same expressions operand for operand: the two must agree bit for bit."""
+    from gcmiipy_b200 import _lib
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    hm = 30.0 * np.random.default_rng(W).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    s = O.synthetic_state(og, seed=3 * H + W)
+    res = {}
+    try:
+        for mode in (0, 2):
+            assert _lib.lib().gcm_tuning_knob(4, mode) == 0
+            st = dynamics.Stepper(geom, *s)
+            st.step(100.0, 3)
+            res[mode] = st.download()
+    finally:
+        _lib.lib().gcm_tuning_knob(4, 0)
+    for a, b in zip(res[0], res[2]):
+        exact(a, b)
+    ref = s
+    for _ in range(3):
+        ref = O.matsuno_timestep(*ref, 100.0, og)
+    check_state(res[0], ref, TOL_RUN)
