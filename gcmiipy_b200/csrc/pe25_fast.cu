@@ -872,7 +872,8 @@ int g_gcm_knob[10] = {0};
 // tuning knobs (bench.py --knob i=v; 0 = automatic):
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
 //   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream
-//   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update
+//   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update;
+//      3 = the one-thread-per-cell update for every member count
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
@@ -1027,7 +1028,8 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     // narrow single grids (the 72 x 46 and 36 x 24 grids, not their ensembles): one thread per cell.  The choice
     // depends on the width and the member count only, never on the rows of the launch, so a latitude band takes the
     // same kernel as the whole grid.
-    const bool cells = (size_t)W * nbatch <= 1024 && (size_t)nrowsU * W < (1u << 22) && g_gcm_knob[4] != 2;
+    const bool cells = ((size_t)W * nbatch <= 1024 || g_gcm_knob[4] == 3) && (size_t)nrowsU * W < (1u << 22) &&
+                       g_gcm_knob[4] != 2;
     if (cells) {
       const dim3 gridc((nrowsU * W + 127) / 128, L, nbatch);
       GCM_LAUNCH_DEP((pe25f_update_cell_kernel<L>), gridc, dim3(128), 0, stream, d, cb, cs, mo, w, dt, segU,

@@ -431,7 +431,8 @@ def test_programmatic_dependent_launch_is_bit_identical(H, W, L):
 @pytest.mark.parametrize("H,W,L", [(46, 72, 9), (24, 36, 9), (5, 18, 3), (1, 6, 9)])
 def test_cell_update_kernel_matches_column_march(backend, H, W, L):
     """Narrow single grids take the one-thread-per-cell update (pe25f_update_cell_kernel); knob 4 = 2 forces the
-    column march (pe25f_update_kernel).  Same expressions operand for operand: the two must agree bit for bit."""
+    column march (pe25f_update_kernel).  Same expressions operand for operand: bit for bit on the emulator build, to
+    the last bit or two on the GPU (FMA contraction is chosen per kernel by the compiler)."""
     from gcmiipy_b200 import _lib
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
     og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
@@ -448,7 +449,10 @@ def test_cell_update_kernel_matches_column_march(backend, H, W, L):
     finally:
         _lib.lib().gcm_tuning_knob(4, 0)
     for a, b in zip(res[0], res[2]):
-        exact(a, b)
+        if backend == "emu":
+            exact(a, b)            # no FMA contraction on the CPU build: bit for bit
+        else:
+            assert rel(a, b) <= 1e-14   # nvcc contracts a*b+c per kernel as it sees fit: last-bit differences
     ref = s
     for _ in range(3):
         ref = O.matsuno_timestep(*ref, 100.0, og)
