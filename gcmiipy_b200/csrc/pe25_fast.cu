@@ -914,7 +914,13 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
   const unsigned magicW = gcm_magic((unsigned)W);
-  const bool tiled = W % PFT_TI == 0 && g_gcm_knob[4] != 1;  // update on staged shared-memory tiles
+  // Update kernel.  Narrow single grids (W x members <= 512: the 72 x 46, 288 x 180 and 36 x 24 grids, not their
+  // ensembles) take one thread per cell: too few columns to fill the chip with a thread per column or a CTA per tile.
+  // The choice depends on the width and the member count only, never on the rows of the launch, so a latitude band
+  // takes the same kernel as the whole grid (bit-identical decomposition).
+  const bool cells = ((size_t)W * nbatch <= 512 || g_gcm_knob[4] == 3) && (size_t)(segU.n1 + segU.n2) * W < (1u << 22) &&
+                     g_gcm_knob[4] != 2;
+  const bool tiled = !cells && W % PFT_TI == 0 && g_gcm_knob[4] != 1;  // update on staged shared-memory tiles
   if (nrowsR > 0) {
     // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run
     // side by side (caller's stream + the geometry's side stream).
@@ -1025,11 +1031,6 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     // direct loads: 32 x 4 (i x j) tiles; rows shorter than 128 that do not fill 32-wide tiles run flat over
     // (row, column)
     GcmProfScope ps(GCM_K_UPDATE_FAST, stream);
-    // narrow single grids (the 72 x 46 and 36 x 24 grids, not their ensembles): one thread per cell.  The choice
-    // depends on the width and the member count only, never on the rows of the launch, so a latitude band takes the
-    // same kernel as the whole grid.
-    const bool cells = ((size_t)W * nbatch <= 1024 || g_gcm_knob[4] == 3) && (size_t)nrowsU * W < (1u << 22) &&
-                       g_gcm_knob[4] != 2;
     if (cells) {
       const dim3 gridc((nrowsU * W + 127) / 128, L, nbatch);
       GCM_LAUNCH_DEP((pe25f_update_cell_kernel<L>), gridc, dim3(128), 0, stream, d, cb, cs, mo, w, dt, segU,

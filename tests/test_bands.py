@@ -34,8 +34,18 @@ def test_single_rank_band_is_bit_identical_to_whole_grid(backend):
         assert np.array_equal(a, b)
 
 
+@pytest.fixture(params=[0, 2], ids=["auto", "no-cell-kernel"])
+def knob4(request, backend):
+    """Narrow single grids take the one-thread-per-cell update by default; knob 4 = 2 keeps them on the tiled /
+    column-march update kernels (what wide grids and ensembles run), so both are covered on bands."""
+    from gcmiipy_b200 import _lib
+    _lib.lib().gcm_tuning_knob(4, request.param)
+    yield request.param
+    _lib.lib().gcm_tuning_knob(4, 0)
+
+
 @pytest.mark.parametrize("H,W,worlds", [(24, 36, (2, 3, 4)), (18, 32, (2, 3))])
-def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, H, W, worlds):
+def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, knob4, H, W, worlds):
     """Bands stepped one by one in this process with halo rows taken from the whole-grid state.  W = 32 with 9 and 6
     owned rows: partial tiles of the shared-memory-tiled update kernel at the band's southern edge."""
     geom, s = _case(H=H, W=W)
@@ -58,7 +68,7 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, 
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
-def test_band_with_tiled_update_is_bit_identical(backend):
+def test_band_with_tiled_update_is_bit_identical(backend, knob4):
     """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too."""
     geom, s = _case(H=16, W=32)
     whole = dynamics.Stepper(geom, *s)
@@ -70,7 +80,7 @@ def test_band_with_tiled_update_is_bit_identical(backend):
 
 
 @pytest.mark.parametrize("wide", [True, False])
-def test_native_band_loop_single_rank(backend, wide):
+def test_native_band_loop_single_rank(backend, knob4, wide):
     """gcm_band_matsuno_step (csrc/comm.cu): the C++ loop with the ring closed on the band itself.  wide: 2 + 4 halo
     rows, one exchange per step, predictor recomputed on the rows across the band edges; else 1 + 2 halo rows, two
     exchanges, and on the GPU the overlapped schedule (side stream, interior rows first, two-segment launches)."""

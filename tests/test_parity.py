@@ -259,9 +259,21 @@ def test_run25_golden(backend, name, H, W, L):
 
 @pytest.mark.parametrize("H,W,L,dt,n", [(10, 64, 9, 300.0, 3), (7, 32, 3, 300.0, 2), (12, 96, 9, 200.0, 2),
                                         (2, 32, 3, 100.0, 2), (3, 32, 9, 100.0, 1)])
-def test_run25_tiled_update_vs_oracle(backend, H, W, L, dt, n):
+@pytest.mark.parametrize("knob4", [2, 0])
+def test_run25_tiled_update_vs_oracle(backend, H, W, L, dt, n, knob4):
     """Widths that are multiples of 32 take the shared-memory-tiled update kernel (asynchronous copies, halo ring with
-    periodic wrap); H not a multiple of the tile height leaves a partial tile."""
+    periodic wrap); H not a multiple of the tile height leaves a partial tile.  Single grids this narrow would take the
+    one-thread-per-cell update by default (knob4 = 0); knob 4 = 2 keeps them on the tiled kernel, which is what the
+    wide grids (1440) and the ensembles run."""
+    from gcmiipy_b200 import _lib
+    _lib.lib().gcm_tuning_knob(4, knob4)
+    try:
+        _run25_vs_oracle(H, W, L, dt, n)
+    finally:
+        _lib.lib().gcm_tuning_knob(4, 0)
+
+
+def _run25_vs_oracle(H, W, L, dt, n):
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
     og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
     hm = 50.0 * np.random.default_rng(H).random((H, W))
