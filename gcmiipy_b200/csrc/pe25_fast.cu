@@ -914,11 +914,12 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const PfMut mo{out->p, out->u, out->v, out->t, out->q};
   const bool ptop0 = d.ptop == 0.0;
   const unsigned magicW = gcm_magic((unsigned)W);
-  // Update kernel.  Narrow single grids (W x members <= 512: the 72 x 46, 288 x 180 and 36 x 24 grids, not their
-  // ensembles) take one thread per cell: too few columns to fill the chip with a thread per column or a CTA per tile.
+  // Update kernel.  Narrow single grids (W x members <= 128: the 72 x 46 and 36 x 24 grids, not their ensembles)
+  // take one thread per cell: too few columns to fill the chip with a thread per column or a CTA per tile (r03g:
+  // 72 x 46 0.055 -> 0.029 ms/step).  Already at 288 x 180 the tiled kernel wins again (r03i: 0.071 vs 0.076).
   // The choice depends on the width and the member count only, never on the rows of the launch, so a latitude band
   // takes the same kernel as the whole grid (bit-identical decomposition).
-  const bool cells = ((size_t)W * nbatch <= 512 || g_gcm_knob[4] == 3) && (size_t)(segU.n1 + segU.n2) * W < (1u << 22) &&
+  const bool cells = ((size_t)W * nbatch <= 128 || g_gcm_knob[4] == 3) && (size_t)(segU.n1 + segU.n2) * W < (1u << 22) &&
                      g_gcm_knob[4] != 2;
   const bool tiled = !cells && W % PFT_TI == 0 && g_gcm_knob[4] != 1;  // update on staged shared-memory tiles
   if (nrowsR > 0) {
