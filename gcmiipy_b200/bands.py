@@ -178,6 +178,26 @@ class BandStepper:
         lo, hi = self.dg.row_lo, self.dg.row_hi
         return tuple(x.narrow(x.dim() - 2, lo, hi - lo) for x in self.cur)
 
+    def diagnostics(self):
+        """The STATS diagnostics of no_limits_2_5d.full_timestep (no_limits_2_5d.py:85-88) over the whole grid:
+        {"u_max", "u_min", "v_max", "v_min", "nonfinite"} -- `gcm_diag_minmax` on the rows this rank owns, then one
+        all-reduce of a few doubles over the ring (MAX of (max, -min), SUM of the non-finite counts)."""
+        _, u, v, _, _ = self.owned()
+        loc = []
+        for x in (u, v):
+            x = x.contiguous()
+            out = _host.empty((3,))
+            _lib.check(_lib.lib().gcm_diag_minmax(_host.ptr(x), x.numel(), _host.ptr(out), _lib.stream()),
+                       "gcm_diag_minmax")
+            loc.append(out)
+        ext = torch.stack([loc[0][1], -loc[0][0], loc[1][1], -loc[1][0]])
+        bad = torch.stack([loc[0][2], loc[1][2]])
+        if self.world > 1:
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(bad, op=dist.ReduceOp.SUM, group=self.group)
+        e, b = ext.cpu().tolist(), bad.cpu().tolist()
+        return {"u_max": e[0], "u_min": -e[1], "v_max": e[2], "v_min": -e[3], "nonfinite": int(b[0] + b[1])}
+
     def gather(self):
         """The full fields on every rank (all_gather of the owned rows), in the caller's array family."""
         parts = [x.contiguous() for x in self.owned()]

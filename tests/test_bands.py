@@ -68,6 +68,16 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, 
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
+def test_band_diagnostics_single_rank(backend):
+    geom, s = _case()
+    band = bands.BandStepper(geom, *s, rank=0, world=1)
+    band.step(450.0, 2)
+    full = band.gather()
+    d = band.diagnostics()
+    assert d == {"u_max": np.max(full[1]), "u_min": np.min(full[1]), "v_max": np.max(full[2]),
+                 "v_min": np.min(full[2]), "nonfinite": 0}
+
+
 def test_band_with_tiled_update_is_bit_identical(backend, knob4):
     """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too."""
     geom, s = _case(H=16, W=32)
@@ -147,6 +157,10 @@ def _worker(rank, world, port, nsteps, out):
     assert (b.rank, b.world) == (rank, world)
     b.step(450.0, nsteps)
     full = b.gather()
+    diag = b.diagnostics()                       # all-reduce over the ring: every rank gets the whole-grid values
+    assert diag["nonfinite"] == 0
+    assert diag["u_max"] == np.max(full[1]) and diag["u_min"] == np.min(full[1])
+    assert diag["v_max"] == np.max(full[2]) and diag["v_min"] == np.min(full[2])
     if rank == 0:
         np.savez(out, *full)
     dist.barrier()
