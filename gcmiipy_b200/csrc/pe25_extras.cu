@@ -50,6 +50,7 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
                     const double* __restrict__ spu, const double* __restrict__ pn, double* __restrict__ u,
                     double* __restrict__ v, double* __restrict__ t, double* __restrict__ q, double dt, int rj,
                     size_t b2, size_t b3) {
+  gcm_pdl_wait();  // launched with the programmatic-stream-serialization attribute right behind the update kernel
   const int H = g.H, W = g.W, L = g.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W) return;
@@ -182,7 +183,7 @@ int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_st
   const unsigned gy = (unsigned)((nrows + rj - 1) / rj);
   {
     GcmProfScope ps(GCM_K_EXTRAS, stream);
-    GCM_LAUNCH(pe25x_extras_kernel, dim3(gx, gy, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p, star->u, star->v,
+    GCM_LAUNCH_DEP(pe25x_extras_kernel, dim3(gx, gy, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p, star->u, star->v,
                star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, rj, (size_t)H * W,
                (size_t)L * H * W);
   }
