@@ -84,10 +84,14 @@ def full_timestep(p, u, v, t, q, g, dt, utc, geom):
     return p, u, v, t, q, g
 
 
-def run_model(height, width, layers, dt, timesteps, callback, stats=True):
+def run_model(height, width, layers, dt, timesteps, callback, stats=True, options=None):
     """no_limits_2_5d.py:220-236.  The state stays resident on the device for the whole run; it is
-    downloaded only for `callback` and at the end.  stats=False skips the per-step diagnostics."""
+    downloaded only for `callback` and at the end.  stats=False skips the per-step diagnostics; options = kwargs of
+    `dynamics.configure` (Coriolis, viscosity, flux-limited tracers; default: the reference's step)."""
     geom = gen_geometry(height, width, layers, sig_func=geometry.manabe_sig)
+    if options:
+        from .dynamics import configure
+        configure(geom, **options)
     p, u, v, t, q, g = gen_initial_conditions(geom)
     v[0, 0, 0] = 0.1
     u *= 0

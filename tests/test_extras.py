@@ -300,3 +300,50 @@ def test_options_full_size_properties():
     st.step(dt, 20)
     torch.cuda.synchronize()
     assert all(np.isfinite(a).all() for a in st.download())
+
+
+@pytest.mark.parametrize("H,W,L,ptop", [(1, 16, 17, 0.0), (2, 8, 3, 0.0), (3, 2, 3, 0.0), (5, 6, 9, 1000.0), (8, 8, 3, 0.0)])
+def test_options_on_degenerate_grids_vs_oracle(backend, H, W, L, ptop):
+    """One and two rows (every j neighbour is the row itself / the other row), two columns (i +- 2 wraps onto the
+    cell), 17 layers (the general 4-kernel path), ptop != 0, a mountain: the periodic wraps of the limiter's
+    five-point reach and of the Coriolis / viscosity stencils against the numpy rolls of the oracle."""
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    geom.ptop = og.ptop = ptop
+    hm = np.zeros((H, W)); hm[0, W // 2] = 800.0
+    geom.heightmap = hm; og.heightmap = hm.copy()
+    s = O.synthetic_state(og, seed=H * 100 + W)
+    rng = np.random.default_rng(H + W)
+    s = s[:4] + (s[4] * (1 + 0.3 * rng.random(s[4].shape)),)
+    kw = dict(coriolis=True, viscosity=5.0e4, limit_q=True, limit_t=True)
+    dynamics.configure(geom, **kw)
+    dt = 100.0
+    ref = O.matsuno_timestep_ext(*s, dt, og, _oopt(kw))
+    assert all(np.isfinite(a).all() for a in ref)
+    check_state(dynamics.matsuno_timestep(*s, dt, geom), ref, TOL_CALL)
+
+
+def test_coriolis_on_a_square_geometry_is_zero(backend):
+    """gen_square_geometry has no latitudes (geometry.py:174: lat = 0): the Coriolis parameters are zero and the
+    option changes nothing but round-off-free zeros."""
+    geom = geometry.gen_square_geometry(6, 10, 3, 300e3, 250e3, sig_func=geometry.manabe_sig)
+    og = O.gen_square_geometry(6, 10, 3, 300e3, 250e3, sig_func=O.manabe_sig)
+    s = O.synthetic_state(og, seed=5)
+    base = dynamics.matsuno_timestep(*s, 200.0, geom)
+    dynamics.configure(geom, coriolis=True)
+    cor = dynamics.matsuno_timestep(*s, 200.0, geom)
+    for a, b in zip(base, cor):
+        assert np.array_equal(a, b)
+    check_state(cor, O.matsuno_timestep_ext(*s, 200.0, og, O.StepOptions(coriolis=True)), TOL_CALL)
+
+
+def test_run_model_with_options(backend):
+    """no_limits_2_5d.run_model (no_limits_2_5d.py:220-236) with the opt-in terms: same ICs, same loop."""
+    from gcmiipy_b200 import no_limits_2_5d as nl
+    kw = dict(coriolis=True, limit_q=True, viscosity=1.0e5)
+    p, u, v, t, q, g, geom = nl.run_model(8, 8, 3, 450.0, 4, None, stats=False, options=kw)
+    og = O.gen_geometry(8, 8, 3, sig_func=O.manabe_sig)
+    ref = O.run_model_ic(og)
+    for _ in range(4):
+        ref = O.matsuno_timestep_ext(*ref, 450.0, og, _oopt(kw))
+    check_state((p, u, v, t, q), ref, TOL_RUN)
