@@ -57,9 +57,18 @@ class BandStepper:
         full0 = _host.dev(p)
         if native is None:
             native = full0.is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
+        # opt-in terms (dynamics.configure): the limiter reaches j - 2 ... j + 2, so two halo rows on either side and the
+        # two-exchange schedule below (exchange + gcm_pe25_half_step); the native loop keeps the reference's widths
+        opts = getattr(geom, "step_options", None)
+        self.options_on = opts is not None and opts.any()
+        if self.options_on:
+            native = False
         # native ring: twice the halo (2 north, 4 south) buys ONE exchange per step (see csrc/comm.cu)
         wide = bool(native) and wide_halo and self.owned_rows >= 2 * HALO_S and _wide_ok(geom)
         self.halo_n, self.halo_s = (2 * HALO_N, 2 * HALO_S) if wide else (HALO_N, HALO_S)
+        if self.options_on:
+            self.halo_n, self.halo_s = 2, 2
+        self.xn, self.xs = (self.halo_n, self.halo_s) if self.options_on else (HALO_N, HALO_S)   # rows per exchange
         self.dg = device_geom(geom, band=(self.j0, self.j1, self.halo_n, self.halo_s))
         self.family = _host.Family(p, u, v, t, q)
         rows = torch.arange(self.j0 - self.halo_n, self.j1 + self.halo_s) % H
@@ -70,8 +79,8 @@ class BandStepper:
         self.star = [torch.empty_like(x) for x in self.cur]
         self.nxt = [torch.empty_like(x) for x in self.cur]
         lib = _lib.lib()
-        n_s = lib.gcm_halo_buffer_doubles(self.dg.handle, HALO_S)
-        n_n = lib.gcm_halo_buffer_doubles(self.dg.handle, HALO_N)
+        n_s = lib.gcm_halo_buffer_doubles(self.dg.handle, self.xs)
+        n_n = lib.gcm_halo_buffer_doubles(self.dg.handle, self.xn)
         mk = lambda n: torch.empty(n, dtype=torch.float64, device=_lib.device())
         self.send_north, self.recv_south = mk(n_s), mk(n_s)      # my first 2 owned rows -> north neighbour's south halo
         self.send_south, self.recv_north = mk(n_n), mk(n_n)      # my last owned row     -> south neighbour's north halo
@@ -109,15 +118,16 @@ class BandStepper:
         lib, dg, s = _lib.lib(), self.dg, _struct(state)
         lo, hi = dg.row_lo, dg.row_hi
         stream = _lib.stream()
+        xn, xs = self.xn, self.xs
         if self.world == 1:
-            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), lo, ctypes.byref(s), hi, HALO_S, stream),
+            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), lo, ctypes.byref(s), hi, xs, stream),
                        "gcm_halo_copy_rows")
-            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), hi - HALO_N, ctypes.byref(s), lo - HALO_N,
-                                              HALO_N, stream), "gcm_halo_copy_rows")
+            _lib.check(lib.gcm_halo_copy_rows(dg.handle, ctypes.byref(s), hi - xn, ctypes.byref(s), lo - xn,
+                                              xn, stream), "gcm_halo_copy_rows")
             return
-        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), lo, HALO_S, _host.ptr(self.send_north), stream),
+        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), lo, xs, _host.ptr(self.send_north), stream),
                    "gcm_halo_pack")
-        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), hi - HALO_N, HALO_N, _host.ptr(self.send_south), stream),
+        _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), hi - xn, xn, _host.ptr(self.send_south), stream),
                    "gcm_halo_pack")
         ops = [dist.P2POp(dist.isend, self.send_north, self.north, self.group, tag=1),
                dist.P2POp(dist.isend, self.send_south, self.south, self.group, tag=2),
@@ -125,9 +135,9 @@ class BandStepper:
                dist.P2POp(dist.irecv, self.recv_north, self.north, self.group, tag=2)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), hi, HALO_S, _host.ptr(self.recv_south), stream),
+        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), hi, xs, _host.ptr(self.recv_south), stream),
                    "gcm_halo_unpack")
-        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), lo - HALO_N, HALO_N, _host.ptr(self.recv_north),
+        _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), lo - xn, xn, _host.ptr(self.recv_north),
                                        stream), "gcm_halo_unpack")
 
     # ---- stepping -------------------------------------------------------------------------------------

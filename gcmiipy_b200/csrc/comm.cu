@@ -255,6 +255,7 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
   GCM_REQUIRE(g && c && cur && star && nxt && ws, GCM_ENULL);
   GCM_REQUIRE(nsteps > 0, GCM_ESHAPE);
   GCM_REQUIRE(!g->d.wrap_j, GCM_EUNSUP);
+  GCM_REQUIRE(!gcm_extras_on(g), GCM_EUNSUP);  // the opt-in terms reach j - 2 ... j + 2: stepped by bands.BandStepper
   const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi, lo = g->d.row_lo, n = g->d.row_hi - g->d.row_lo;
   const bool wide = hn == 2 * GCM_HALO_N && hs == 2 * GCM_HALO_S;
   GCM_REQUIRE(wide || (hn == GCM_HALO_N && hs == GCM_HALO_S), GCM_ESHAPE);

@@ -270,6 +270,10 @@ int gcm_fft_make_plan(int n, GcmFftPlan* plan);
 static inline bool gcm_extras_on(const gcm_geom* g) {
   return g->x.coriolis || g->x.limit_q || g->x.limit_t || g->x.nu != 0.0;
 }
+// rows j - 2 ... j + 2 of every owned row are stored: whole grid, or a band with two halo rows on either side
+static inline bool gcm_extras_rows_ok(const gcm_geom* g) {
+  return g->d.wrap_j || (g->d.row_lo >= 2 && g->d.H - g->d.row_hi >= 2);
+}
 // pe25_extras.cu: adds the opt-in terms to the freshly written `out` of a half step (whole-grid geometry)
-int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu, double dt,
-                          int nbatch, void* stream);
+int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu,
+                          const double* pn, double dt, int nbatch, void* stream);

@@ -80,6 +80,7 @@ extern "C" int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_
                                           double dt, int nblocks, void* ws, size_t ws_bytes, void* stream) {
   GCM_REQUIRE(g && h_in && h_out && d_cur && d_star && d_nxt && ws, GCM_ENULL);
   GCM_REQUIRE(g->d.wrap_j, GCM_EUNSUP);
+  GCM_REQUIRE(!gcm_extras_on(g), GCM_EUNSUP);  // the latitude blocks carry the reference's halo widths
   const int H = g->d.H;
   cudaStream_t main = (cudaStream_t)stream;
   // automatic: pipeline only when the copies dwarf the per-block launch overhead (about 2 M cells and up)

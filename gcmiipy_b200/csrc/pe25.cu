@@ -415,10 +415,10 @@ static int pe25_half_step_core(const gcm_geom* g, const gcm_state* base, const g
 static int pe25_half_step_impl(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,
                                double dt, int nbatch, const Pe25Work& w, void* stream) {
   if (!gcm_extras_on(g)) return pe25_half_step_core(g, base, star, out, dt, nbatch, w, stream);
-  GCM_REQUIRE(g->d.wrap_j, GCM_EUNSUP);
+  GCM_REQUIRE(gcm_extras_rows_ok(g), GCM_EUNSUP);
   int st = pe25_half_step_core(g, base, star, out, dt, nbatch, w, stream);
   if (st) return st;
-  return gcm_pe25_extras_apply(g, star, out, w.spu, dt, nbatch, stream);
+  return gcm_pe25_extras_apply(g, star, out, w.spu, w.pn, dt, nbatch, stream);
 }
 
 static int pe25_half_step_core(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,

@@ -16,7 +16,8 @@
 // Divides are reciprocals (metric tables, gcm_rcp): fp64 division is a ~30-instruction software sequence.  The march is
 // bound by load latency (ncu r03c: long-scoreboard 12.9 cycles per issue), so each row asks the next row's lines into L1.
 // The default path (no option set) launches nothing from this file and stays bit-identical to the reference step.
-// Whole-grid geometries only (rows periodic in j): the limiter reads j - 2 ... j + 2.
+// The limiter reads j - 2 ... j + 2: whole-grid geometries (rows periodic in j), or latitude bands that store at least
+// two halo rows on either side (gcm_pe25_half_step only; the row-segment schedules keep the reference's halo widths).
 #include <math.h>
 
 #include "gcm_common.h"
@@ -35,6 +36,11 @@ __device__ __forceinline__ double px_edge_excess(double qm, double q0, double q1
   return flux > 0 ? 0.5 * (lim - b) : 0.5 * (b - lim);   // (q0 + lim/2) - (q0+q1)/2   |   (q1 - lim/2) - (q0+q1)/2
 }
 
+// A correction flux is one rounded product: the flux through an edge is evaluated by the cell north of it (carried in
+// a register) or at the start of a march, and both must give the same bits whatever the march length and the band
+// decomposition -- no FMA contraction into the divergence that follows.
+__device__ __forceinline__ double px_mul(double a, double b) { return __dmul_rn(a, b); }
+
 // column i of one tracer while the thread marches south: the five rows j-2 ... j+2 and the correction flux through
 // the north edge of row j (the south edge of the row before)
 struct PxColumn {
@@ -51,7 +57,7 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
                     double* __restrict__ v, double* __restrict__ t, double* __restrict__ q, double dt, int rj,
                     size_t b2, size_t b3) {
   gcm_pdl_wait();  // launched with the programmatic-stream-serialization attribute right behind the update kernel
-  const int H = g.H, W = g.W, L = g.L;
+  const int H = g.H, W = g.W, L = g.L, wrap = g.wrap_j;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W) return;
   const int j0 = g.row_lo + blockIdx.y * rj;
@@ -71,7 +77,7 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
   const bool trc_on[2] = {x.limit_q != 0, x.limit_t != 0};
 
   // state carried from row to row (row offsets r* = row * W)
-  int jm1 = gcm_row(j0, -1, H, 1), jp1 = gcm_row(j0, 1, H, 1);
+  int jm1 = gcm_row(j0, -1, H, wrap), jp1 = gcm_row(j0, 1, H, wrap);
   int rn = jm1 * W, rc = j0 * W, rs = jp1 * W;
   double sp_n = sp[rn + i], sp_c = sp[rc + i], sp_s = sp[rs + i];
   double spv_n = sv[rn + i] * ((sp_n + sp_c) / 2);  // star mass flux in j (dynamics.py:191) through the north edge
@@ -80,14 +86,14 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
   for (int f = 0; f < 2; ++f)
     if (trc_on[f]) {
       const double* __restrict__ a = trc_in[f];
-      const int rn2 = gcm_row(jm1, -1, H, 1) * W, rs2 = gcm_row(jp1, 1, H, 1) * W;
+      const int rn2 = gcm_row(jm1, -1, H, wrap) * W, rs2 = gcm_row(jp1, 1, H, wrap) * W;
       col[f].m2 = a[rn2 + i]; col[f].m1 = a[rn + i]; col[f].c = a[rc + i];
       col[f].p1 = a[rs + i]; col[f].p2 = a[rs2 + i];
-      col[f].gj_n = spv_n * px_edge_excess(col[f].m2, col[f].m1, col[f].c, col[f].p1, spv_n);
+      col[f].gj_n = px_mul(spv_n, px_edge_excess(col[f].m2, col[f].m1, col[f].c, col[f].p1, spv_n));
     }
 
   for (int j = j0; j < j1; ++j) {
-    const int jp2 = gcm_row(jp1, 1, H, 1);
+    const int jp2 = gcm_row(jp1, 1, H, wrap);
     const int rs2 = jp2 * W;
     const int c = rc + i;
     if (j + 1 < j1) {  // the next row's lines into L1 while this row is computed (the march is load-latency bound)
@@ -104,7 +110,7 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
       for (int f = 0; f < 2; ++f)
         if (trc_on[f]) {
           gcm_prefetch_l1(trc_out[f] + cn);
-          gcm_prefetch_l1(trc_in[f] + gcm_row(jp2, 1, H, 1) * W + i);
+          gcm_prefetch_l1(trc_in[f] + gcm_row(jp2, 1, H, wrap) * W + i);
         }
     }
     const double rdxj = g.rdx_j[j];
@@ -144,7 +150,7 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
     if (trc_on[0] || trc_on[1]) {
       const double pu_c = spu[c], pu_w = spu[rc + im1];
       const double rpn = gcm_rcp(pn_c);
-      const int rs3 = gcm_row(jp2, 1, H, 1) * W;
+      const int rs3 = gcm_row(jp2, 1, H, wrap) * W;
 #pragma unroll
       for (int f = 0; f < 2; ++f)
         if (trc_on[f]) {
@@ -152,9 +158,9 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
           PxColumn& cl = col[f];
           const double fw1 = a[rc + im1], fw2 = a[rc + im2];
           const double fe1 = a[rc + ip1], fe2 = a[rc + ip2];
-          const double gi_c = pu_c * px_edge_excess(fw1, cl.c, fe1, fe2, pu_c);          // edge i + 1/2
-          const double gi_w = pu_w * px_edge_excess(fw2, fw1, cl.c, fe1, pu_w);          // edge i - 1/2
-          const double gj_c = spv_c * px_edge_excess(cl.m1, cl.c, cl.p1, cl.p2, spv_c);  // edge j + 1/2
+          const double gi_c = px_mul(pu_c, px_edge_excess(fw1, cl.c, fe1, fe2, pu_c));          // edge i + 1/2
+          const double gi_w = px_mul(pu_w, px_edge_excess(fw2, fw1, cl.c, fe1, pu_w));          // edge i - 1/2
+          const double gj_c = px_mul(spv_c, px_edge_excess(cl.m1, cl.c, cl.p1, cl.p2, spv_c));  // edge j + 1/2
           const double div = (gi_c - gi_w) * rdxj + (gj_c - cl.gj_n) * rdy;
           trc_out[f][c] -= (div * dt) * rpn;
           cl.m2 = cl.m1; cl.m1 = cl.c; cl.c = cl.p1; cl.p1 = cl.p2;
@@ -170,10 +176,12 @@ pe25x_extras_kernel(GcmGeomDev g, GcmExtras x, const double* __restrict__ sp, co
   }
 }
 
-int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu, double dt,
-                          int nbatch, void* stream) {
+// pn: p_n of the half step on the owned rows AND the first row to their south (the step's work field: `out->p` of a
+// band does not hold the halo row that jph(p_n) reaches)
+int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_state* out, const double* spu,
+                          const double* pn, double dt, int nbatch, void* stream) {
   const GcmGeomDev& d = g->d;
-  GCM_REQUIRE(d.wrap_j, GCM_EUNSUP);
+  GCM_REQUIRE(gcm_extras_rows_ok(g), GCM_EUNSUP);
   GCM_REQUIRE((double)d.H * d.W < 2147483648.0, GCM_EUNSUP);  // 32-bit offsets within a layer
   const int H = d.H, W = d.W, L = d.L, nrows = d.row_hi - d.row_lo;
   const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
@@ -184,7 +192,7 @@ int gcm_pe25_extras_apply(const gcm_geom* g, const gcm_state* star, const gcm_st
   {
     GcmProfScope ps(GCM_K_EXTRAS, stream);
     GCM_LAUNCH_DEP(pe25x_extras_kernel, dim3(gx, gy, L * nbatch), dim3(tc), 0, stream, d, g->x, star->p, star->u, star->v,
-               star->t, star->q, spu, out->p, out->u, out->v, out->t, out->q, dt, rj, (size_t)H * W,
+               star->t, star->q, spu, pn, out->u, out->v, out->t, out->q, dt, rj, (size_t)H * W,
                (size_t)L * H * W);
   }
   GCM_CHECK_LAUNCH();
@@ -202,7 +210,7 @@ extern "C" int gcm_pe25_set_options(gcm_geom* g, const gcm_pe25_options* opt) {
     x.nu = opt->nu;
   }
   const bool any = x.coriolis || x.limit_q || x.limit_t || x.nu != 0.0;
-  GCM_REQUIRE(!any || g->d.wrap_j, GCM_EUNSUP);  // latitude bands carry halos for the reference's stencil only
+  GCM_REQUIRE(!any || gcm_extras_rows_ok(g), GCM_EUNSUP);  // a band needs two halo rows on either side
   if (x.coriolis) {
     GCM_REQUIRE(opt->h_cor_u && opt->h_cor_v, GCM_ENULL);
     const size_t n = (size_t)g->d.H;

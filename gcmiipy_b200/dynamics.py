@@ -42,10 +42,11 @@ def configure(geom, coriolis=False, viscosity=0.0, limit_q=False, limit_t=False)
     opt = StepOptions(coriolis, viscosity, limit_q, limit_t)
     geom.step_options = opt
     for dg in list(geom._dev.values()):
-        if dg.wrap_j:
+        if dg.wrap_j or (dg.row_lo >= 2 and dg.H - dg.row_hi >= 2):
             _push_options(geom, dg)
         elif opt.any():
-            raise ValueError("the opt-in terms are not available on latitude bands")
+            raise ValueError("a latitude band of this geometry is already resident with fewer than two halo rows: "
+                             "configure() before creating the BandStepper")
     return opt
 
 

@@ -144,6 +144,8 @@ def _push_options(geom, dg):
             dg.options_on = False
         return
     cu, cv = coriolis_parameters(geom) if opt.coriolis else (None, None)
+    if cu is not None and dg.rows is not None:      # a latitude band: the values of the rows it stores
+        cu, cv = np.ascontiguousarray(cu[dg.rows]), np.ascontiguousarray(cv[dg.rows])
     o = _abi.Pe25Options(int(opt.coriolis), int(opt.limit_q), int(opt.limit_t), float(opt.viscosity),
                          _host.hptr(cu), _host.hptr(cv))
     _lib.check(_lib.lib().gcm_pe25_set_options(dg.handle, ctypes.byref(o)), "gcm_pe25_set_options")
@@ -157,6 +159,7 @@ class DeviceGeom:
         self.handle, self.H, self.W, self.L = handle, H, W, L
         self.row_lo, self.row_hi, self.wrap_j = row_lo, row_hi, wrap_j
         self.options_on = False
+        self.rows = None              # global row of every stored row (latitude bands only)
 
     def __del__(self):
         try:
@@ -187,8 +190,10 @@ def device_geom(geom, band=None):
     key = _fingerprint(geom, band)
     if key in geom._dev:
         return geom._dev[key]
-    if band is not None and getattr(geom, "step_options", None) is not None and geom.step_options.any():
-        raise ValueError("the opt-in terms (dynamics.configure) are not available on latitude bands")
+    if band is not None and getattr(geom, "step_options", None) is not None and geom.step_options.any() and (
+            band[2] < 2 or band[3] < 2):
+        raise ValueError("the opt-in terms (dynamics.configure) reach rows j - 2 ... j + 2: a latitude band needs two "
+                         "halo rows on either side")
     H, W, L = geom.height, geom.width, geom.layers
     sig, dsig = _vec(geom.sig, L), _vec(geom.dsig, L)
     sigb, sigt = _vec(geom.sigb, L), _vec(geom.sigt, L)
@@ -221,4 +226,8 @@ def device_geom(geom, band=None):
     geom._dev[key] = obj
     if band is None:
         _push_options(geom, obj)
+    else:
+        obj.rows = rows
+        if obj.row_lo >= 2 and Hs - obj.row_hi >= 2:
+            _push_options(geom, obj)
     return obj

@@ -136,8 +136,10 @@ int gcm_tuning_knob(int idx, int value);
  *             upwind + 1/2 van_leer(r) * (downwind - upwind), r = flux_limiter.calc_r seen from the upwind cell
  *             (flux_limiter.py:10-27); phi = 1 is the reference's centred flux, phi = 0 its donor cell.
  * Applied by one extra launch per half step (csrc/pe25_extras.cu) inside gcm_pe25_half_step / gcm_pe25_matsuno_step.
- * Whole-grid geometries only: with any option on, band geometries (wrap_j = 0), gcm_pe25_half_step_rows,
- * gcm_pe25_matsuno_step_host and gcm_band_matsuno_step return GCM_EUNSUP.  opt = NULL switches everything off. */
+ * The limiter reads rows j - 2 ... j + 2: whole-grid geometries, or band geometries that store at least two halo rows
+ * on either side (stepped with gcm_pe25_half_step around halo exchanges; h_cor_u / h_cor_v then hold the values of the
+ * STORED rows).  With any option on, gcm_pe25_half_step_rows, gcm_pe25_matsuno_step_host and gcm_band_matsuno_step
+ * (schedules built on the reference's halo widths) return GCM_EUNSUP.  opt = NULL switches everything off. */
 typedef struct {
   int coriolis;
   int limit_q;

@@ -68,6 +68,23 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, 
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
+@pytest.mark.parametrize("H,W", [(24, 36), (16, 32), (12, 14)])
+def test_single_rank_band_with_options_is_bit_identical(backend, H, W):
+    """The ring closed on the band itself, opt-in terms on (2 + 2 halo rows, two rows per exchange): narrow fused
+    kernels (36), the 32-wide grid, the general 4-kernel path (14 has a factor 7)."""
+    geom, s = _case(H=H, W=W, L=9 if W != 14 else 4)
+    dynamics.configure(geom, **OPTS)
+    whole = dynamics.Stepper(geom, *s)
+    whole.step(300.0, 3)
+    band = bands.BandStepper(geom, *s, rank=0, world=1)
+    assert band.comm is None and (band.halo_n, band.halo_s) == (2, 2)
+    band.step(300.0, 3)
+    for a, b in zip(band.gather(), whole.download()):
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):                      # the reference's halo widths are not enough
+        geometry.device_geom(geom, band=(0, H // 2, 1, 2))
+
+
 def test_band_diagnostics_single_rank(backend):
     geom, s = _case()
     band = bands.BandStepper(geom, *s, rank=0, world=1)
@@ -143,7 +160,10 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, nsteps, out):
+OPTS = dict(coriolis=True, viscosity=1.0e5, limit_q=True, limit_t=True)
+
+
+def _worker(rank, world, port, nsteps, out, options=None):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -153,8 +173,11 @@ def _worker(rank, world, port, nsteps, out):
     _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     geom, s = _case()
+    if options:
+        dynamics.configure(geom, **options)
     b = bands.BandStepper(geom, *s)
     assert (b.rank, b.world) == (rank, world)
+    assert (b.halo_n, b.halo_s) == ((2, 2) if options else (1, 2))
     b.step(450.0, nsteps)
     full = b.gather()
     diag = b.diagnostics()                       # all-reduce over the ring: every rank gets the whole-grid values
@@ -167,16 +190,20 @@ def _worker(rank, world, port, nsteps, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_gloo_ranks_bit_identical_to_single_process(world, tmp_path):
+@pytest.mark.parametrize("world,options", [(2, None), (4, None), (2, OPTS), (3, OPTS)])
+def test_gloo_ranks_bit_identical_to_single_process(world, options, tmp_path):
+    """options: the opt-in terms (Coriolis, viscosity, flux-limited tracers) reach j - 2 ... j + 2, so the bands carry
+    two halo rows on either side and exchange two rows each way; still bit-identical to the whole-grid run."""
     torch.set_num_threads(1)
     out = str(tmp_path / "bands.npz")
-    mp.spawn(_worker, args=(world, _free_port(), 3, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 3, out, options), nprocs=world, join=True)
     from emu import emu_lib
     from gcmiipy_b200 import _lib
     _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
     try:
         geom, s = _case()
+        if options:
+            dynamics.configure(geom, **options)
         whole = dynamics.Stepper(geom, *s)
         whole.step(450.0, 3)
         with np.load(out) as z:

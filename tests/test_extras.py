@@ -213,7 +213,7 @@ def test_options_on_an_ensemble(backend):
 def test_options_are_refused_where_they_do_not_apply(backend):
     geom, og, s = _case(24, 36, 9)
     dynamics.configure(geom, limit_q=True)
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError):                      # a band with the reference's halo widths (1 north, 2 south)
         geometry.device_geom(geom, band=(0, 12, 1, 2))
     dg = geometry.device_geom(geom)
     assert dg.options_on
