@@ -38,7 +38,8 @@ class StepOptions:
 
 def configure(geom, coriolis=False, viscosity=0.0, limit_q=False, limit_t=False):
     """Switch the opt-in terms of `half_timestep` / `matsuno_timestep` / `Stepper.step` on or off for `geom`
-    (whole-grid stepping only).  `configure(geom)` restores the reference's step.  Returns the StepOptions."""
+    (whole grids, and latitude bands created afterwards by `bands.BandStepper`, which then carry two halo rows on
+    either side).  `configure(geom)` restores the reference's step.  Returns the StepOptions."""
     opt = StepOptions(coriolis, viscosity, limit_q, limit_t)
     geom.step_options = opt
     for dg in list(geom._dev.values()):
