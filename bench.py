@@ -211,8 +211,8 @@ def run_native(args):
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
     options = parse_options(args.options)
     if options:
-        assert world == 1, "the opt-in terms run on whole-grid geometries (one GPU)"
-        dynamics.configure(geom, **options)
+        assert world == 1 or members == 1, "the opt-in terms run on whole grids and on latitude bands"
+        dynamics.configure(geom, **options)     # before the BandStepper: its bands then carry 2 + 2 halo rows
         desc += " + opt-in terms"
     _lib.lib().gcm_pe25_select_path(args.path)
     for kv in args.knob:
