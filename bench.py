@@ -322,7 +322,10 @@ def run_native(args):
                     "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
                     "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                     "avg_launch_ms": tot / n, "alg_bytes_per_launch": alg_bytes,
-                    "kernel_share_of_step": tot / sum(t for _, t, _ in kinds),
+                    # the two chains of the row phase run side by side, so the per-kernel times add up to more than
+                    # the step: the share is taken against the measured step, the second figure against that sum
+                    "kernel_share_of_step": (tot / psteps) / (ms / args.steps),
+                    "kernel_share_of_summed_kernel_time": tot / sum(t for _, t, _ in kinds),
                     "kernels_ms_per_step": {nm: t / psteps for nm, t, _ in kinds},
                     "whole_step": {"achieved": value * b_alg(L) / 1e9 / world, "frac": value * b_alg(L) / 1e9 / world / peak}}
 
@@ -334,14 +337,15 @@ def run_native(args):
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample --------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        # bounded sample of about 15 s of single-core work (the numpy port does ~2.3 M cell-updates/s)
         if members > 1:
-            nmem = 64
+            nmem = max(64, int(15 * 2.3e6 // (H * W * L)))
             t = cpu_oracle_step_rate(H, W, L, dt, nmem, options=options)
             cpu = {"value": H * W * L * nmem / t, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "%d member-steps of the %dx%dx%d grid, numpy oracle, 1 thread" % (nmem, W, H, L)}
         else:
             rows = H if H * W * L <= 2_000_000 else 180
-            nst = max(1, int(2_000_000 // (rows * W * L)))
+            nst = max(1, int(15 * 2.3e6 // (rows * W * L)))
             t = cpu_oracle_step_rate(rows, W, L, dt, nst, options=options)
             cpu = {"value": rows * W * L * nst / t, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "%d Matsuno step(s) of a %dx%dx%d grid, numpy oracle, 1 thread" % (nst, W, rows, L)}
