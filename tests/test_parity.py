@@ -469,3 +469,18 @@ def test_cell_update_kernel_matches_column_march(backend, H, W, L):
     for _ in range(3):
         ref = O.matsuno_timestep(*ref, 100.0, og)
     check_state(res[0], ref, TOL_RUN)
+
+
+def test_single_column_like_standard_atmosphere_isa(backend):
+    """standard_atmosphere_isa.py:15-40 feeds a 1 x 1 x 18 column to compute_geopotential: W = 1 skips the polar filter
+    (low_pass.py:58-59), every i / j neighbour is the column itself."""
+    geom = geometry.gen_geometry(1, 1, 18, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(1, 1, 18, sig_func=O.manabe_sig)
+    p = np.full((1, 1), 101325.0)
+    tt = np.linspace(288.0, 216.0, 18).reshape(18, 1, 1)
+    t = O.to_potential_temp(tt, p * og.sig + og.ptop)
+    assert rel(dynamics.compute_geopotential(p, t, geom), O.compute_geopotential(p, t, og)) <= TOL_CALL
+    s = (p, np.zeros((18, 1, 1)), np.zeros((18, 1, 1)), t, np.full((18, 1, 1), 1e-3))
+    got, ref = dynamics.matsuno_timestep(*s, 100.0, geom), O.matsuno_timestep(*s, 100.0, og)
+    for a, b in zip(got, ref):
+        assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(b)), 1.0)
