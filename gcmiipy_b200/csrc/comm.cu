@@ -255,16 +255,23 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
   GCM_REQUIRE(g && c && cur && star && nxt && ws, GCM_ENULL);
   GCM_REQUIRE(nsteps > 0, GCM_ESHAPE);
   GCM_REQUIRE(!g->d.wrap_j, GCM_EUNSUP);
-  GCM_REQUIRE(!gcm_extras_on(g), GCM_EUNSUP);  // the opt-in terms reach j - 2 ... j + 2: stepped by bands.BandStepper
   const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi, lo = g->d.row_lo, n = g->d.row_hi - g->d.row_lo;
-  const bool wide = hn == 2 * GCM_HALO_N && hs == 2 * GCM_HALO_S;
-  GCM_REQUIRE(wide || (hn == GCM_HALO_N && hs == GCM_HALO_S), GCM_ESHAPE);
+  // opt-in terms (gcm_pe25_set_options): they reach j - 2 ... j + 2, so the band carries two halo rows on either side
+  // and both states are exchanged, two rows each way, before a whole-band half step (no row-segment schedule)
+  const bool ext = gcm_extras_on(g);
+  const bool wide = !ext && hn == 2 * GCM_HALO_N && hs == 2 * GCM_HALO_S;
+  GCM_REQUIRE(ext ? (hn == 2 && hs == 2) : (wide || (hn == GCM_HALO_N && hs == GCM_HALO_S)), GCM_ESHAPE);
   GCM_REQUIRE(n >= hs, GCM_ESHAPE);
   cudaStream_t main = (cudaStream_t)stream;
   const gcm_state *a = cur, *b = nxt;
   int st;
   for (int s = 0; s < nsteps; ++s) {
-    if (wide) {
+    if (ext) {
+      if ((st = band_exchange(g, c, a, hn, hs, main))) return st;
+      if ((st = gcm_pe25_half_step(g, a, a, star, dt, 1, ws, ws_bytes, main))) return st;           // dynamics.py:231
+      if ((st = band_exchange(g, c, star, hn, hs, main))) return st;
+      if ((st = gcm_pe25_half_step(g, a, star, b, dt, 1, ws, ws_bytes, main))) return st;           // dynamics.py:234
+    } else if (wide) {
       // ONE exchange per step: with 2 + 4 halo rows of the base state the band computes the predictor also on the
       // three rows its corrector reads across the band edges (the neighbours compute the same values from the same
       // inputs with the same kernels), so the star state needs no exchange.  Halves the latency-bound messages.

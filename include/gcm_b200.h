@@ -138,8 +138,9 @@ int gcm_tuning_knob(int idx, int value);
  * Applied by one extra launch per half step (csrc/pe25_extras.cu) inside gcm_pe25_half_step / gcm_pe25_matsuno_step.
  * The limiter reads rows j - 2 ... j + 2: whole-grid geometries, or band geometries that store at least two halo rows
  * on either side (stepped with gcm_pe25_half_step around halo exchanges; h_cor_u / h_cor_v then hold the values of the
- * STORED rows).  With any option on, gcm_pe25_half_step_rows, gcm_pe25_matsuno_step_host and gcm_band_matsuno_step
- * (schedules built on the reference's halo widths) return GCM_EUNSUP.  opt = NULL switches everything off. */
+ * STORED rows; gcm_band_matsuno_step then exchanges two rows each way before each whole-band half step).  With any
+ * option on, gcm_pe25_half_step_rows and gcm_pe25_matsuno_step_host (schedules built on the reference's halo widths)
+ * return GCM_EUNSUP.  opt = NULL switches everything off. */
 typedef struct {
   int coriolis;
   int limit_q;
@@ -206,7 +207,8 @@ int gcm_comm_unique_id(unsigned char* h_out128);
 int gcm_comm_create(int nranks, int rank, const unsigned char* h_id128, gcm_comm** out);
 int gcm_comm_destroy(gcm_comm* c);
 /* dynamics.matsuno_timestep (dynamics.py:230-237) `nsteps` times on this rank's band (geometry with wrap_j = 0,
- * 1 halo row north, 2 south).  `cur` = the band incl. halo rows (halo content is overwritten), `star` = scratch
+ * 1 halo row north and 2 south, or 2 + 4 for the one-exchange schedule, or 2 + 2 with opt-in terms on).  `cur` =
+ * the band incl. halo rows (halo content is overwritten), `star` = scratch
  * state of the same shape; the newest state ends in `nxt` if nsteps is odd, else in `cur`.  overlap = 1: interior
  * rows run while the halos are in flight.  Bit-identical to the whole-grid step for any number of ranks. */
 int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_state* cur, const gcm_state* star,

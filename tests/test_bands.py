@@ -68,16 +68,18 @@ def test_band_of_every_rank_matches_whole_grid_after_one_half_exchange(backend, 
                 assert np.array_equal(got.cpu().numpy()[..., 1:-2, :], want[..., b.j0:b.j1, :])
 
 
+@pytest.mark.parametrize("native", [False, True])
 @pytest.mark.parametrize("H,W", [(24, 36), (16, 32), (12, 14)])
-def test_single_rank_band_with_options_is_bit_identical(backend, H, W):
+def test_single_rank_band_with_options_is_bit_identical(backend, H, W, native):
     """The ring closed on the band itself, opt-in terms on (2 + 2 halo rows, two rows per exchange): narrow fused
-    kernels (36), the 32-wide grid, the general 4-kernel path (14 has a factor 7)."""
+    kernels (36), the 32-wide grid, the general 4-kernel path (14 has a factor 7); the torch.distributed schedule and
+    the native loop of csrc/comm.cu."""
     geom, s = _case(H=H, W=W, L=9 if W != 14 else 4)
     dynamics.configure(geom, **OPTS)
     whole = dynamics.Stepper(geom, *s)
     whole.step(300.0, 3)
-    band = bands.BandStepper(geom, *s, rank=0, world=1)
-    assert band.comm is None and (band.halo_n, band.halo_s) == (2, 2)
+    band = bands.BandStepper(geom, *s, rank=0, world=1, native=native)
+    assert (band.comm is not None) == native and (band.halo_n, band.halo_s) == (2, 2)
     band.step(300.0, 3)
     for a, b in zip(band.gather(), whole.download()):
         assert np.array_equal(a, b)
