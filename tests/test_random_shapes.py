@@ -56,3 +56,38 @@ def test_random_shape_steps_like_the_oracle(emu, seed):
     for m, r in enumerate(refs):
         assert all(np.isfinite(a).all() for a in r), "unstable case: pick another seed"
         check_state(got if nb == 1 else tuple(a[m] for a in got), r, 1e-11)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_band_split_is_bit_identical(emu, seed):
+    """Every band of a random split, halo rows taken from the whole-grid states: predictor and corrector of the band
+    equal the whole-grid half steps BIT for bit on the rows the band owns (with and without opt-in terms)."""
+    from gcmiipy_b200 import bands
+    rng = np.random.default_rng(5000 + seed)
+    world = int(rng.choice([2, 3, 4]))
+    H = world * int(rng.integers(2, 6))
+    W = int(rng.choice([8, 14, 20, 32, 36, 64]))
+    L = int(rng.choice([3, 4, 9]))
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    geom.heightmap = 150.0 * rng.random((H, W))
+    if rng.random() < 0.6:
+        dynamics.configure(geom, coriolis=bool(rng.random() < 0.5), viscosity=float(rng.choice([0.0, 2.0e4])),
+                           limit_q=True, limit_t=bool(rng.random() < 0.5))
+    s = O.synthetic_state(og, seed=seed)
+    dt = 60.0
+    star = dynamics.half_timestep(*s, *s, dt, geom)
+    new = dynamics.half_timestep(*s, *star, dt, geom)
+    for rank in range(world):
+        b = bands.BandStepper(geom, *s, rank=rank, world=world, native=False)
+        hn, hs = b.halo_n, b.halo_s
+        rows = np.arange(b.j0 - hn, b.j1 + hs) % H
+        own = slice(hn, hn + b.j1 - b.j0)
+        b._half(b.cur, b.cur, b.star, dt)
+        for got, want in zip(b.star, star):
+            assert np.array_equal(got.numpy()[..., own, :], want[..., b.j0:b.j1, :])
+        for dst, src in zip(b.star, star):       # what the exchange of the star state would deliver
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(np.take(src, rows, axis=-2))))
+        b._half(b.cur, b.star, b.nxt, dt)
+        for got, want in zip(b.nxt, new):
+            assert np.array_equal(got.numpy()[..., own, :], want[..., b.j0:b.j1, :])
