@@ -61,6 +61,8 @@ class BandStepper:
         # two-row exchanges per step (native loop and torch.distributed path alike), each before a whole-band half step
         opts = getattr(geom, "step_options", None)
         self.options_on = opts is not None and opts.any()
+        if self.options_on and native is None:
+            native = False      # default: the torch.distributed schedule (run on the B200); native=True asks for the C++ loop
         # native ring: twice the halo (2 north, 4 south) buys ONE exchange per step (see csrc/comm.cu)
         wide = bool(native) and wide_halo and self.owned_rows >= 2 * HALO_S and _wide_ok(geom) and not self.options_on
         self.halo_n, self.halo_s = (2 * HALO_N, 2 * HALO_S) if wide else (HALO_N, HALO_S)
