@@ -55,14 +55,14 @@ class BandStepper:
             raise ValueError("a band needs at least %d rows" % HALO_S)
         self.j0, self.j1 = rank * self.owned_rows, (rank + 1) * self.owned_rows
         full0 = _host.dev(p)
-        if native is None:
-            native = full0.is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
         # opt-in terms (dynamics.configure): the limiter reaches j - 2 ... j + 2, so two halo rows on either side and two
         # two-row exchanges per step (native loop and torch.distributed path alike), each before a whole-band half step
         opts = getattr(geom, "step_options", None)
         self.options_on = opts is not None and opts.any()
         if self.options_on and native is None:
             native = False      # default: the torch.distributed schedule (run on the B200); native=True asks for the C++ loop
+        if native is None:
+            native = full0.is_cuda and (world == 1 or (dist.is_initialized() and dist.get_backend(group) == "nccl"))
         # native ring: twice the halo (2 north, 4 south) buys ONE exchange per step (see csrc/comm.cu)
         wide = bool(native) and wide_halo and self.owned_rows >= 2 * HALO_S and _wide_ok(geom) and not self.options_on
         self.halo_n, self.halo_s = (2 * HALO_N, 2 * HALO_S) if wide else (HALO_N, HALO_S)
