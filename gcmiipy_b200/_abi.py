@@ -33,6 +33,7 @@ SIGNATURES = {
     "gcm_geom_create": (_i, [C.POINTER(GeomDesc), C.POINTER(_geom)]),
     "gcm_geom_destroy": (_i, [_geom]),
     "gcm_pe25_workspace_bytes": (_z, [_geom, _i]),
+    "gcm_pe25_workspace_field": (_z, [_geom, _i, _i]),
     "gcm_pe25_half_step": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, c_stream]),
     "gcm_pe25_matsuno_step": (_i, [_geom, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
     "gcm_pe25_half_step_rows": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -386,6 +386,23 @@ static void pe25_carve(const gcm_geom* g, int nbatch, void* ws, Pe25Work* w) {
   w->tmp.p = d; d += n2;
 }
 
+// element offset (in doubles) of a work field of the half step inside the workspace, member 0: 0 = spu (filtered mass
+// flux, dynamics.py:189), 1 = pgf (filtered pgfu + phiu, :202), 2 = pit, 3 = p_n (:193-194); (size_t)-1 if unknown.
+// Lets the parity tests compare the polar-filter outputs of the fused kernels with the oracle directly.
+extern "C" size_t gcm_pe25_workspace_field(const gcm_geom* g, int nbatch, int which) {
+  if (!g || nbatch <= 0) return (size_t)-1;
+  Pe25Work w;
+  double* base = reinterpret_cast<double*>((uintptr_t)4096);  // carve relative to a dummy origin
+  pe25_carve(g, nbatch, base, &w);
+  switch (which) {
+    case 0: return (size_t)(w.spu - base);
+    case 1: return (size_t)(w.pgf - base);
+    case 2: return (size_t)(w.pit - base);
+    case 3: return (size_t)(w.pn - base);
+    default: return (size_t)-1;
+  }
+}
+
 static int pe25_check_state(const gcm_state* s) {
   GCM_REQUIRE(s && s->p && s->u && s->v && s->t && s->q, GCM_ENULL);
   GCM_REQUIRE(gcm_aligned16(s->p) && gcm_aligned16(s->u) && gcm_aligned16(s->v) && gcm_aligned16(s->t) &&

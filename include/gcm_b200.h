@@ -88,6 +88,11 @@ typedef struct {
 /* bytes of device scratch a half step / Matsuno step needs for `nbatch` members */
 size_t gcm_pe25_workspace_bytes(const gcm_geom* g, int nbatch);
 
+/* element offset (doubles, member 0) of a work field a half step leaves in the workspace: 0 = spu, the filtered mass
+ * flux arakawa_1977(su * iph(sp)) (dynamics.py:187-189); 1 = the filtered pgfu + phiu (:202); 2 = pit (:39-40);
+ * 3 = p_n (:193-194).  (size_t)-1 for an unknown field.  Diagnostic / test access only. */
+size_t gcm_pe25_workspace_field(const gcm_geom* g, int nbatch, int which);
+
 /* dynamics.half_timestep (dynamics.py:183-227): out = base + dt * F(star).  Rows of `star` within
  * [-1, +2] of an owned row (and row +1 of base.p) must be valid (halo rows in band mode). */
 int gcm_pe25_half_step(const gcm_geom* g, const gcm_state* base, const gcm_state* star, const gcm_state* out,

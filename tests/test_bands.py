@@ -74,9 +74,6 @@ def test_single_rank_band_with_options_is_bit_identical(backend, H, W, native):
     """The ring closed on the band itself, opt-in terms on (2 + 2 halo rows, two rows per exchange): narrow fused
     kernels (36), the 32-wide grid, the general 4-kernel path (14 has a factor 7); the torch.distributed schedule and
     the native loop of csrc/comm.cu."""
-    if native and backend == "gpu":
-        pytest.skip("native loop with opt-in terms: validated on the emulator build; the GPU budget of round 1 ran out "
-                    "before it could be run on a B200 (same C calls as the native=False case, which is)")
     geom, s = _case(H=H, W=W, L=9 if W != 14 else 4)
     dynamics.configure(geom, **OPTS)
     whole = dynamics.Stepper(geom, *s)
