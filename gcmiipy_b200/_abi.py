@@ -30,6 +30,8 @@ _i, _d, _z = C.c_int, C.c_double, C.c_size_t
 SIGNATURES = {
     "gcm_version": (_i, []),
     "gcm_status_string": (C.c_char_p, [_i]),
+    "gcm_last_status": (_i, [_i]),
+    "gcm_nonfinite_read": (_i, [C.c_void_p, _i, c_stream]),
     "gcm_geom_create": (_i, [C.POINTER(GeomDesc), C.POINTER(_geom)]),
     "gcm_geom_destroy": (_i, [_geom]),
     "gcm_pe25_workspace_bytes": (_z, [_geom, _i]),

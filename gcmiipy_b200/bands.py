@@ -84,7 +84,10 @@ class BandStepper:
         mk = lambda n: torch.empty(n, dtype=torch.float64, device=_lib.device())
         self.send_north, self.recv_south = mk(n_s), mk(n_s)      # my first 2 owned rows -> north neighbour's south halo
         self.send_south, self.recv_north = mk(n_n), mk(n_n)      # my last owned row     -> south neighbour's north halo
-        self.north, self.south = (rank - 1) % world, (rank + 1) % world
+        self.north, self.south = (rank - 1) % world, (rank + 1) % world       # ring neighbours, ranks within the group
+        # dist.P2POp addresses peers by GLOBAL rank
+        glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        self._north_g, self._south_g = (glob(self.north), glob(self.south)) if world > 1 else (0, 0)
         self.nsteps_done = 0
         self.overlap = True
         self.comm = None
@@ -92,15 +95,22 @@ class BandStepper:
             self._make_comm()
 
     # ---- native ring: gcm_comm (NCCL bound inside the library) + the C++ band loop -------------------------
+    def _share_id(self, make_id):
+        """128 bytes made by `make_id()` on the first rank of the group, shipped to every rank of the group.
+        dist.broadcast takes a GLOBAL source rank: group rank 0 is translated (a sub-group need not contain global 0)."""
+        idbuf = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            make_id(idbuf)
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device=_lib.device())
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(t, src, group=self.group)
+        return (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+
     def _make_comm(self):
         lib = _lib.lib()
         idbuf = (ctypes.c_ubyte * 128)()
         if self.world > 1:
-            if self.rank == 0:
-                _lib.check(lib.gcm_comm_unique_id(idbuf), "gcm_comm_unique_id")
-            t = torch.tensor(list(idbuf), dtype=torch.uint8, device=_lib.device())
-            dist.broadcast(t, 0, group=self.group)           # rank 0 within the group ships the NCCL unique id
-            idbuf = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+            idbuf = self._share_id(lambda b: _lib.check(lib.gcm_comm_unique_id(b), "gcm_comm_unique_id"))
         h = ctypes.c_void_p()
         _lib.check(lib.gcm_comm_create(self.world, self.rank, idbuf, ctypes.byref(h)), "gcm_comm_create")
         self.comm = h
@@ -129,10 +139,10 @@ class BandStepper:
                    "gcm_halo_pack")
         _lib.check(lib.gcm_halo_pack(dg.handle, ctypes.byref(s), hi - xn, xn, _host.ptr(self.send_south), stream),
                    "gcm_halo_pack")
-        ops = [dist.P2POp(dist.isend, self.send_north, self.north, self.group, tag=1),
-               dist.P2POp(dist.isend, self.send_south, self.south, self.group, tag=2),
-               dist.P2POp(dist.irecv, self.recv_south, self.south, self.group, tag=1),
-               dist.P2POp(dist.irecv, self.recv_north, self.north, self.group, tag=2)]
+        ops = [dist.P2POp(dist.isend, self.send_north, self._north_g, self.group, tag=1),
+               dist.P2POp(dist.isend, self.send_south, self._south_g, self.group, tag=2),
+               dist.P2POp(dist.irecv, self.recv_south, self._south_g, self.group, tag=1),
+               dist.P2POp(dist.irecv, self.recv_north, self._north_g, self.group, tag=2)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         _lib.check(lib.gcm_halo_unpack(dg.handle, ctypes.byref(s), hi, xs, _host.ptr(self.recv_south), stream),
@@ -142,7 +152,7 @@ class BandStepper:
 
     # ---- stepping -------------------------------------------------------------------------------------
     def _half(self, base, star, out, dt):
-        ws, need = _workspace(self.dg, 1)
+        ws, need = _workspace(self.dg, 1, self)
         sb, ss, so = _struct(base), _struct(star), _struct(out)
         _lib.check(_lib.lib().gcm_pe25_half_step(self.dg.handle, ctypes.byref(sb), ctypes.byref(ss), ctypes.byref(so),
                                                  float(dt), 1, _host.ptr(ws), need, _lib.stream()), "gcm_pe25_half_step")
@@ -151,7 +161,7 @@ class BandStepper:
         dt = _host.scalar(dt)
         nsteps = int(nsteps)
         if self.comm is not None and nsteps > 0:
-            ws, need = _workspace(self.dg, 1)
+            ws, need = _workspace(self.dg, 1, self)
             sc, ss, sn = _struct(self.cur), _struct(self.star), _struct(self.nxt)
             _lib.check(_lib.lib().gcm_band_matsuno_step(self.dg.handle, self.comm, ctypes.byref(sc), ctypes.byref(ss),
                                                         ctypes.byref(sn), float(dt), nsteps, int(self.overlap),

@@ -74,10 +74,10 @@ static int gcm_nccl_load() {
 #endif
 }
 
-#define GCM_NCCL(call)                             \
-  do {                                             \
-    int r_ = (call);                               \
-    if (r_ != 0) return GCM_ENCCL_BASE + r_;       \
+#define GCM_NCCL(call)                                             \
+  do {                                                             \
+    int r_ = (call);                                               \
+    if (r_ != 0) return gcm_set_status(GCM_ENCCL_BASE + r_);       \
   } while (0)
 
 struct gcm_comm {
@@ -99,6 +99,7 @@ extern "C" int gcm_comm_unique_id(unsigned char* out128) {
   return GCM_OK;
 }
 
+extern "C" int gcm_comm_destroy(gcm_comm* c);
 extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128, gcm_comm** out) {
   GCM_REQUIRE(out, GCM_ENULL);
   GCM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, GCM_ESHAPE);
@@ -113,13 +114,13 @@ extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128,
     gcm_nccl_id id;
     memcpy(id.internal, id128, 128);
     int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
-    if (r != 0) { free(c); return GCM_ENCCL_BASE + r; }
+    if (r != 0) { c->comm = nullptr; gcm_comm_destroy(c); return gcm_set_status(GCM_ENCCL_BASE + r); }
   }
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rint, cudaEventDisableTiming);
-  if (e != cudaSuccess) { free(c); return (int)e; }
+  if (e != cudaSuccess) { gcm_comm_destroy(c); return gcm_set_status((int)e); }  // frees whatever exists so far
 #else
   (void)id128;
   GCM_REQUIRE(nranks == 1, GCM_EUNSUP);

@@ -43,19 +43,21 @@ extern int g_gcm_knob[10];
   gcm_launch_dep(g_gcm_knob[9] != 3, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
-#define GCM_CHECK_LAUNCH()                        \
-  do {                                            \
-    cudaError_t e_ = cudaGetLastError();          \
-    if (e_ != cudaSuccess) return (int)e_;        \
+// geom.cu: remembers the newest non-zero status of the calling thread (gcm_last_status) and returns it unchanged
+int gcm_set_status(int st);
+#define GCM_CHECK_LAUNCH()                                        \
+  do {                                                            \
+    cudaError_t e_ = cudaGetLastError();                          \
+    if (e_ != cudaSuccess) return gcm_set_status((int)e_);        \
   } while (0)
-#define GCM_CUDA(call)                            \
-  do {                                            \
-    cudaError_t e_ = (call);                      \
-    if (e_ != cudaSuccess) return (int)e_;        \
+#define GCM_CUDA(call)                                            \
+  do {                                                            \
+    cudaError_t e_ = (call);                                      \
+    if (e_ != cudaSuccess) return gcm_set_status((int)e_);        \
   } while (0)
-#define GCM_REQUIRE(cond, code) \
-  do {                          \
-    if (!(cond)) return (code); \
+#define GCM_REQUIRE(cond, code)                       \
+  do {                                                \
+    if (!(cond)) return gcm_set_status((code));       \
   } while (0)
 
 // physical constants, SI (reference constants.py:16-48)
@@ -175,6 +177,15 @@ __device__ __forceinline__ void gcm_pdl_trigger() {
 #endif
 }
 
+// Asynchronous "non-finite seen" watch (replaces the caller-side np.isnan(u).any() poll, matsuno_c_grid.py:184-187):
+// one 32-bit counter per device; every step kernel adds 1 per thread that wrote a non-finite value.  Read it with
+// gcm_nonfinite_read (a stream-ordered 4-byte copy: no synchronisation of the caller).
+unsigned int* gcm_nonfinite_word();  // geom.cu: the current device's counter (NULL if it cannot be allocated)
+__device__ __forceinline__ bool gcm_not_finite(double s) { return !(fabs(s) <= 1.7976931348623157e308); }
+__device__ __forceinline__ void gcm_flag_nonfinite(unsigned int* flag, bool bad) {
+  if (bad && flag) atomicAdd(flag, 1u);
+}
+
 // device-resident geometry tables, passed to kernels by value
 struct GcmGeomDev {
   int H, W, L;
@@ -203,6 +214,7 @@ struct GcmGeomDev {
   const double2* tws;   // per-stage twiddles of the in-place transform, contiguous in the butterfly index:
                         //         tws[twoff[s] + (m-1) stride_s + q] = exp(-2 pi i q m / n_s)
   double rdy;           // 1 / dy
+  unsigned int* nonfinite;  // the device's non-finite counter (gcm_nonfinite_word)
   int pdl_early;        // 1 = kernels trigger their dependents at entry (set per launch from tuning knob 9)
   // per-layer tables by value (kernel parameters live in the constant bank: no load instruction) when L <= 16
   double c_sig[GCM_MAXLC], c_dsig[GCM_MAXLC], c_sigb[GCM_MAXLC], c_sigt[GCM_MAXLC], c_rdsig[GCM_MAXLC],

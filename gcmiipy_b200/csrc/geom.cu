@@ -11,6 +11,44 @@
 extern "C" int gcm_version(void) { return 100; }
 int g_gcm_tuning_epoch = 0;
 
+static thread_local int tl_last_status = 0;
+int gcm_set_status(int st) {
+  if (st != 0) tl_last_status = st;
+  return st;
+}
+extern "C" int gcm_last_status(int clear) {
+  const int st = tl_last_status;
+  if (clear) tl_last_status = 0;
+  return st;
+}
+
+// one counter per device, allocated on first use and never freed (4 bytes)
+unsigned int* gcm_nonfinite_word() {
+#ifdef GCM_EMU
+  static unsigned int word = 0;
+  return &word;
+#else
+  static unsigned int* words[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!words[dev]) {
+    unsigned int* w = nullptr;
+    if (cudaMalloc((void**)&w, 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaMemset(w, 0, 256);
+    words[dev] = w;
+  }
+  return words[dev];
+#endif
+}
+
+extern "C" int gcm_nonfinite_read(unsigned int* host_out, int reset, void* stream) {
+  unsigned int* w = gcm_nonfinite_word();
+  GCM_REQUIRE(w, (int)cudaErrorMemoryAllocation);
+  if (host_out) GCM_CUDA(cudaMemcpyAsync(host_out, w, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (reset) GCM_CUDA(cudaMemsetAsync(w, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  return GCM_OK;
+}
+
 extern "C" const char* gcm_status_string(int s) {
   switch (s) {
     case GCM_OK: return "ok";
@@ -239,6 +277,7 @@ extern "C" int gcm_geom_create(const gcm_geom_desc* d, gcm_geom** out) {
   g->d.smmzp = (const double*)(b + o_smmzp);
   g->d.tws = (const double2*)(b + o_tws);
   g->d.rdy = 1.0 / d->dy;
+  g->d.nonfinite = gcm_nonfinite_word();
   for (int k = 0; k < L && k < GCM_MAXLC; ++k) {
     g->d.c_sig[k] = d->h_sig[k];
     g->d.c_dsig[k] = d->h_dsig[k];

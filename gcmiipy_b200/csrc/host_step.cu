@@ -29,8 +29,14 @@ struct GcmHostPipe {
 };
 
 #ifndef GCM_EMU
-static GcmHostPipe* g_pipe = nullptr;  // one per process: a step_host call is stream-ordered on the caller's stream
+// one per device (streams and events belong to the device that was current when they were made); a step_host call is
+// stream-ordered on the caller's stream
+static GcmHostPipe* g_pipes[64] = {nullptr};
 static int host_pipe(GcmHostPipe** out) {
+  int dev = 0;
+  GCM_CUDA(cudaGetDevice(&dev));
+  GCM_REQUIRE(dev >= 0 && dev < 64, GCM_EUNSUP);
+  GcmHostPipe*& g_pipe = g_pipes[dev];
   if (!g_pipe) {
     GcmHostPipe* p = (GcmHostPipe*)calloc(1, sizeof(GcmHostPipe));
     GCM_REQUIRE(p, (int)cudaErrorMemoryAllocation);

@@ -333,18 +333,22 @@ __global__ void pe25_update_kernel(GcmGeomDev g, GcmStateC base, GcmStateC star,
   const double pv = v[c] * ((p_c + p_jp) / 2);
   const double pu_n = pu - (dut + dus + pgf[c]) * dt;
   const double pv_n = pv - (dvt + dvs + phiv + pgv) * dt;
-  out.u[o3 + c] = pu_n / ((pn_c + pn_ip) / 2);
+  const double u_n = pu_n / ((pn_c + pn_ip) / 2);
+  out.u[o3 + c] = u_n;
   double v_n = pv_n / ((pn_c + pn_jp) / 2);
   if (j == g.zero_v_row || j == g.zero_v_row2) v_n *= 0.0;  // dynamics.py:222
   out.v[o3 + c] = v_n;
 
   const double adv_t = gcm_cell_advec_t(g, st, fpu, fpv, k, j, jm, jp, i, im, ip);
   const double ads_t = gcm_cell_advec_sig(g, st, sd_k, sd_kp, k, km, kp, j, i);
-  out.t[o3 + c] = (t[c] * p_c - (adv_t + ads_t) * dt) / pn_c;
+  const double t_n = (t[c] * p_c - (adv_t + ads_t) * dt) / pn_c;
+  out.t[o3 + c] = t_n;
   const double adv_q = gcm_cell_advec_t(g, sq, fpu, fpv, k, j, jm, jp, i, im, ip);
   const double ads_q = gcm_cell_advec_sig(g, sq, sd_k, sd_kp, k, km, kp, j, i);
-  out.q[o3 + c] = (q[c] * p_c - (adv_q + ads_q) * dt) / pn_c;
+  const double q_n = (q[c] * p_c - (adv_q + ads_q) * dt) / pn_c;
+  out.q[o3 + c] = q_n;
   if (k == 0) out.p[o2 + IDX2(j, i)] = pn_c;
+  gcm_flag_nonfinite(g.nonfinite, gcm_not_finite((u_n + v_n) + (t_n + q_n) + pn_c));
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -215,6 +215,11 @@ extern "C" int gcm_pe25_set_options(gcm_geom* g, const gcm_pe25_options* opt) {
     GCM_REQUIRE(opt->h_cor_u && opt->h_cor_v, GCM_ENULL);
     const size_t n = (size_t)g->d.H;
     if (!g->d_cor) GCM_CUDA(cudaMalloc(&g->d_cor, 2 * n * sizeof(double)));
+#ifndef GCM_EMU
+    // steps of this geometry may still be reading the table on non-blocking side streams, which a cudaMemcpy on the
+    // legacy stream does not wait for: drain the device first (configure() is a rare, host-synchronous call)
+    GCM_CUDA(cudaDeviceSynchronize());
+#endif
     GCM_CUDA(cudaMemcpy(g->d_cor, opt->h_cor_u, n * sizeof(double), cudaMemcpyHostToDevice));
     GCM_CUDA(cudaMemcpy((double*)g->d_cor + n, opt->h_cor_v, n * sizeof(double), cudaMemcpyHostToDevice));
     x.cor_u = (const double*)g->d_cor;

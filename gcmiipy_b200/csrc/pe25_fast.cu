@@ -471,6 +471,7 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
     gcm_prefetch_l1(u + ec); gcm_prefetch_l1(v + ec); gcm_prefetch_l1(t + ec); gcm_prefetch_l1(q + ec);
   };
   for (int k = 0; k < pfd && k < L; ++k) prefetch_layer(e_c + k * plane, e_jp + k * plane, e_jm + k * plane);
+  bool bad = gcm_not_finite(pn_c);
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
@@ -507,29 +508,35 @@ pe25f_update_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork 
 
     const double pu_n = u[e_c] * pu_fac - (dut + dus + pgf[e_c]) * dt;   // dynamics.py:206
     const double pv_n = v[e_c] * pv_fac - (dvt + dvs + fv[e_c]) * dt;    // dynamics.py:207
-    ou[e_c] = pu_n * r_pnu;
+    const double u_n = pu_n * r_pnu;
+    ou[e_c] = u_n;
     double v_n = pv_n * r_pnv;
     if (zero_v) v_n *= 0.0;  // dynamics.py:222
     ov[e_c] = v_n;
 
     // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
+    double t_n, q_n;
     {
       const double x_ip = st[e_ip], x_im = st[e_im], x_jp = st[e_jp], x_jm = st[e_jm];
       const double adv = ((pu_c * (t_k + x_ip) - pu_im * (x_im + t_k)) * rdxj +
                           (pv_c * (t_k + x_jp) - pv_jm * (x_jm + t_k)) * rdy) * 0.5;
-      ot[e_c] = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
+      t_n = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
+      ot[e_c] = t_n;
     }
     {
       const double x_ip = sq[e_ip], x_im = sq[e_im], x_jp = sq[e_jp], x_jm = sq[e_jm];
       const double adv = ((pu_c * (q_k + x_ip) - pu_im * (x_im + q_k)) * rdxj +
                           (pv_c * (q_k + x_jp) - pv_jm * (x_jm + q_k)) * rdy) * 0.5;
-      oq[e_c] = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
+      q_n = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
+      oq[e_c] = q_n;
     }
+    bad |= gcm_not_finite((u_n + v_n) + (t_n + q_n));
     fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
     u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
     e_c += plane; e_im += plane; e_ip += plane; e_jp += plane; e_jm += plane; e_jp_im += plane; e_jm_ip += plane;
   }
   out.p[o2 + j * W + i] = pn_c;
+  gcm_flag_nonfinite(g.nonfinite, bad);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -632,25 +639,30 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 
   const double pu_n = u[e_c] * pu_fac - (dut + dus + pgf[e_c]) * dt;   // dynamics.py:206
   const double pv_n = v[e_c] * pv_fac - (dvt + dvs + fv[e_c]) * dt;    // dynamics.py:207
-  out.u[o3 + e_c] = pu_n * r_pnu;
+  const double u_n = pu_n * r_pnu;
+  out.u[o3 + e_c] = u_n;
   double v_n = pv_n * r_pnv;
   if (zero_v) v_n *= 0.0;  // dynamics.py:222
   out.v[o3 + e_c] = v_n;
 
   // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
+  double t_n, q_n;
   {
     const double x_ip = st[e_ip], x_im = st[e_im], x_jp = st[e_jp], x_jm = st[e_jm];
     const double adv = ((pu_c * (t_k + x_ip) - pu_im * (x_im + t_k)) * rdxj +
                         (pv_c * (t_k + x_jp) - pv_jm * (x_jm + t_k)) * rdy) * 0.5;
-    out.t[o3 + e_c] = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
+    t_n = (t[e_c] * p_c - (adv + ads_t) * dt) * r_pn;
+    out.t[o3 + e_c] = t_n;
   }
   {
     const double x_ip = sq[e_ip], x_im = sq[e_im], x_jp = sq[e_jp], x_jm = sq[e_jm];
     const double adv = ((pu_c * (q_k + x_ip) - pu_im * (x_im + q_k)) * rdxj +
                         (pv_c * (q_k + x_jp) - pv_jm * (x_jm + q_k)) * rdy) * 0.5;
-    out.q[o3 + e_c] = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
+    q_n = (q[e_c] * p_c - (adv + ads_q) * dt) * r_pn;
+    out.q[o3 + e_c] = q_n;
   }
   if (k == 0) out.p[o2 + c2] = pn_c;
+  gcm_flag_nonfinite(g.nonfinite, gcm_not_finite((u_n + v_n) + (t_n + q_n) + pn_c));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -781,6 +793,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   double ft = (t_k + t_top) * 0.5 * sd_c;
   double fq = (q_k + q_top) * 0.5 * sd_c;
   const double fu0 = fu, fv0 = fv_, ft0 = ft, fq0 = fq;
+  bool bad = active && gcm_not_finite(pn_c);
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
@@ -853,15 +866,20 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     const double adv_q = ((pu_c * (q_k + sq_[1]) - pu_im * (sq_[-1] + q_k)) * rdxj +
                           (pv_c * (q_k + sq_[PFT_ROW]) - pv_jm * (sq_[-PFT_ROW] + q_k)) * rdy) * 0.5;
     if (active) {
-      ou[e] = pu_n * r_pnu;
+      const double u_n = pu_n * r_pnu;
+      const double t_n = (own_t * p_c - (adv_t + ads_t) * dt) * r_pn;
+      const double q_n = (own_q * p_c - (adv_q + ads_q) * dt) * r_pn;
+      ou[e] = u_n;
       ov[e] = v_n;
-      ot[e] = (own_t * p_c - (adv_t + ads_t) * dt) * r_pn;
-      oq[e] = (own_q * p_c - (adv_q + ads_q) * dt) * r_pn;
+      ot[e] = t_n;
+      oq[e] = q_n;
+      bad |= gcm_not_finite((u_n + v_n) + (t_n + q_n));
     }
     fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
     u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
   }
   if (active) out.p[o2 + e_c] = pn_c;
+  gcm_flag_nonfinite(g.nonfinite, bad);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -88,7 +88,8 @@ __global__ void pe2d_half_kernel(const double* __restrict__ p, const double* __r
                                  const double* __restrict__ sp, const double* __restrict__ su,
                                  const double* __restrict__ sv, const double* __restrict__ st, double* __restrict__ po,
                                  double* __restrict__ uo, double* __restrict__ vo, double* __restrict__ to,
-                                 double* __restrict__ qo, int H, int W, double dt, double dx) {
+                                 double* __restrict__ qo, int H, int W, double dt, double dx,
+                                 unsigned int* nonfinite) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= W) return;
   const Pe2dIdx ix = pe2d_idx(j, i, H, W);
@@ -104,8 +105,9 @@ __global__ void pe2d_half_kernel(const double* __restrict__ p, const double* __r
   const double pv = v[c] * ((p_c + A2(p, 1, 0)) / 2);
   const double pu_n = pu - (dut + pgu) * dt;
   const double pv_n = pv - (dvt + pgv) * dt;
-  uo[c] = pu_n / ((pn_c + pn_ip) / 2);
-  vo[c] = pv_n / ((pn_c + pn_jp) / 2);
+  const double u_n = pu_n / ((pn_c + pn_ip) / 2), v_n = pv_n / ((pn_c + pn_jp) / 2);
+  uo[c] = u_n;
+  vo[c] = v_n;
   // advec_t (no_limits_2d.py:92-101)
   const double sp_c = A2(sp, 0, 0), st_c = A2(st, 0, 0);
   const double spu = A2(su, 0, 0) * ((sp_c + A2(sp, 0, 1)) / 2);
@@ -117,9 +119,11 @@ __global__ void pe2d_half_kernel(const double* __restrict__ p, const double* __r
   const double tpv = spv * ((st_c + A2(st, 1, 0)) / 2);
   const double tpv_jm = spv_jm * ((A2(st, -1, 0) + st_c) / 2);
   const double adv = (tpu - tpu_im) / dx + (tpv - tpv_jm) / dx;
-  to[c] = t[c] - (adv / pn_c) * dt;
+  const double t_n = t[c] - (adv / pn_c) * dt;
+  to[c] = t_n;
   po[c] = pn_c;
   qo[c] = q[c];  // q is passed through (no_limits_2d.py:126)
+  gcm_flag_nonfinite(nonfinite, gcm_not_finite((u_n + v_n) + (t_n + pn_c)));
 }
 
 static int pe2d_check(const gcm_state* s) {
@@ -132,7 +136,8 @@ static int pe2d_half_impl(const gcm_state* b, const gcm_state* s, const gcm_stat
   const int tc = W >= 128 ? 128 : (W + 31) / 32 * 32;
   GCM_LAUNCH(pe2d_half_kernel, dim3((W + tc - 1) / tc, H, 1), dim3(tc), 0, stream, (const double*)b->p,
              (const double*)b->u, (const double*)b->v, (const double*)b->t, (const double*)b->q, (const double*)s->p,
-             (const double*)s->u, (const double*)s->v, (const double*)s->t, o->p, o->u, o->v, o->t, o->q, H, W, dt, dx);
+             (const double*)s->u, (const double*)s->v, (const double*)s->t, o->p, o->u, o->v, o->t, o->q, H, W, dt, dx,
+             gcm_nonfinite_word());
   GCM_CHECK_LAUNCH();
   return GCM_OK;
 }

@@ -118,7 +118,7 @@ extern "C" int gcm_laplacian5(const double* q, double* out, int H, int W, double
 __global__ void __launch_bounds__(256) sw2d_matsuno_tile_kernel(const double* __restrict__ u, const double* __restrict__ v,
                                                                 const double* __restrict__ p, double* __restrict__ uo,
                                                                 double* __restrict__ vo, double* __restrict__ po, int H,
-                                                                int W, double dx, double dt) {
+                                                                int W, double dx, double dt, unsigned int* nonfinite) {
   __shared__ double bu[(SW_TH + 4) * SW_BP], bv[(SW_TH + 4) * SW_BP], bp[(SW_TH + 4) * SW_BP];
   __shared__ double su[(SW_TH + 2) * SW_SP], sv[(SW_TH + 2) * SW_SP], sp[(SW_TH + 2) * SW_SP];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) sw2d_matsuno_tile_kernel(const double* __
     sp[e] = bp[c] - dt * sw_adv_p(bu, bv, bp, n, dx);
   }
   __syncthreads();
+  bool bad = false;
   for (int e = tid; e < SW_TH * SW_TW; e += nthr) {
     const int tj = e / SW_TW, ti = e % SW_TW;
     const int j = j0 + tj, i = i0 + ti;
@@ -145,10 +146,15 @@ __global__ void __launch_bounds__(256) sw2d_matsuno_tile_kernel(const double* __
     const GcmNb n = gcm_nb_tile(tj + 1, ti + 1, SW_SP);
     const int c = (tj + 2) * SW_BP + ti + 2;
     const size_t g = (size_t)j * W + i;
-    uo[g] = bu[c] - dt * (sw_adv_u(su, sv, n, dx) + sw_grad_u(sp, n, dx));
-    vo[g] = bv[c] - dt * (sw_adv_v(su, sv, n, dx) + sw_grad_v(sp, n, dx));
-    po[g] = bp[c] - dt * sw_adv_p(su, sv, sp, n, dx);
+    const double u_n = bu[c] - dt * (sw_adv_u(su, sv, n, dx) + sw_grad_u(sp, n, dx));
+    const double v_n = bv[c] - dt * (sw_adv_v(su, sv, n, dx) + sw_grad_v(sp, n, dx));
+    const double p_n = bp[c] - dt * sw_adv_p(su, sv, sp, n, dx);
+    uo[g] = u_n;
+    vo[g] = v_n;
+    po[g] = p_n;
+    bad |= gcm_not_finite(u_n + v_n + p_n);
   }
+  gcm_flag_nonfinite(nonfinite, bad);
 }
 
 // Matsuno steps, resident: the whole grid lives in one CTA's shared memory for all `nsteps` steps (the
@@ -158,7 +164,8 @@ __global__ void __launch_bounds__(1024) sw2d_matsuno_resident_kernel(const doubl
                                                                      const double* __restrict__ v,
                                                                      const double* __restrict__ p, double* __restrict__ uo,
                                                                      double* __restrict__ vo, double* __restrict__ po,
-                                                                     int H, int W, double dx, double dt, int nsteps) {
+                                                                     int H, int W, double dx, double dt, int nsteps,
+                                                                     unsigned int* nonfinite) {
   GCM_DYN_SMEM(double, smem);
   const int n2 = H * W;
   double *bu = smem, *bv = bu + n2, *bp = bv + n2, *su = bp + n2, *sv = su + n2, *sp = sv + n2;
@@ -181,7 +188,12 @@ __global__ void __launch_bounds__(1024) sw2d_matsuno_resident_kernel(const doubl
     }
     __syncthreads();
   }
-  for (int e = tid; e < n2; e += nthr) { uo[e] = bu[e]; vo[e] = bv[e]; po[e] = bp[e]; }
+  bool bad = false;
+  for (int e = tid; e < n2; e += nthr) {
+    uo[e] = bu[e]; vo[e] = bv[e]; po[e] = bp[e];
+    bad |= gcm_not_finite(bu[e] + bv[e] + bp[e]);
+  }
+  gcm_flag_nonfinite(nonfinite, bad);
 }
 
 #define SW_RESIDENT_MAX_BYTES (220 * 1024)
@@ -206,7 +218,7 @@ extern "C" int gcm_sw2d_matsuno_step(const double* u, const double* v, const dou
     const int n2 = H * W;
     const int thr = n2 >= 1024 ? 1024 : (n2 + 31) / 32 * 32;
     GCM_LAUNCH(sw2d_matsuno_resident_kernel, dim3(1), dim3(thr), resident, stream, u, v, p, uo, vo, po, H, W, dx, dt,
-               nsteps);
+               nsteps, gcm_nonfinite_word());
     GCM_CHECK_LAUNCH();
     return GCM_OK;
   }
@@ -221,7 +233,8 @@ extern "C" int gcm_sw2d_matsuno_step(const double* u, const double* v, const dou
     double* du = to_out ? uo : t[0];
     double* dv = to_out ? vo : t[1];
     double* dp = to_out ? po : t[2];
-    GCM_LAUNCH(sw2d_matsuno_tile_kernel, grid, dim3(256), 0, stream, cu, cv, cp, du, dv, dp, H, W, dx, dt);
+    GCM_LAUNCH(sw2d_matsuno_tile_kernel, grid, dim3(256), 0, stream, cu, cv, cp, du, dv, dp, H, W, dx, dt,
+               gcm_nonfinite_word());
     GCM_CHECK_LAUNCH();
     cu = du; cv = dv; cp = dp;
   }

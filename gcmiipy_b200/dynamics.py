@@ -41,13 +41,17 @@ def configure(geom, coriolis=False, viscosity=0.0, limit_q=False, limit_t=False)
     (whole grids, and latitude bands created afterwards by `bands.BandStepper`, which then carry two halo rows on
     either side).  `configure(geom)` restores the reference's step.  Returns the StepOptions."""
     opt = StepOptions(coriolis, viscosity, limit_q, limit_t)
+    resident = list(geom._dev.values())
+    # validate every resident geometry BEFORE touching anything: the opt-in terms need exactly 2 + 2 halo rows on a
+    # band (the one-exchange bands carry 2 + 4 and run the row-segment schedule, which the options do not support)
+    for dg in resident:
+        if not dg.wrap_j and opt.any() != dg.options_on and not (dg.row_lo == 2 and dg.H - dg.row_hi == 2):
+            raise ValueError("a latitude band of this geometry is already resident with a halo layout other than 2 + 2 "
+                             "rows: configure() before creating the BandStepper")
     geom.step_options = opt
-    for dg in list(geom._dev.values()):
-        if dg.wrap_j or (dg.row_lo >= 2 and dg.H - dg.row_hi >= 2):
+    for dg in resident:
+        if dg.wrap_j or (dg.row_lo == 2 and dg.H - dg.row_hi == 2):
             _push_options(geom, dg)
-        elif opt.any():
-            raise ValueError("a latitude band of this geometry is already resident with fewer than two halo rows: "
-                             "configure() before creating the BandStepper")
     return opt
 
 
@@ -55,13 +59,18 @@ def _struct(ts):
     return _abi.State(*[_host.ptr(t) for t in ts])
 
 
-def _workspace(dg, nbatch):
-    """Scratch fields of a half step, cached on the device geometry."""
-    ws = getattr(dg, "_ws", None)
+def _workspace(dg, nbatch, owner=None):
+    """Scratch fields of a half step.  A Stepper / BandStepper owns its own (`owner`), so two steppers of one geometry
+    driven from different streams do not share spu / pgf / the star state; the functional calls (half_timestep,
+    matsuno_timestep, ...) share one per device geometry and are single-stream per geometry by contract.  `dg._ws`
+    always names the workspace of the latest call (the tests read work fields through it)."""
+    holder = owner if owner is not None else dg
+    ws = getattr(holder, "_ws_own", None)
     need = _lib.lib().gcm_pe25_workspace_bytes(dg.handle, nbatch)
     if ws is None or ws.numel() * 8 < need or ws.device != _lib.device():
         ws = torch.empty((need + 7) // 8, dtype=torch.float64, device=_lib.device())
-        dg._ws = ws
+        holder._ws_own = ws
+    dg._ws = ws
     return ws, need
 
 
@@ -99,7 +108,7 @@ class Stepper:
             dst.copy_(_host.dev(src), non_blocking=True)
 
     def step(self, dt, nsteps=1):
-        ws, need = _workspace(self.dg, self.nbatch)
+        ws, need = _workspace(self.dg, self.nbatch, self)
         sin, sout = _struct(self.cur), _struct(self.nxt)
         _lib.check(_lib.lib().gcm_pe25_matsuno_step(self.dg.handle, ctypes.byref(sin), ctypes.byref(sout),
                                                     _host.scalar(dt), int(nsteps), self.nbatch, _host.ptr(ws), need,
@@ -116,7 +125,7 @@ class Stepper:
                 not x.is_cuda and x.is_contiguous() and x.dtype == torch.float64 for x in list(host_in) + list(host_out)):
             if getattr(self, "_star", None) is None:
                 self._star = [torch.empty_like(x) for x in self.cur]
-            ws, need = _workspace(self.dg, 1)
+            ws, need = _workspace(self.dg, 1, self)
             hi, ho = _struct(host_in), _struct(host_out)
             sc, ss, sn = _struct(self.cur), _struct(self._star), _struct(self.nxt)
             _lib.check(_lib.lib().gcm_pe25_matsuno_step_host(self.dg.handle, ctypes.byref(hi), ctypes.byref(ho),

@@ -180,6 +180,7 @@ def _fingerprint(geom, band):
         h.update(np.ascontiguousarray(_host.magnitude(a), dtype=np.float64).tobytes())
     h.update(np.asarray([_host.scalar(geom.dy), _host.scalar(geom.ptop)]).tobytes())
     h.update(repr(band).encode())
+    h.update(str(_lib.device()).encode())      # tables, streams and events belong to one device
     return h.hexdigest()
 
 
@@ -221,8 +222,10 @@ def device_geom(geom, band=None):
     handle = ctypes.c_void_p()
     _lib.check(_lib.lib().gcm_geom_create(ctypes.byref(desc), ctypes.byref(handle)), "gcm_geom_create")
     obj = DeviceGeom(handle, Hs, W, L, row_lo, row_hi, wrap)
-    if len(geom._dev) >= 8:       # a caller that keeps editing the heightmap: drop the stale tables
-        geom._dev.clear()
+    if len(geom._dev) >= 8:       # a caller that keeps editing the heightmap: drop stale tables nobody else holds
+        import sys
+        for k in [k for k, v in geom._dev.items() if sys.getrefcount(v) <= 3]:
+            del geom._dev[k]      # (dict + loop variable + getrefcount's argument): no Stepper / BandStepper owns it
     geom._dev[key] = obj
     if band is None:
         _push_options(geom, obj)

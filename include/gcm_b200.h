@@ -39,6 +39,19 @@ extern "C" {
 int gcm_version(void);
 const char* gcm_status_string(int status);
 
+/* The newest non-zero status any entry point returned on the calling thread (0 if none since the last clear);
+ * clear != 0 resets it.  For callers that batch several calls and look once (the reference's callers have nothing to
+ * check: numpy raises or propagates NaN, matsuno_c_grid.py:184-187 polls np.isnan). */
+int gcm_last_status(int clear);
+
+/* Asynchronous "non-finite seen" watch -- replaces the caller-side poll `np.isnan(u).any()` of
+ * matsuno_c_grid.py:184-187 / no_limits_2_5d.py:85-88.  Every step kernel (2.5-D update, 2-D shallow water, 2-D
+ * primitive equations) adds, per thread that has just written an inf or NaN, one to a 32-bit counter that lives on the
+ * device.  gcm_nonfinite_read enqueues on `stream` a 4-byte copy of the current device's counter into *host_out
+ * (pinned memory keeps it asynchronous; NULL = no read) and, if reset != 0, zeroes it afterwards.  The value is valid
+ * once the stream has reached that point (event / stream query): nothing here synchronises the caller. */
+int gcm_nonfinite_read(unsigned int* host_out, int reset, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Geometry: metric + sigma tables kept resident on the device (geometry.py:9-182, Geom).
  * A geometry describes the rows STORED by one process: either the whole grid (wrap_j = 1, rows are

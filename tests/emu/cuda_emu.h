@@ -77,6 +77,7 @@ static inline double atomicAdd(double* a, double v) {
     if (__atomic_compare_exchange_n(u, &old, nu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { memcpy(&d, &old, 8); return d; }
   }
 }
+static inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long x; memcpy(&x, &d, 8); return x; }
 static inline double __dmul_rn(double a, double b) { return a * b; }

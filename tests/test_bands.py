@@ -213,3 +213,52 @@ def test_gloo_ranks_bit_identical_to_single_process(world, options, tmp_path):
                 assert np.array_equal(z[k], b), k
     finally:
         _lib._override_for_tests(None, None)
+
+
+def _subgroup_worker(rank, world, port, out):
+    """World of 3, the bands live on the sub-group {1, 2} (global rank 0 is not a member): the 128-byte id made by the
+    group's first rank must reach every member (dist.broadcast takes a GLOBAL source rank), and the band
+    run on the sub-group must equal the whole grid."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["GCM_EMU_THREADS"] = "2"
+    from emu import emu_lib
+    from gcmiipy_b200 import _lib
+    _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grp = dist.new_group([1, 2])
+    if rank in (1, 2):
+        geom, s = _case()
+        b = bands.BandStepper(geom, *s, group=grp)
+        assert (b.rank, b.world) == (rank - 1, 2)
+
+        def make(buf):
+            for n in range(128):
+                buf[n] = (7 * n + 3) % 251
+        got = bytes(b._share_id(make))
+        assert got == bytes((7 * n + 3) % 251 for n in range(128)), "id did not reach group rank %d" % b.rank
+        b.step(450.0, 2)
+        full = b.gather()
+        if b.rank == 0:
+            np.savez(out, *full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_subgroup_bands(tmp_path):
+    torch.set_num_threads(1)
+    out = str(tmp_path / "sub.npz")
+    mp.spawn(_subgroup_worker, args=(3, _free_port(), out), nprocs=3, join=True)
+    from emu import emu_lib
+    from gcmiipy_b200 import _lib
+    _lib._override_for_tests(emu_lib.load(), torch.device("cpu"))
+    try:
+        geom, s = _case()
+        whole = dynamics.Stepper(geom, *s)
+        whole.step(450.0, 2)
+        with np.load(out) as z:
+            for k, b in zip(sorted(z.files, key=lambda n: int(n.split("_")[1])), whole.download()):
+                assert np.array_equal(z[k], b), k
+    finally:
+        _lib._override_for_tests(None, None)

@@ -543,3 +543,50 @@ def test_benchmark_grids_vs_oracle(H, W, L, dt, n):
     for _ in range(n):
         ref = O.matsuno_timestep(*ref, dt, og)
     check_state(st.download(), ref, TOL_RUN)
+
+
+# ---- C-ABI error reporting: gcm_last_status and the asynchronous non-finite watch -----------------
+def test_nonfinite_watch_and_last_status(backend):
+    """matsuno_c_grid.py:184-187 polls np.isnan(u).any() on the host after every step; here the step kernels count
+    non-finite writes on the device and the count is read by a stream-ordered 4-byte copy."""
+    from gcmiipy_b200 import _lib, watch
+    geom = geometry.gen_geometry(12, 32, 9, sig_func=geometry.manabe_sig)
+    s = O.synthetic_state(O.gen_geometry(12, 32, 9, sig_func=O.manabe_sig), seed=5)
+    w = watch.NonFiniteWatch()
+    st = dynamics.Stepper(geom, *s)
+    st.step(100.0, 2)
+    w.poll()
+    assert w.value(wait=True) == 0
+    bad = [a.copy() for a in s]
+    bad[3][4, 5, 6] = np.nan
+    st = dynamics.Stepper(geom, *bad)
+    st.step(100.0, 1)
+    w.poll(reset=True)
+    assert w.value(wait=True) > 0
+    w.poll()
+    assert w.value(wait=True) == 0          # the reset is ordered after the read
+    # narrow grid (one thread per cell update) and the 2-D schemes feed the same counter
+    g2 = geometry.gen_geometry(6, 12, 3)
+    s2 = list(O.synthetic_state(O.gen_geometry(6, 12, 3), seed=6))
+    s2[1] = s2[1].copy(); s2[1][1, 2, 3] = np.inf
+    dynamics.matsuno_timestep(*s2, 10.0, g2)
+    w.poll(reset=True)
+    assert w.value(wait=True) > 0
+    u = np.zeros((8, 8)); v = np.zeros((8, 8)); h = np.full((8, 8), 8000.0)
+    matsuno_c_grid.matsumo_scheme(u, v, h, 300e3, 300.0)
+    w.poll()
+    assert w.value(wait=True) == 0
+    u[3, 3] = np.nan
+    matsuno_c_grid.matsumo_scheme(u, v, h, 300e3, 300.0)
+    w.poll(reset=True)
+    assert w.value(wait=True) > 0
+    # gcm_last_status: the newest non-zero status of this thread, cleared on request
+    watch.last_status(clear=True)
+    assert watch.last_status() == 0
+    assert _lib.lib().gcm_pe25_workspace_bytes(None, 1) == 0
+    assert _lib.lib().gcm_geom_destroy(None) == 0
+    assert watch.last_status() == 0
+    assert _lib.lib().gcm_tuning_knob(99, 0) == -2
+    assert watch.last_status() == -2
+    assert _lib.lib().gcm_tuning_knob(0, 0) == 0
+    assert watch.last_status(clear=True) == -2 and watch.last_status() == 0
