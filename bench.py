@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the Matsuno C-grid hot path (BASELINE.json: cell-updates/s, fraction of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c3|c2|c4] [--impl native|reference]
-                    [--options coriolis,limit_q,limit_t,viscosity=NU]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--repeats R] [--workload c5|c3|c2|c4|c1|c1big|p2d]
+                    [--impl native|reference] [--options coriolis,limit_q,limit_t,viscosity=NU]
 
 One "step" = one full Matsuno step (predictor + corrector, dynamics.py:230-237) of the 2.5-D model over the
 whole grid.  Default workload: the 0.25 deg grid 1440 x 720 x 9 (BASELINE.json configs[4], the grid the metric
 "cell-updates/s at 1/2/4/8 B200" is quoted on; 307 MB of state > 126 MB L2, so every step streams from HBM).
 N > 1 (torchrun, one rank per GPU): latitude-band decomposition, strong scaling.
+The timed call (K steps from the same initial state) is repeated R >= 5 times (more until >= 200 ms are timed);
+`value` / `ms_per_step` are the MEDIAN repeat (the sustained figure), `best_ms_per_step` the fastest.  `state_sha256`
+is the SHA-256 of the gathered state after K steps: identical lines at N = 1, 2, 4, 8 prove that the latitude-band
+decomposition is bitwise invariant.  c1 / c1big (2-D shallow water, matsuno_c_grid.py:125-142, 48 B per cell-update)
+and p2d (2-D primitive equations, no_limits_2d.py:129-131, 64 B) are single-GPU workloads.
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm (oracle/np_oracle.py,
 numpy, all host cores as independent processes) on a bounded sample of the same workload.
 """
@@ -31,6 +36,13 @@ WORKLOADS = {
     "c4": (24, 36, 9, 450.0, 1024, "ensemble of 1024 x 8x10deg 36x24x9 runs (BASELINE configs[3])"),
     # tuning aid: the per-rank share of configs[4] on 8 GPUs as a stand-alone periodic grid (not a BASELINE config)
     "c5b8": (90, 1440, 9, 10.0, 1, "1440x90x9: one of 8 latitude bands of configs[4], stepped alone (tuning aid)"),
+}
+# 2-D schemes: name: (kind, H, W, dt, dx, description)
+WORKLOADS_2D = {
+    "c1": ("sw2d", 64, 64, 300.0, 300e3, "2-D shallow-water Matsuno C-grid 64x64, dx = 300 km, dt = 300 s (BASELINE configs[0]; the "
+           "reference's dt = 700 s diverges after 8 steps, SURVEY 8d)"),
+    "c1big": ("sw2d", 8192, 8192, 300.0, 300e3, "2-D shallow-water Matsuno C-grid 8192x8192 (HBM-resident: 1.6 GB of state)"),
+    "p2d": ("pe2d", 4096, 4096, 100.0, 300e3, "2-D primitive equations (no_limits_2d) 4096x4096"),
 }
 METRIC = "cell_updates_per_sec"
 UNIT = "cell-updates/s"
@@ -255,22 +267,40 @@ def run_native(args):
     # is captured on first use, once for each of the two buffer parities (one-time cost, not steady state)
     for _ in range(2):
         stepper.step(dt, args.steps)
-    reset()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    stepper.step(dt, args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    rep_ms = []
+    repeats = max(args.repeats, 1)
+    while len(rep_ms) < repeats or (sum(rep_ms) < 200.0 and len(rep_ms) < 200):
+        reset()
+        barrier()
+        e0.record()
+        stepper.step(dt, args.steps)
+        e1.record()
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)        # the slowest rank defines the repeat
+        rep_ms.append(float(tms.item()))
+    ms = sorted(rep_ms)[len(rep_ms) // 2]                       # median repeat: the sustained figure
+    ms_best = min(rep_ms)
     finite = all(bool(torch.isfinite(x).all()) for x in stepper.tensors())
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = total_cells * args.steps / (ms * 1e-3)
+    # SHA-256 of the whole state after K steps from the fixed initial state (gathered over the ranks): the same line
+    # at every N proves the band decomposition bitwise invariant
+    state_sha = None
+    if not args.no_hash:
+        import hashlib
+        if world > 1:
+            full = stepper.gather()
+        else:
+            full = stepper.download()
+        if rank == 0:
+            h = hashlib.sha256()
+            for a in full:
+                h.update(np.ascontiguousarray(a.cpu().numpy() if hasattr(a, "cpu") else a).tobytes())
+            state_sha = h.hexdigest()
+        del full
 
     # ---- end to end through the host-facing call: pinned host state in, pinned host state out, every step ----
     reset()
@@ -280,16 +310,20 @@ def run_native(args):
     for _ in range(2):
         stepper.step_host(host_in, host_out, dt, 1)
     barrier()
-    e0.record()
-    for _ in range(args.steps):
-        stepper.step_host(host_in, host_out, dt, 1)
-        host_in, host_out = host_out, host_in
-    e1.record()
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_value = total_cells * args.steps / (float(tms.item()) * 1e-3)
+    e2e_ms = []
+    for _ in range(3):
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            stepper.step_host(host_in, host_out, dt, 1)
+            host_in, host_out = host_out, host_in
+        e1.record()
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms.append(float(tms.item()))
+    e2e_value = total_cells * args.steps / (sorted(e2e_ms)[1] * 1e-3)            # median of three
     # clocks / throttle reasons sampled across both timed regions (the device-resident one alone lasts ~50 ms)
     clocks = sampler.stop() if sampler else None
 
@@ -312,15 +346,18 @@ def run_native(args):
     kinds = [(lib.gcm_prof_kind_name(k).decode(), k_ms[k], k_n[k]) for k in range(nk) if k_n[k] > 0]
     if kinds:
         launches_per_step = sum(n for _, _, n in kinds) / psteps
-        name, tot, n = max(kinds, key=lambda x: x[1])
+        name, tot, n = max((x for x in kinds if x[0] != "halo_exchange"), key=lambda x: x[1])
         peak, peak_src = measured_peak()
         launches_of_kind_per_step = n / psteps
         alg_bytes = b_alg(L) * cells_rank / launches_of_kind_per_step      # the kernel's share of one cell-update
         achieved = alg_bytes / (tot / n * 1e-3) / 1e9
         traffic = ncu_traffic(name) if (args.workload == "c5" and world == 1) else None
+        halo = [(t, n) for nm, t, n in kinds if nm == "halo_exchange"]
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+                    # `traffic` is NOT measured by this run: it is the ncu --set full capture named here (profiles/)
                     "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
+                    "halo_exchange_ms_per_step": (halo[0][0] / psteps) if halo else None,
                     "avg_launch_ms": tot / n, "alg_bytes_per_launch": alg_bytes,
                     # the two chains of the row phase run side by side, so the per-kernel times add up to more than
                     # the step: the share is taken against the measured step, the second figure against that sum
@@ -352,7 +389,9 @@ def run_native(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "best_ms_per_step": ms_best / args.steps, "repeats": len(rep_ms),
+        "timed_ms_total": sum(rep_ms), "value_is": "median of `repeats` timed calls of `steps` steps each",
+        "state_sha256": state_sha, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "grid": [H, W, L], "dt_s": dt, "members": members, "options": options or None,
                    "parallelism": "lat-bands x%d" % world if members == 1 else "members split x%d" % world,
@@ -369,12 +408,121 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def _cpu_2d(kind, H, W, dt, dx, nsteps, seed=7):
+    """The oracle's 2-D scheme on one host core; returns (seconds, state)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_oracle as O
+    s = _state_2d(kind, H, W, seed)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        s = O.matsumo_scheme(*s, dx, dt) if kind == "sw2d" else O.pe2d_matsuno_timestep(*s, dt, dx)
+    return time.perf_counter() - t0, s
+
+
+def _state_2d(kind, H, W, seed=7):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    if kind == "sw2d":           # matsuno_c_grid.py:146-157: flat 8000 m layer, u bump, + 0.1 m/s noise (SURVEY 8d)
+        u = 0.1 * rng.standard_normal((H, W)); v = 0.1 * rng.standard_normal((H, W))
+        u[H // 2, W // 2] += 1.0
+        return u, v, np.full((H, W), 8000.0)
+    p = 1e5 + 50.0 * rng.standard_normal((H, W))      # no_limits_2d.py:134-150 style: p, u, v, t, q
+    return (p, 0.1 * rng.standard_normal((H, W)), 0.1 * rng.standard_normal((H, W)),
+            300.0 + 0.5 * rng.standard_normal((H, W)), np.full((H, W), 1e-3))
+
+
+def run_2d(args):
+    """c1 / c1big: matsuno_c_grid.matsumo_scheme (48 B per cell-update: u, v, h read + written once per step);
+    p2d: no_limits_2d.matsuno_timestep (64 B: p, u, v, t; q untouched).  Single GPU."""
+    kind, H, W, dt, dx, desc = WORKLOADS_2D[args.workload]
+    bpc = 48.0 if kind == "sw2d" else 64.0
+    cells = H * W
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        rows = H if cells <= 1 << 20 else max(8, (1 << 20) // W)
+        n = max(1, min(args.steps, int(20 * 2.5e6 // (rows * W)) or 1))
+        t, _ = _cpu_2d(kind, rows, W, dt, dx, n)
+        v = rows * W * n / t
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": n, "warmup": 0, "ms_per_step": 1e3 * t / n, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": desc, "grid": [H, W], "dt_s": dt},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                           "sample": "%d step(s) of a %dx%d grid, numpy oracle, 1 thread" % (n, W, rows)},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    import numpy as np
+    import torch
+    from gcmiipy_b200 import _lib, matsuno_c_grid, no_limits_2d
+    assert args.gpus == 1 and torch.cuda.is_available(), "the 2-D workloads are single-GPU"
+    torch.cuda.set_device(0)
+    s0 = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in _state_2d(kind, H, W)]
+    step = (lambda s, n: matsuno_c_grid.matsumo_scheme(*s, dx, dt, nsteps=n)) if kind == "sw2d" else (
+        lambda s, n: no_limits_2d.matsuno_timestep(*s, dt, dx, nsteps=n))
+    for _ in range(3):
+        step(s0, max(args.warmup, 1))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rep = []
+    while len(rep) < max(args.repeats, 1) or (sum(rep) < 200.0 and len(rep) < 500):
+        torch.cuda.synchronize()
+        e0.record()
+        out = step(s0, args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        rep.append(e0.elapsed_time(e1))
+    ms = sorted(rep)[len(rep) // 2]
+    value = cells * args.steps / (ms * 1e-3)
+    # e2e: host arrays in, host arrays out, one step per call (the reference's own calling convention)
+    hs = [a.cpu().pin_memory() for a in s0]
+    for _ in range(2):
+        step(hs, 1)
+    n_e2e = max(3, min(args.steps, 20))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cur = hs
+    for _ in range(n_e2e):
+        cur = step(cur, 1)
+    torch.cuda.synchronize()
+    e2e = cells * n_e2e / (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = value * bpc / 1e9
+    rows = H if cells <= 1 << 20 else max(8, (1 << 20) // W)
+    ncpu = max(1, int(10 * 2.5e6 // (rows * W)))
+    tcpu, _ = _cpu_2d(kind, rows, W, dt, dx, ncpu)
+    nfields = 3 if kind == "sw2d" else 5
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "best_ms_per_step": min(rep) / args.steps, "repeats": len(rep),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "grid": [H, W], "dt_s": dt, "dx_m": dx,
+                       "l2_policy": "state %.0f MB > 126 MB L2: no flush" % (cells * bpc / 2e6) if cells * bpc / 2 > 126e6
+                       else "state fits one SM's shared memory / L2 (latency-bound config); no flush"},
+            "finite": all(bool(torch.isfinite(x).all()) for x in out),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cells * 8 * nfields,
+                    "d2h_bytes_per_step": cells * 8 * nfields},
+            "gpu_launches": args.steps if not (kind == "sw2d" and 6 * cells * 8 <= 220 * 1024) else 1,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "sw2d_matsuno_tile_kernel" if kind == "sw2d" else "pe2d_half_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "alg_bytes_per_cell_update": bpc},
+            "cpu_baseline": {"value": rows * W * ncpu / tcpu, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d step(s) of a %dx%d grid, numpy oracle, 1 thread" % (ncpu, W, rows)}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS) + sorted(WORKLOADS_2D))
+    ap.add_argument("--repeats", type=int, default=5, help="timed calls of --steps steps (median reported; at least 200 ms)")
+    ap.add_argument("--no-hash", action="store_true", help="skip the SHA-256 of the final state")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 = fused kernels (default), 1 = general 4-kernel path")
@@ -383,7 +531,9 @@ def main():
     ap.add_argument("--knob", action="append", default=[], help="tuning knob i=v (gcm_tuning_knob)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    if args.impl == "reference":
+    if args.workload in WORKLOADS_2D:
+        run_2d(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

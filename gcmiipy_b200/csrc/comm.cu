@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "gcm_common.h"
+#include "prof.h"
 
 #ifndef GCM_EMU
 #include <dlfcn.h>
@@ -173,6 +174,7 @@ __global__ void band_halo2_kernel(gcm_state s, int H, int W, int L, GcmHaloJob a
 
 // fill the halo rows of `s` (hn north, hs south) from the ring neighbours, on stream `q`
 static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, cudaStream_t q) {
+  GcmProfScope ps(GCM_K_HALO, q);
   const int lo = g->d.row_lo, hi = g->d.row_hi;
   int st;
   if (c->nranks == 1) {  // the ring closes on the band itself
