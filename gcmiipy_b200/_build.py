@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 SOURCES = {
     "geom.cu": [],
     "prof.cu": [],
+    "tma.cu": [],
     "comm.cu": [],
     "host_step.cu": [],
     "pe25.cu": ["-fmad=false"],

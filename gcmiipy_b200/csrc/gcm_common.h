@@ -15,7 +15,7 @@
 #define GCM_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define GCM_DYN_SMEM(type, name)                                 \
-  extern __shared__ __align__(16) unsigned char gcm_dyn_smem_[]; \
+  extern __shared__ __align__(128) unsigned char gcm_dyn_smem_[]; \
   type* name = reinterpret_cast<type*>(gcm_dyn_smem_)
 #endif
 
