@@ -23,6 +23,7 @@
 // (tests/test_parity.py); the bit-exact operator kernels stay in pe25.cu.
 #include "fft_inplace.h"
 #include "gcm_common.h"
+#include "gcm_tma.h"
 #include "prof.h"
 
 struct PfConst {
@@ -882,6 +883,224 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   gcm_flag_nonfinite(g.nonfinite, bad);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// U, TMA: the tiled update with every operand delivered by the Tensor Memory Accelerator.  Per layer ONE thread issues
+// bulk tensor loads (cp.async.bulk.tensor.3d, SASS UTMALDG): the (TJ + 2) x 36 halo box of su, sv, st, sq, spu and the
+// TJ x 32 box of the six once-read fields (pgf, fv, and in the corrector the base u, v, t, q; in the predictor
+// base == star and the cell's own staged value is used), three layers in flight, each stage completing on its own
+// mbarrier.  No thread computes a load address in the layer loop: the LDGSTS kernel above spends a quarter of its
+// instructions on them and keeps the LSU pipe 65 % busy (ncu r03j).  A box that leaves the grid is zero-filled by the
+// hardware; the periodic wrap in i (every band and grid) and in j (whole grids) is patched by the CTAs on the seam --
+// 2 of W / 32 tile columns, 2 of H / TJ tile rows -- with plain loads after the box has landed.
+// ---------------------------------------------------------------------------------------------------
+struct PfTmaMaps {
+  GcmTmap halo[PFT_NF];  // su, sv, st, sq, spu: box 36 x (TJ + 2) x 1
+  GcmTmap cen[6];        // pgf, fv, u, v, t, q: box 32 x TJ x 1
+};
+
+template <int L, int PFT_TJ, bool SAME>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
+pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, PfConst base, PfConst star, PfMut out,
+                        PfWork w, double dt, GcmRowSeg seg, size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
+  GCM_DYN_SMEM(unsigned char, smraw);
+  GcmMbar* bars = reinterpret_cast<GcmMbar*>(smraw);  // PFT_NS barriers in the first 128 bytes
+  double* sm = reinterpret_cast<double*>(smraw + 128);
+  constexpr int HBOX = (PFT_TJ + 2) * PFT_ROW;        // doubles a halo box delivers
+  constexpr int HT = (HBOX + 15) / 16 * 16;           // halo tile pitch: box destinations are 128-byte aligned
+  constexpr int CT = PFT_TJ * PFT_TI;                 // centre tile
+  constexpr int NCEN = SAME ? 2 : 6;
+  constexpr int STAGE = PFT_NF * HT + NCEN * CT;
+  constexpr unsigned STAGE_BYTES = (PFT_NF * HBOX + NCEN * CT) * sizeof(double);
+  const int H = g.H, W = g.W, plane = H * W, wrap = g.wrap_j;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PFT_TI + tx;
+  const int i = blockIdx.x * PFT_TI + tx;
+  const int r = blockIdx.y * PFT_TJ + ty;
+  const bool active = r < seg.n1;
+  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile
+  const int x0 = blockIdx.x * PFT_TI - 2;      // first column of the halo box: the interior starts 16-byte aligned
+  auto rowc = [&](int x) { return wrap ? ((x % H) + H) % H : (x < 0 ? 0 : (x >= H ? H - 1 : x)); };
+  const int j = rowc(j0 + ty);
+  const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
+  const int zb = blockIdx.z * L;  // first layer of this member in the [members * L][H][W] view of the tensor maps
+  const double* __restrict__ p = base.p + o2;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ pn = w.pn + o2;
+  const double* __restrict__ pit = w.pit + o2;
+  const double* fld[PFT_NF] = {star.u + o3, star.v + o3, star.t + o3, star.q + o3, w.spu + o3};
+  double* __restrict__ ou = out.u + o3;
+  double* __restrict__ ov = out.v + o3;
+  double* __restrict__ ot = out.t + o3;
+  double* __restrict__ oq = out.q + o3;
+
+  if (tid == 0) {
+    for (int s = 0; s < PFT_NS; ++s) gcm_mbar_init(&bars[s], 1);
+    gcm_mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k, int s) {  // layer k -> stage s (one thread)
+    if (tid == 0) {
+      gcm_fence_proxy_async();
+      double* st = sm + s * STAGE;
+      gcm_mbar_expect_tx(&bars[s], STAGE_BYTES);
+#pragma unroll
+      for (int f = 0; f < PFT_NF; ++f) gcm_tma_load3(st + f * HT, &maps.halo[f], x0, j0 - 1, zb + k, &bars[s]);
+#pragma unroll
+      for (int f = 0; f < NCEN; ++f)
+        gcm_tma_load3(st + PFT_NF * HT + f * CT, &maps.cen[f], blockIdx.x * PFT_TI, j0, zb + k, &bars[s]);
+    }
+  };
+  // CTAs whose halo box leaves the grid patch the zero-filled part with the periodic neighbour (rows only on a whole
+  // grid: a band stores its halo rows, and rows outside it are never used by an active thread)
+  const bool edge = blockIdx.x == 0 || blockIdx.x + 1 == gridDim.x || (wrap && (j0 - 1 < 0 || j0 + PFT_TJ + 1 > H));
+  auto fixup = [&](int k, int s) {
+    double* st = sm + s * STAGE;
+    for (int rr = tid; rr < HBOX; rr += PFT_TI * PFT_TJ) {
+      const int dr = rr / PFT_ROW, c = rr - dr * PFT_ROW;
+      int gj = j0 - 1 + dr, gi = x0 + c;
+      const bool oj = gj < 0 || gj >= H, oi = gi < 0 || gi >= W;
+      if (!oj && !oi) continue;
+      if (oj) {
+        if (!wrap) continue;
+        gj = ((gj % H) + H) % H;
+      }
+      if (oi) gi = gi < 0 ? gi + W : gi - W;
+      const int src = k * plane + gj * W + gi;
+#pragma unroll
+      for (int f = 0; f < PFT_NF; ++f) st[f * HT + rr] = fld[f][src];
+    }
+  };
+  issue(0, 0);
+  if (1 < L) issue(1, 1);
+
+  const int jm = rowc(j0 + ty - 1), jp = rowc(j0 + ty + 1), jpp = rowc(j0 + ty + 2);
+  const int ip = gcm_ip(i, W);
+  const int e_c = j * W + i;
+  const int t_c = (ty + 1) * PFT_ROW + (tx + 2);  // own position in a halo tile
+  const int c_c = ty * PFT_TI + tx;               // own position in a centre tile
+
+  // per-column (2-D) factors while the first layers are on their way
+  const double rdxj = g.rdx_j[j], rdxh = g.rdx_h[j], rdy = g.rdy;
+  const double p_c = p[e_c], p_ip = p[j * W + ip], p_jp = p[jp * W + i];
+  const double pn_c = pn[e_c], pn_ip = pn[j * W + ip], pn_jp = pn[jp * W + i];
+  const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                    // calc_pu / calc_pv
+  const double r_pnu = 1.0 / ((pn_c + pn_ip) * 0.5), r_pnv = 1.0 / ((pn_c + pn_jp) * 0.5);  // un_pu / un_pv
+  const double r_pn = 1.0 / pn_c;
+  const double sp_c = sp[e_c], sp_ip = sp[j * W + ip], sp_jp = sp[jp * W + i], sp_jm = sp[jm * W + i];
+  const double a_c = (sp_c + sp_jp) * 0.5;                     // jph(sp) at (j, i)
+  const double a_ip = (sp_ip + sp[jp * W + ip]) * 0.5;         // (j, i+1)
+  const double a_jm = (sp_jm + sp_c) * 0.5;                    // (j-1, i)
+  const double a_jm_ip = (sp[jm * W + ip] + sp_ip) * 0.5;      // (j-1, i+1)
+  const double a_jp = (sp_jp + sp[jpp * W + i]) * 0.5;         // (j+1, i)
+  const bool zero_v = j == g.zero_v_row || j == g.zero_v_row2;
+  // sd of the three columns the vertical fluxes need is rebuilt from pit and the running sums of conv (see the
+  // LDGSTS kernel above)
+  const double pit_c = pit[e_c], pit_ip = pit[j * W + ip], pit_jp = pit[jp * W + i];
+  const double rdxj_jp = g.rdx_j[jp];
+  double pre_c = 0.0, pre_ip = 0.0, pre_jp = 0.0;
+  // layer L-1 pairs with layer 0 through the bottom of layer 0 (np.roll), times sd[0] = 0
+  const double u_top = fld[0][(L - 1) * plane + e_c], v_top = fld[1][(L - 1) * plane + e_c],
+               t_top = fld[2][(L - 1) * plane + e_c], q_top = fld[3][(L - 1) * plane + e_c];
+
+  gcm_mbar_wait(&bars[0], 0);
+  if (edge) fixup(0, 0);
+  double u_k = 0.0, v_k = 0.0, t_k = 0.0, q_k = 0.0;
+  double fu = 0.0, fv_ = 0.0, ft = 0.0, fq = 0.0, fu0 = 0.0, fv0 = 0.0, ft0 = 0.0, fq0 = 0.0;
+  double sd_c = 0.0, sd_ip = 0.0, sd_jp = 0.0;  // level 0
+  bool bad = active && gcm_not_finite(pn_c);
+
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    if (k + 1 < L) {  // the next layer's centre values feed the fluxes through the top of layer k
+      gcm_mbar_wait(&bars[(k + 1) % PFT_NS], ((k + 1) / PFT_NS) & 1);
+      if (edge) fixup(k + 1, (k + 1) % PFT_NS);
+    }
+    __syncthreads();  // stages of layers k and k + 1 are complete and patched; the stage of layer k - 1 is free
+    if (k + 2 < L) issue(k + 2, (k + 2) % PFT_NS);
+    const double* sk = sm + (k % PFT_NS) * STAGE;
+    const double* sn = sm + ((k + 1) % PFT_NS) * STAGE;
+    if (k == 0) {
+      u_k = sk[0 * HT + t_c]; v_k = sk[1 * HT + t_c]; t_k = sk[2 * HT + t_c]; q_k = sk[3 * HT + t_c];
+      fu = (u_k + u_top) * 0.5 * ((sd_c + sd_ip) * 0.5);
+      fv_ = (v_k + v_top) * 0.5 * ((sd_c + sd_jp) * 0.5);
+      ft = (t_k + t_top) * 0.5 * sd_c;
+      fq = (q_k + q_top) * 0.5 * sd_c;
+      fu0 = fu; fv0 = fv_; ft0 = ft; fq0 = fq;
+    }
+    const int e = k * plane + e_c;
+    const double* ck = sk + PFT_NF * HT + c_c;
+    const double own_pgf = ck[0 * CT], own_fv = ck[1 * CT];
+    const double own_u = SAME ? u_k : ck[2 * CT], own_v = SAME ? v_k : ck[3 * CT];
+    const double own_t = SAME ? t_k : ck[4 * CT], own_q = SAME ? q_k : ck[5 * CT];
+    // horizontal neighbours from the tile
+    const double* su_ = sk + 0 * HT + t_c;
+    const double* sv_ = sk + 1 * HT + t_c;
+    const double* st_ = sk + 2 * HT + t_c;
+    const double* sq_ = sk + 3 * HT + t_c;
+    const double* pu_ = sk + 4 * HT + t_c;
+    const double u_im = su_[-1], u_ip = su_[1], u_jp = su_[PFT_ROW], u_jm = su_[-PFT_ROW];
+    const double v_im = sv_[-1], v_ip = sv_[1], v_jp = sv_[PFT_ROW], v_jm = sv_[-PFT_ROW], v_jm_ip = sv_[1 - PFT_ROW];
+    const double pu_c = pu_[0], pu_im = pu_[-1], pu_ip = pu_[1], pu_jp = pu_[PFT_ROW], pu_jp_im = pu_[PFT_ROW - 1];
+    const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
+                 pv_jp = v_jp * a_jp;
+
+    // fluxes through the top of layer k (advec_sig, dynamics.py:49-52) with sd at level k + 1
+    double fu_n = fu0, fv_n = fv0, ft_n = ft0, fq_n = fq0;
+    double u_kp = 0.0, v_kp = 0.0, t_kp = 0.0, q_kp = 0.0;
+    if (k + 1 < L) {
+      const double ds = g.c_dsig[k], sb = g.c_sigb[k + 1];
+      pre_c += ((pu_c - pu_im) * rdxj + (pv_c - pv_jm) * rdy) * ds;           // conv of (j, i)      dynamics.py:39
+      pre_ip += ((pu_ip - pu_c) * rdxj + (pv_ip - pv_jm_ip) * rdy) * ds;      //         (j, i+1)
+      pre_jp += ((pu_jp - pu_jp_im) * rdxj_jp + (pv_jp - pv_c) * rdy) * ds;   //         (j+1, i)
+      sd_c = (pit_c - pre_c) - pit_c * sb;
+      sd_ip = (pit_ip - pre_ip) - pit_ip * sb;
+      sd_jp = (pit_jp - pre_jp) - pit_jp * sb;
+      u_kp = sn[0 * HT + t_c]; v_kp = sn[1 * HT + t_c]; t_kp = sn[2 * HT + t_c]; q_kp = sn[3 * HT + t_c];
+      fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
+      fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
+      ft_n = (t_kp + t_k) * 0.5 * sd_c;
+      fq_n = (q_kp + q_k) * 0.5 * sd_c;
+    }
+    const double rds = g.c_rdsig[k];
+    const double dus = (fu_n - fu) * rds, dvs = (fv_n - fv_) * rds;  // -(F_k - F_k+1) / dsig
+    const double ads_t = (ft_n - ft) * rds, ads_q = (fq_n - fq) * rds;
+
+    // advec_m_pu (dynamics.py:55-108); (a/2)(b/2) = ab/4 exactly
+    const double puum = (u_k + u_im) * (pu_c + pu_im), puup = (u_ip + u_k) * (pu_ip + pu_c);
+    const double puvp = (pv_c + pv_ip) * (u_k + u_jp), puvm = (pv_jm + pv_jm_ip) * (u_jm + u_k);
+    const double dut = ((puum - puup) * rdxj + (puvm - puvp) * rdy) * 0.25;
+    const double pvvm = (v_k + v_jm) * (pv_c + pv_jm), pvvp = (v_jp + v_k) * (pv_jp + pv_c);
+    const double pvup = (v_k + v_ip) * (pu_c + pu_jp), pvum = (v_im + v_k) * (pu_im + pu_jp_im);
+    const double dvt = ((pvvm - pvvp) * rdy + (pvum - pvup) * rdxh) * 0.25;
+
+    const double pu_n = own_u * pu_fac - (dut + dus + own_pgf) * dt;  // dynamics.py:206
+    const double pv_n = own_v * pv_fac - (dvt + dvs + own_fv) * dt;   // dynamics.py:207
+    double v_n = pv_n * r_pnv;
+    if (zero_v) v_n *= 0.0;  // dynamics.py:222
+    // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
+    const double adv_t = ((pu_c * (t_k + st_[1]) - pu_im * (st_[-1] + t_k)) * rdxj +
+                          (pv_c * (t_k + st_[PFT_ROW]) - pv_jm * (st_[-PFT_ROW] + t_k)) * rdy) * 0.5;
+    const double adv_q = ((pu_c * (q_k + sq_[1]) - pu_im * (sq_[-1] + q_k)) * rdxj +
+                          (pv_c * (q_k + sq_[PFT_ROW]) - pv_jm * (sq_[-PFT_ROW] + q_k)) * rdy) * 0.5;
+    if (active) {
+      const double u_n = pu_n * r_pnu;
+      const double t_n = (own_t * p_c - (adv_t + ads_t) * dt) * r_pn;
+      const double q_n = (own_q * p_c - (adv_q + ads_q) * dt) * r_pn;
+      ou[e] = u_n;
+      ov[e] = v_n;
+      ot[e] = t_n;
+      oq[e] = q_n;
+      bad |= gcm_not_finite((u_n + v_n) + (t_n + q_n));
+    }
+    fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
+    u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
+  }
+  if (active) out.p[o2 + e_c] = pn_c;
+  gcm_flag_nonfinite(g.nonfinite, bad);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -891,7 +1110,7 @@ int g_gcm_knob[10] = {0};
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
 //   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream
 //   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update;
-//      3 = the one-thread-per-cell update for every member count
+//      3 = the one-thread-per-cell update for every member count; 4 = the LDGSTS tiled update instead of the TMA one
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
 //   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel)
@@ -1033,7 +1252,47 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     }
 #endif
   }
-  if (nrowsU > 0 && tiled) {
+  // TMA update (default for W % 32 == 0): tensor maps of the 11 fields (cached per pointer); knob 4 = 4 keeps the
+  // LDGSTS kernel (A/B), as does a driver without cuTensorMapEncodeTiled
+  bool tma = tiled && g_gcm_knob[4] != 4 && (size_t)nbatch * L < 2147483647u;
+  PfTmaMaps maps;
+  constexpr int tjt = 4;
+  if (tma && nrowsU > 0) {
+    const double* hf[PFT_NF] = {star->u, star->v, star->t, star->q, w.spu};
+    const double* cf[6] = {w.pgf, w.fv, base->u, base->v, base->t, base->q};
+    for (int f = 0; f < PFT_NF && tma; ++f)
+      tma = gcm_tmap_get(&maps.halo[f], hf[f], W, H, nbatch * L, PFT_ROW, tjt + 2) == GCM_OK;
+    for (int f = 0; f < 6 && tma; ++f) tma = gcm_tmap_get(&maps.cen[f], cf[f], W, H, nbatch * L, PFT_TI, tjt) == GCM_OK;
+  }
+  if (nrowsU > 0 && tma) {
+    GcmProfScope ps(GCM_K_UPDATE_TMA, stream);
+    const bool same = base->u == star->u && base->v == star->v && base->t == star->t && base->q == star->q;
+    const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
+    constexpr int HT = ((tjt + 2) * PFT_ROW + 15) / 16 * 16, CT = tjt * PFT_TI;
+    const size_t smt = 128 + (size_t)PFT_NS * (PFT_NF * HT + (same ? 2 : 6) * CT) * sizeof(double);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (parts[s2].n1 <= 0) continue;
+      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tjt - 1) / tjt, nbatch), blockt(PFT_TI, tjt);
+      if (same) {
+#ifndef GCM_EMU
+        if (smt > 48 * 1024)
+          GCM_CUDA(cudaFuncSetAttribute(pe25f_update_tma_kernel<L, tjt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smt));
+#endif
+        GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, tjt, true>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, dt,
+                       parts[s2], b2, b3);
+      } else {
+#ifndef GCM_EMU
+        if (smt > 48 * 1024)
+          GCM_CUDA(cudaFuncSetAttribute(pe25f_update_tma_kernel<L, tjt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smt));
+#endif
+        GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, tjt, false>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, dt,
+                       parts[s2], b2, b3);
+      }
+      GCM_CHECK_LAUNCH();
+    }
+  } else if (nrowsU > 0 && tiled) {
     GcmProfScope ps(GCM_K_UPDATE_TILED, stream);
     // a tile needs contiguous rows: a two-segment launch becomes one launch per segment (same kernel for every
     // row, so a band stays bit-identical to the whole grid)

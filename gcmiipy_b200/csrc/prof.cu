@@ -52,6 +52,7 @@ extern "C" const char* gcm_prof_kind_name(int kind) {
     case GCM_K_FILTER_B: return "pe25f_filter_kernel<0>";
     case GCM_K_EXTRAS: return "pe25x_extras_kernel";
     case GCM_K_HALO: return "halo_exchange";
+    case GCM_K_UPDATE_TMA: return "pe25f_update_tma_kernel";
     default: return "?";
   }
 }

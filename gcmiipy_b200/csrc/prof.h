@@ -17,7 +17,8 @@ enum GcmProfKind {
   GCM_K_UPDATE_TILED = 10,  // pe25f_update_tiled_kernel
   GCM_K_EXTRAS = 11,        // pe25x_extras_kernel (pe25_extras.cu, opt-in terms)
   GCM_K_HALO = 12,          // one halo exchange of a latitude band: pack + NCCL / peer copies + unpack (comm.cu)
-  GCM_K_COUNT = 13
+  GCM_K_UPDATE_TMA = 13,    // pe25f_update_tma_kernel (TMA box loads + mbarrier)
+  GCM_K_COUNT = 14
 };
 
 #ifdef GCM_EMU
