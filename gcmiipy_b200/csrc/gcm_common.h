@@ -5,6 +5,8 @@
 
 #include "gcm_b200.h"
 
+#define GCM_NKNOBS 16  // tuning knobs (gcm_tuning_knob)
+
 #ifdef GCM_EMU
 #include "cuda_emu.h"  // tests/emu: CPU execution of these sources for the no-GPU test-suite only
 #define GCM_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -38,7 +40,7 @@ static inline void gcm_launch_dep(bool pdl, void (*kern)(KArgs...), dim3 grid, d
   cfg.numAttrs = pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
-extern int g_gcm_knob[10];
+extern int g_gcm_knob[GCM_NKNOBS];
 #define GCM_LAUNCH_DEP(kern, grid, block, smem, stream, ...) \
   gcm_launch_dep(g_gcm_knob[9] != 3, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif

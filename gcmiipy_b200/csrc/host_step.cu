@@ -19,7 +19,7 @@ extern "C" int gcm_pe25_half_step_rows(const gcm_geom*, const gcm_state*, const 
 extern "C" int gcm_pe25_matsuno_step(const gcm_geom*, const gcm_state*, const gcm_state*, double, int, int, void*, size_t,
                                      void*);
 bool gcm_pe25_fast_supported(const gcm_geom* g);
-extern int g_gcm_knob[10];  // pe25_fast.cu; knob 6 = latitude blocks of the host-resident step
+extern int g_gcm_knob[GCM_NKNOBS];  // pe25_fast.cu; knob 6 = latitude blocks of the host-resident step
 
 #define GCM_HOST_MAX_BLOCKS 64
 

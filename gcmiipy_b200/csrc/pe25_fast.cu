@@ -899,14 +899,14 @@ struct PfTmaMaps {
   GcmTmap cen[6];        // pgf, fv, u, v, t, q: box 32 x TJ x 1
 };
 
-template <int L, int PFT_TJ, bool SAME>
+template <int L, int PFT_TJ, bool SAME, int NS>
 __global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
 pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, PfConst base, PfConst star, PfMut out,
                         PfWork w, double dt, GcmRowSeg seg, size_t bstride2, size_t bstride3) {
   if (g.pdl_early) gcm_pdl_trigger();
   gcm_pdl_wait();
   GCM_DYN_SMEM(unsigned char, smraw);
-  GcmMbar* bars = reinterpret_cast<GcmMbar*>(smraw);  // PFT_NS barriers in the first 128 bytes
+  GcmMbar* bars = reinterpret_cast<GcmMbar*>(smraw);  // NS barriers in the first 128 bytes
   double* sm = reinterpret_cast<double*>(smraw + 128);
   constexpr int HBOX = (PFT_TJ + 2) * PFT_ROW;        // doubles a halo box delivers
   constexpr int HT = (HBOX + 15) / 16 * 16;           // halo tile pitch: box destinations are 128-byte aligned
@@ -936,7 +936,7 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
   double* __restrict__ oq = out.q + o3;
 
   if (tid == 0) {
-    for (int s = 0; s < PFT_NS; ++s) gcm_mbar_init(&bars[s], 1);
+    for (int s = 0; s < NS; ++s) gcm_mbar_init(&bars[s], 1);
     gcm_mbar_fence_init();
   }
   __syncthreads();
@@ -952,24 +952,34 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
         gcm_tma_load3(st + PFT_NF * HT + f * CT, &maps.cen[f], blockIdx.x * PFT_TI, j0, zb + k, &bars[s]);
     }
   };
-  // CTAs whose halo box leaves the grid patch the zero-filled part with the periodic neighbour (rows only on a whole
-  // grid: a band stores its halo rows, and rows outside it are never used by an active thread)
-  const bool edge = blockIdx.x == 0 || blockIdx.x + 1 == gridDim.x || (wrap && (j0 - 1 < 0 || j0 + PFT_TJ + 1 > H));
+  // CTAs whose halo box leaves the grid patch the zero-filled part with the periodic neighbour
+  const bool edge_w = blockIdx.x == 0, edge_e = blockIdx.x + 1 == gridDim.x;
+  const bool edge_j = wrap && (j0 - 1 < 0 || j0 + PFT_TJ + 1 > H);
+  auto patch = [&](int k, double* st, int dr, int c) {  // tile element (dr, c) <- its periodic image
+    int gj = j0 - 1 + dr, gi = x0 + c;
+    if (gj < 0 || gj >= H) {
+      if (!wrap) return;  // a band stores its halo rows; rows outside it are never used by an active thread
+      gj = ((gj % H) + H) % H;
+    }
+    gi = gi < 0 ? gi + W : (gi >= W ? gi - W : gi);
+    const int src = k * plane + gj * W + gi, rr = dr * PFT_ROW + c;
+#pragma unroll
+    for (int f = 0; f < PFT_NF; ++f) st[f * HT + rr] = fld[f][src];
+  };
   auto fixup = [&](int k, int s) {
     double* st = sm + s * STAGE;
-    for (int rr = tid; rr < HBOX; rr += PFT_TI * PFT_TJ) {
-      const int dr = rr / PFT_ROW, c = rr - dr * PFT_ROW;
-      int gj = j0 - 1 + dr, gi = x0 + c;
-      const bool oj = gj < 0 || gj >= H, oi = gi < 0 || gi >= W;
-      if (!oj && !oi) continue;
-      if (oj) {
-        if (!wrap) continue;
-        gj = ((gj % H) + H) % H;
+    if (edge_w || edge_e) {  // the halo column beyond the seam: tile column 1 (i = -1) / 34 (i = W)
+      if (tid < 2 * (PFT_TJ + 2)) {
+        const int side = tid / (PFT_TJ + 2), dr = tid - side * (PFT_TJ + 2);
+        if (side == 0 ? edge_w : edge_e) patch(k, st, dr, side == 0 ? 1 : PFT_TI + 2);
       }
-      if (oi) gi = gi < 0 ? gi + W : gi - W;
-      const int src = k * plane + gj * W + gi;
-#pragma unroll
-      for (int f = 0; f < PFT_NF; ++f) st[f * HT + rr] = fld[f][src];
+    }
+    if (edge_j) {  // whole rows beyond the first / last row of a periodic grid
+      for (int dr = 0; dr < PFT_TJ + 2; ++dr) {
+        const int gj = j0 - 1 + dr;
+        if (gj >= 0 && gj < H) continue;
+        if (tid >= 1 && tid <= PFT_TI + 2) patch(k, st, dr, tid);
+      }
     }
   };
   issue(0, 0);
@@ -1005,7 +1015,7 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
                t_top = fld[2][(L - 1) * plane + e_c], q_top = fld[3][(L - 1) * plane + e_c];
 
   gcm_mbar_wait(&bars[0], 0);
-  if (edge) fixup(0, 0);
+  if (edge_w || edge_e || edge_j) fixup(0, 0);
   double u_k = 0.0, v_k = 0.0, t_k = 0.0, q_k = 0.0;
   double fu = 0.0, fv_ = 0.0, ft = 0.0, fq = 0.0, fu0 = 0.0, fv0 = 0.0, ft0 = 0.0, fq0 = 0.0;
   double sd_c = 0.0, sd_ip = 0.0, sd_jp = 0.0;  // level 0
@@ -1014,13 +1024,13 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
 #pragma unroll
   for (int k = 0; k < L; ++k) {
     if (k + 1 < L) {  // the next layer's centre values feed the fluxes through the top of layer k
-      gcm_mbar_wait(&bars[(k + 1) % PFT_NS], ((k + 1) / PFT_NS) & 1);
-      if (edge) fixup(k + 1, (k + 1) % PFT_NS);
+      gcm_mbar_wait(&bars[(k + 1) % NS], ((k + 1) / NS) & 1);
+      if (edge_w || edge_e || edge_j) fixup(k + 1, (k + 1) % NS);
     }
     __syncthreads();  // stages of layers k and k + 1 are complete and patched; the stage of layer k - 1 is free
-    if (k + 2 < L) issue(k + 2, (k + 2) % PFT_NS);
-    const double* sk = sm + (k % PFT_NS) * STAGE;
-    const double* sn = sm + ((k + 1) % PFT_NS) * STAGE;
+    if (k + 2 < L) issue(k + 2, (k + 2) % NS);
+    const double* sk = sm + (k % NS) * STAGE;
+    const double* sn = sm + ((k + 1) % NS) * STAGE;
     if (k == 0) {
       u_k = sk[0 * HT + t_c]; v_k = sk[1 * HT + t_c]; t_k = sk[2 * HT + t_c]; q_k = sk[3 * HT + t_c];
       fu = (u_k + u_top) * 0.5 * ((sd_c + sd_ip) * 0.5);
@@ -1104,7 +1114,7 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int g_gcm_knob[10] = {0};
+int g_gcm_knob[GCM_NKNOBS] = {0};
 
 // tuning knobs (bench.py --knob i=v; 0 = automatic):
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
@@ -1118,8 +1128,10 @@ int g_gcm_knob[10] = {0};
 //   9  programmatic dependent launch of the half-step kernels: 0 / 1 = on (a kernel's launch overlaps the drain of its
 //      predecessor in the stream: -3 ... -5 % per step, r03e), 2 = on + every kernel triggers its dependents at entry
 //      (waiting CTAs then hold SM slots the running kernel could use: slower on most grids), 3 = off
+//  10  TMA update kernel: layers in flight (2..4; 0 = 3)     11  TMA update kernel: tile rows (8; 0 = 4)
+//  12  L2 promotion of the tensor maps: 0 = 128 B, 1 = none, 2 = 256 B
 extern "C" int gcm_tuning_knob(int idx, int value) {
-  GCM_REQUIRE(idx >= 0 && idx < 10, GCM_ESHAPE);
+  GCM_REQUIRE(idx >= 0 && idx < GCM_NKNOBS, GCM_ESHAPE);
   g_gcm_knob[idx] = value;
   ++g_gcm_tuning_epoch;
   return GCM_OK;
@@ -1256,7 +1268,8 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   // LDGSTS kernel (A/B), as does a driver without cuTensorMapEncodeTiled
   bool tma = tiled && g_gcm_knob[4] != 4 && (size_t)nbatch * L < 2147483647u;
   PfTmaMaps maps;
-  constexpr int tjt = 4;
+  const int tjt = g_gcm_knob[11] == 8 ? 8 : 4;                          // tile rows
+  const int nst = g_gcm_knob[10] >= 2 && g_gcm_knob[10] <= 4 ? g_gcm_knob[10] : 3;  // layers in flight
   if (tma && nrowsU > 0) {
     const double* hf[PFT_NF] = {star->u, star->v, star->t, star->q, w.spu};
     const double* cf[6] = {w.pgf, w.fv, base->u, base->v, base->t, base->q};
@@ -1268,27 +1281,33 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     GcmProfScope ps(GCM_K_UPDATE_TMA, stream);
     const bool same = base->u == star->u && base->v == star->v && base->t == star->t && base->q == star->q;
     const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
-    constexpr int HT = ((tjt + 2) * PFT_ROW + 15) / 16 * 16, CT = tjt * PFT_TI;
-    const size_t smt = 128 + (size_t)PFT_NS * (PFT_NF * HT + (same ? 2 : 6) * CT) * sizeof(double);
+    const int HT = ((tjt + 2) * PFT_ROW + 15) / 16 * 16, CT = tjt * PFT_TI;
+    const size_t smt = 128 + (size_t)nst * (PFT_NF * HT + (same ? 2 : 6) * CT) * sizeof(double);
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
       const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tjt - 1) / tjt, nbatch), blockt(PFT_TI, tjt);
-      if (same) {
 #ifndef GCM_EMU
-        if (smt > 48 * 1024)
-          GCM_CUDA(cudaFuncSetAttribute(pe25f_update_tma_kernel<L, tjt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smt));
+#define PF_TMA_ATTR(K) \
+  if (smt > 48 * 1024) GCM_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt))
+#else
+#define PF_TMA_ATTR(K)
 #endif
-        GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, tjt, true>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, dt,
-                       parts[s2], b2, b3);
+#define PF_TMA_GO(TJ_, SAME_, NS_)                                                                                   \
+  do {                                                                                                               \
+    PF_TMA_ATTR((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_>));                                                      \
+    GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, \
+                   dt, parts[s2], b2, b3);                                                                           \
+  } while (0)
+#define PF_TMA_NS(TJ_, SAME_)               \
+  do {                                      \
+    if (nst == 2) PF_TMA_GO(TJ_, SAME_, 2); \
+    else if (nst == 4) PF_TMA_GO(TJ_, SAME_, 4); \
+    else PF_TMA_GO(TJ_, SAME_, 3);          \
+  } while (0)
+      if (tjt == 8) {
+        if (same) PF_TMA_NS(8, true); else PF_TMA_NS(8, false);
       } else {
-#ifndef GCM_EMU
-        if (smt > 48 * 1024)
-          GCM_CUDA(cudaFuncSetAttribute(pe25f_update_tma_kernel<L, tjt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smt));
-#endif
-        GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, tjt, false>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, dt,
-                       parts[s2], b2, b3);
+        if (same) PF_TMA_NS(4, true); else PF_TMA_NS(4, false);
       }
       GCM_CHECK_LAUNCH();
     }

@@ -23,6 +23,7 @@ struct TmapEntry {
   const double* base;
   int W, H, NZ, bw, bh;
   unsigned long long stamp;
+  int epoch;  // tuning epoch the map was encoded under (knob 12 = L2 promotion)
   CUtensorMap map;
 };
 #define GCM_TMAP_CACHE 64
@@ -53,7 +54,7 @@ int gcm_tmap_get(GcmTmap* out, const double* base, int W, int H, int NZ, int bw,
   int victim = 0;
   for (int e = 0; e < GCM_TMAP_CACHE; ++e) {
     TmapEntry& t = g_cache[e];
-    if (t.base == base && t.W == W && t.H == H && t.NZ == NZ && t.bw == bw && t.bh == bh) {
+    if (t.base == base && t.W == W && t.H == H && t.NZ == NZ && t.bw == bw && t.bh == bh && t.epoch == g_gcm_tuning_epoch) {
       t.stamp = ++g_stamp;
       memcpy(out, &t.map, sizeof(CUtensorMap));
       return GCM_OK;
@@ -66,12 +67,16 @@ int gcm_tmap_get(GcmTmap* out, const double* base, int W, int H, int NZ, int bw,
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   CUtensorMap m;
   const CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              g_gcm_knob[12] == 1 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                                  : (g_gcm_knob[12] == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                                         : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GCM_REQUIRE(r == CUDA_SUCCESS, GCM_EUNSUP);
   TmapEntry& t = g_cache[victim];
   t.base = base; t.W = W; t.H = H; t.NZ = NZ; t.bw = bw; t.bh = bh;
   t.stamp = ++g_stamp;
+  t.epoch = g_gcm_tuning_epoch;
   t.map = m;
   memcpy(out, &m, sizeof(CUtensorMap));
   return GCM_OK;

@@ -590,3 +590,31 @@ def test_nonfinite_watch_and_last_status(backend):
     assert watch.last_status() == -2
     assert _lib.lib().gcm_tuning_knob(0, 0) == 0
     assert watch.last_status(clear=True) == -2 and watch.last_status() == 0
+
+
+@pytest.mark.parametrize("knobs", [{}, {4: 4}, {10: 2}, {10: 4}, {11: 8}, {11: 8, 10: 2}, {12: 1}])
+@pytest.mark.parametrize("H,W", [(10, 64), (3, 32)])
+def test_tma_update_variants_vs_oracle(backend, knobs, H, W):
+    """pe25f_update_tma_kernel (TMA box loads on mbarriers): default 3 layers in flight, 32 x 4 tiles; knob 10 = layers
+    in flight, knob 11 = 8 tile rows, knob 12 = L2 promotion of the tensor maps, knob 4 = 4 the LDGSTS kernel.  Two tile
+    columns / one (both seams in one CTA), partial tiles in j, the periodic wrap in i and j patched by the seam CTAs."""
+    from gcmiipy_b200 import _lib
+    geom = geometry.gen_geometry(H, W, 9, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, 9, sig_func=O.manabe_sig)
+    hm = 50.0 * np.random.default_rng(H).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    s = list(O.synthetic_state(og, seed=H * W))
+    s[2] = s[2] + 0.3 * np.random.default_rng(1).standard_normal(s[2].shape)   # v != 0 on the wall row: the j wrap matters
+    try:
+        for k, v in knobs.items():
+            assert _lib.lib().gcm_tuning_knob(k, v) == 0
+        st = dynamics.Stepper(geom, *s)
+        st.step(20.0, 3)
+        got = st.download()
+    finally:
+        for k in knobs:
+            _lib.lib().gcm_tuning_knob(k, 0)
+    ref = tuple(s)
+    for _ in range(3):
+        ref = O.matsuno_timestep(*ref, 20.0, og)
+    check_state(got, ref, TOL_RUN)
