@@ -91,6 +91,7 @@ class BandStepper:
         self.nsteps_done = 0
         self.overlap = True
         self.comm = None
+        self.peer = False
         if native:
             self._make_comm()
 
@@ -106,14 +107,48 @@ class BandStepper:
         dist.broadcast(t, src, group=self.group)
         return (ctypes.c_ubyte * 128)(*t.cpu().tolist())
 
-    def _make_comm(self):
+    def _make_comm(self, nccl=True, peer=None):
+        """The library-side ring: an NCCL communicator (fallback transport) and, on CUDA with more than one rank, the
+        peer mailboxes (NVLink peer stores, csrc/comm.cu) -- GCM_BAND_PEER=0 in the environment keeps NCCL."""
+        import os
         lib = _lib.lib()
-        idbuf = (ctypes.c_ubyte * 128)()
-        if self.world > 1:
+        idbuf = None
+        if self.world > 1 and nccl:
             idbuf = self._share_id(lambda b: _lib.check(lib.gcm_comm_unique_id(b), "gcm_comm_unique_id"))
         h = ctypes.c_void_p()
         _lib.check(lib.gcm_comm_create(self.world, self.rank, idbuf, ctypes.byref(h)), "gcm_comm_create")
         self.comm = h
+        if peer is None:
+            peer = self.world > 1 and nccl and os.environ.get("GCM_BAND_PEER", "1") != "0"
+        if peer:
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Exchange the CUDA IPC handles of the mailboxes over torch.distributed and map the ring neighbours'.  Every
+        rank must succeed, else every rank stays on NCCL (one all-reduce decides)."""
+        lib = _lib.lib()
+        handle = (ctypes.c_ubyte * 64)()
+        ok = lib.gcm_comm_peer_setup(self.comm, self.dg.handle, handle) == 0
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=_lib.device())
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        if ok:
+            hn = (ctypes.c_ubyte * 64)(*allh[self.north].cpu().tolist())
+            hs = (ctypes.c_ubyte * 64)(*allh[self.south].cpu().tolist())
+            ok = lib.gcm_comm_peer_connect(self.comm, hn, hs, 0) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=_lib.device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.peer = bool(flag.item())
+        if not self.peer:           # somebody could not map a neighbour: drop the ring and rebuild it on NCCL only
+            lib.gcm_comm_destroy(self.comm)
+            self.comm = None
+            self._make_comm(nccl=True, peer=False)
+
+    def peer_timeouts(self):
+        """Pull kernels of this rank that gave up waiting for a neighbour's halo rows (0 on a healthy ring)."""
+        n = ctypes.c_uint(0)
+        _lib.lib().gcm_comm_peer_status(self.comm, ctypes.byref(n))
+        return int(n.value)
 
     def __del__(self):
         try:

@@ -28,6 +28,8 @@ extern "C" int gcm_pe25_half_step(const gcm_geom*, const gcm_state*, const gcm_s
 extern "C" int gcm_pe25_half_step_rows(const gcm_geom*, const gcm_state*, const gcm_state*, const gcm_state*, double, int,
                                        void*, size_t, const int*, const int*, void*);
 
+extern "C" size_t gcm_halo_buffer_doubles(const gcm_geom* g, int nrows);
+
 #define GCM_HALO_N 1
 #define GCM_HALO_S 2
 #define GCM_ENCCL_BASE 1000000  // status = GCM_ENCCL_BASE + ncclResult_t
@@ -88,7 +90,27 @@ struct gcm_comm {
   cudaEvent_t ev_ready, ev_halo, ev_rint;
   double* buf;                  // send_n | send_s | recv_s | recv_n
   size_t buf_doubles;
+  // Peer-memory halo exchange (NVLink peer stores instead of NCCL): every rank owns a MAILBOX (cudaMalloc, exported
+  // with cudaIpcGetMemHandle); the neighbours map it and write my halo rows straight into it, then raise a flag in it.
+  unsigned char* mbox;          // my mailbox: GcmMboxHeader | slot 0 | slot 1, slot = rows from north | rows from south
+  size_t mbox_bytes;
+  size_t part_n, part_s;        // doubles per slot part: halo rows from the north / from the south neighbour
+  int mb_hn, mb_hs, mb_W, mb_L; // halo layout the mailbox was sized for
+  unsigned char* peer_n;        // the north / south neighbour's mailbox as mapped into this process
+  unsigned char* peer_s;
+  int peer_mode;                // 0 = NCCL, 1 = mapped through CUDA IPC, 2 = plain pointers of the same process (tests)
+  int push_blocks;              // grid of the push kernel (the ticket of its last block closes the message)
 };
+
+// first 256 bytes of a mailbox
+struct GcmMboxHeader {
+  unsigned long long flag_from_n;  // sequence number of the newest complete message from the north neighbour
+  unsigned long long flag_from_s;  //                                              ... from the south neighbour
+  unsigned long long seq;          // messages this rank has sent (local)
+  unsigned int ticket;             // finished blocks of the running push kernel (local)
+  unsigned int timeouts;           // pull kernels that gave up waiting (local; reported by gcm_comm_peer_status)
+};
+#define GCM_MBOX_HDR 256
 
 extern "C" int gcm_comm_unique_id(unsigned char* out128) {
   GCM_REQUIRE(out128, GCM_ENULL);
@@ -109,8 +131,8 @@ extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128,
   c->nranks = nranks;
   c->rank = rank;
 #ifndef GCM_EMU
-  if (nranks > 1) {
-    int st = id128 ? gcm_nccl_load() : GCM_ENULL;
+  if (nranks > 1 && id128) {  // id128 == NULL: no NCCL communicator, the ring runs on peer mailboxes only
+    int st = gcm_nccl_load();
     if (st) { free(c); return st; }
     gcm_nccl_id id;
     memcpy(id.internal, id128, 128);
@@ -123,8 +145,7 @@ extern "C" int gcm_comm_create(int nranks, int rank, const unsigned char* id128,
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rint, cudaEventDisableTiming);
   if (e != cudaSuccess) { gcm_comm_destroy(c); return gcm_set_status((int)e); }  // frees whatever exists so far
 #else
-  (void)id128;
-  GCM_REQUIRE(nranks == 1, GCM_EUNSUP);
+  (void)id128;  // no NCCL on the emulator build: ranks > 1 exist only for the same-process peer-mailbox tests
 #endif
   *out = c;
   return GCM_OK;
@@ -140,8 +161,89 @@ extern "C" int gcm_comm_destroy(gcm_comm* c) {
   if (c->ev_rint) cudaEventDestroy(c->ev_rint);
 #endif
   if (c->buf) cudaFree(c->buf);
+#ifndef GCM_EMU
+  if (c->peer_mode == 1) {
+    if (c->peer_n) cudaIpcCloseMemHandle(c->peer_n);
+    if (c->peer_s && c->peer_s != c->peer_n) cudaIpcCloseMemHandle(c->peer_s);
+  }
+#endif
+  if (c->mbox) cudaFree(c->mbox);
   free(c);
   return GCM_OK;
+}
+
+// ---- peer-memory mailbox ----------------------------------------------------------------------------------------
+// Allocates this rank's mailbox for the halo layout of band geometry `g` and writes its 64-byte CUDA IPC handle to
+// handle64 (zeros on the emulator build).  The caller ships the handles over its own control plane
+// (bands.BandStepper: one all_gather) and calls gcm_comm_peer_connect.
+extern "C" int gcm_comm_peer_setup(gcm_comm* c, const gcm_geom* g, unsigned char* handle64) {
+  GCM_REQUIRE(c && g && handle64, GCM_ENULL);
+  GCM_REQUIRE(!g->d.wrap_j && !c->mbox, GCM_EUNSUP);
+  const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi;
+  c->mb_hn = hn; c->mb_hs = hs; c->mb_W = g->d.W; c->mb_L = g->d.L;
+  c->part_n = gcm_halo_buffer_doubles(g, hn);
+  c->part_s = gcm_halo_buffer_doubles(g, hs);
+  c->mbox_bytes = GCM_MBOX_HDR + 2 * (c->part_n + c->part_s) * sizeof(double);
+  GCM_CUDA(cudaMalloc((void**)&c->mbox, c->mbox_bytes));
+  GCM_CUDA(cudaMemset(c->mbox, 0, c->mbox_bytes));
+  memset(handle64, 0, 64);
+#ifndef GCM_EMU
+  cudaIpcMemHandle_t h;
+  GCM_CUDA(cudaIpcGetMemHandle(&h, c->mbox));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &h, 64);
+#endif
+  return GCM_OK;
+}
+
+// Maps the neighbours' mailboxes (IPC handles from their gcm_comm_peer_setup).  same_process != 0: the two arguments
+// are gcm_comm* of this process instead (single-process tests of the protocol: ranks stepped one after the other).
+extern "C" int gcm_comm_peer_connect(gcm_comm* c, const void* north, const void* south, int same_process) {
+  GCM_REQUIRE(c && north && south && c->mbox, GCM_ENULL);
+  GCM_REQUIRE(c->peer_mode == 0, GCM_EUNSUP);
+  if (same_process) {
+    const gcm_comm* cn = (const gcm_comm*)north;
+    const gcm_comm* cs = (const gcm_comm*)south;
+    GCM_REQUIRE(cn->mbox && cs->mbox && cn->mbox_bytes == c->mbox_bytes && cs->mbox_bytes == c->mbox_bytes, GCM_ESHAPE);
+    c->peer_n = cn->mbox;
+    c->peer_s = cs->mbox;
+    c->peer_mode = 2;
+    return GCM_OK;
+  }
+#ifdef GCM_EMU
+  return GCM_EUNSUP;
+#else
+  cudaIpcMemHandle_t hn_, hs_;
+  memcpy(&hn_, north, 64);
+  memcpy(&hs_, south, 64);
+  void *pn = nullptr, *ps = nullptr;
+  GCM_CUDA(cudaIpcOpenMemHandle(&pn, hn_, cudaIpcMemLazyEnablePeerAccess));
+  if (memcmp(north, south, 64) == 0) {
+    ps = pn;  // two ranks: both neighbours are the same rank; a handle is mapped once per process
+  } else {
+    cudaError_t e = cudaIpcOpenMemHandle(&ps, hs_, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaIpcCloseMemHandle(pn); return gcm_set_status((int)e); }
+  }
+  c->peer_n = (unsigned char*)pn;
+  c->peer_s = (unsigned char*)ps;
+  c->peer_mode = 1;
+  return GCM_OK;
+#endif
+}
+
+// 0 = NCCL, 1 = CUDA IPC peers, 2 = same-process peers; *timeouts (optional) = pull kernels that gave up waiting for a
+// neighbour (synchronises the device to read the counter)
+extern "C" int gcm_comm_peer_status(gcm_comm* c, unsigned int* timeouts) {
+  GCM_REQUIRE(c, GCM_ENULL);
+  if (timeouts) {
+    *timeouts = 0;
+    if (c->mbox) {
+      GcmMboxHeader h;
+      GCM_CUDA(cudaMemcpy(&h, c->mbox, sizeof(h), cudaMemcpyDeviceToHost));
+      *timeouts = h.timeouts;
+    }
+  }
+  return c->peer_mode;
 }
 
 extern "C" size_t gcm_halo_buffer_doubles(const gcm_geom* g, int nrows);
@@ -172,6 +274,153 @@ __global__ void band_halo2_kernel(gcm_state s, int H, int W, int L, GcmHaloJob a
   }
 }
 
+
+// ---- peer-memory exchange kernels ---------------------------------------------------------------------------------
+__device__ __forceinline__ void band_halo_copy(double* const* fld, int H, int W, int L, const GcmHaloJob& a,
+                                               const GcmHaloJob& b, int unpack) {
+  const size_t na = (size_t)a.nrows * W * (1 + 4 * (size_t)L), nb = (size_t)b.nrows * W * (1 + 4 * (size_t)L);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < na + nb; e += (size_t)gridDim.x * blockDim.x) {
+    const GcmHaloJob& jb = e < na ? a : b;
+    const size_t r0 = e < na ? e : e - na;
+    const size_t per_p = (size_t)jb.nrows * W, per_3 = (size_t)L * per_p;
+    int f;
+    size_t r;
+    if (r0 < per_p) { f = 0; r = r0; } else { f = 1 + (int)((r0 - per_p) / per_3); r = (r0 - per_p) % per_3; }
+    const int i = (int)(r % W), row = (int)((r / W) % jb.nrows), k = (int)(r / per_p);
+    const size_t in_state = ((size_t)k * H + jb.row0 + row) * W + i;
+    if (unpack) fld[f][in_state] = jb.buf[r0];
+    else jb.buf[r0] = fld[f][in_state];
+  }
+}
+
+__device__ __forceinline__ void gcm_fence_system() {
+#ifndef GCM_EMU
+  __threadfence_system();
+#else
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#endif
+}
+__device__ __forceinline__ unsigned long long gcm_load_sys(const unsigned long long* p) {
+#ifndef GCM_EMU
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_SEQ_CST);
+#endif
+}
+__device__ __forceinline__ void gcm_store_sys(unsigned long long* p, unsigned long long v) {
+#ifndef GCM_EMU
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
+#endif
+}
+
+// PUSH: my first owned rows -> the north neighbour's mailbox (its halo rows to the south), my last owned rows -> the
+// south neighbour's (its halo rows to the north), slot = parity of the message number.  The block that finishes last
+// publishes the message: system-wide fence, then the message number into both neighbours' flags.
+__global__ void band_push_kernel(gcm_state s, int H, int W, int L, GcmHaloJob to_n, GcmHaloJob to_s, size_t slot_doubles,
+                                 GcmMboxHeader* mine, GcmMboxHeader* north, GcmMboxHeader* south) {
+  __shared__ unsigned long long seq_s;
+  __shared__ int last_s;
+  if (threadIdx.x == 0) seq_s = mine->seq + 1;  // written only by the closing block of the previous push
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  to_n.buf += (seq & 1) * slot_doubles;
+  to_s.buf += (seq & 1) * slot_doubles;
+  double* fld[5] = {s.p, s.u, s.v, s.t, s.q};
+  band_halo_copy(fld, H, W, L, to_n, to_s, 0);
+  gcm_fence_system();  // my peer stores are performed before the ticket below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&mine->ticket, 1u);
+    last_s = t + 1 == gridDim.x;
+  }
+  __syncthreads();
+  if (last_s && threadIdx.x == 0) {
+    gcm_fence_system();  // every block's stores (ordered before its ticket) before the flags
+    mine->ticket = 0;
+    mine->seq = seq;
+    gcm_store_sys(&north->flag_from_s, seq);
+    gcm_store_sys(&south->flag_from_n, seq);
+  }
+}
+
+// PULL: wait until both neighbours have published message `seq` (my own count: every rank sends the same number of
+// messages), then copy my mailbox slot into my halo rows.  A bounded wait: a neighbour that never answers raises
+// `timeouts` instead of hanging the GPU.
+__global__ void band_pull_kernel(gcm_state s, int H, int W, int L, GcmHaloJob from_s, GcmHaloJob from_n,
+                                 size_t slot_doubles, GcmMboxHeader* mine) {
+  __shared__ unsigned long long seq_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = mine->seq;
+    bool ok = false;
+#ifndef GCM_EMU
+    const long long t0 = clock64();
+    for (;;) {
+      ok = gcm_load_sys(&mine->flag_from_n) >= seq && gcm_load_sys(&mine->flag_from_s) >= seq;
+      if (ok || clock64() - t0 > 4000000000ll) break;  // ~2 s
+      __nanosleep(64);
+    }
+#else
+    ok = gcm_load_sys(&mine->flag_from_n) >= seq && gcm_load_sys(&mine->flag_from_s) >= seq;
+#endif
+    if (!ok && blockIdx.x == 0) atomicAdd(&mine->timeouts, 1u);
+    gcm_fence_system();  // the neighbours' rows were performed before their flags
+    seq_s = seq;
+  }
+  __syncthreads();
+  from_s.buf += (seq_s & 1) * slot_doubles;
+  from_n.buf += (seq_s & 1) * slot_doubles;
+  double* fld[5] = {s.p, s.u, s.v, s.t, s.q};
+  band_halo_copy(fld, H, W, L, from_s, from_n, 1);
+}
+
+// halo rows of `s` through the peer mailboxes (hn north, hs south rows; at most the layout the mailbox was sized for)
+// phase: 1 = push only, 2 = pull only, 3 = both
+static int band_exchange_peer(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, cudaStream_t q,
+                              int phase = 3) {
+  GCM_REQUIRE(c->peer_mode && c->mbox && c->peer_n && c->peer_s, GCM_EUNSUP);
+  GCM_REQUIRE(hn <= c->mb_hn && hs <= c->mb_hs && g->d.W == c->mb_W && g->d.L == c->mb_L, GCM_ESHAPE);
+  const int lo = g->d.row_lo, hi = g->d.row_hi, H = g->d.H, W = g->d.W, L = g->d.L;
+  const size_t slot = c->part_n + c->part_s;
+  GcmMboxHeader* mine = (GcmMboxHeader*)c->mbox;
+  GcmMboxHeader* north = (GcmMboxHeader*)c->peer_n;
+  GcmMboxHeader* south = (GcmMboxHeader*)c->peer_s;
+  // slot layout: [rows from the north neighbour (part_n)][rows from the south neighbour (part_s)]
+  double* n_from_s = (double*)(c->peer_n + GCM_MBOX_HDR) + c->part_n;  // north's "from south" part: my first rows
+  double* s_from_n = (double*)(c->peer_s + GCM_MBOX_HDR);              // south's "from north" part: my last rows
+  double* my_from_n = (double*)(c->mbox + GCM_MBOX_HDR);
+  double* my_from_s = my_from_n + c->part_n;
+  const size_t total = gcm_halo_buffer_doubles(g, hs) + gcm_halo_buffer_doubles(g, hn);
+  unsigned nblk = (unsigned)((total + 255) / 256);
+  nblk = nblk < 1 ? 1 : (nblk > 148 * 2 ? 148 * 2 : nblk);
+  if (phase & 1) {
+    GCM_LAUNCH(band_push_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{lo, hs, n_from_s},
+               GcmHaloJob{hi - hn, hn, s_from_n}, slot, mine, north, south);
+    GCM_CHECK_LAUNCH();
+  }
+  if (phase & 2) {
+    GCM_LAUNCH(band_pull_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{hi, hs, my_from_s},
+               GcmHaloJob{lo - hn, hn, my_from_n}, slot, mine);
+    GCM_CHECK_LAUNCH();
+  }
+  return GCM_OK;
+}
+
+// The two halves of a peer-mailbox exchange on their own (phase 1 = push my boundary rows to the neighbours, 2 = wait
+// for theirs and fill my halo rows): hn / hs halo rows north / south.  A caller that steps several ranks from one
+// process (tests) pushes on every rank before it pulls on any.
+extern "C" int gcm_band_halo_peer(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, int phase,
+                                  void* stream) {
+  GCM_REQUIRE(g && c && s && s->p && s->u && s->v && s->t && s->q, GCM_ENULL);
+  GCM_REQUIRE(!g->d.wrap_j && hn >= 0 && hs >= 0 && phase >= 1 && phase <= 3, GCM_ESHAPE);
+  GCM_REQUIRE(hn <= g->d.row_lo && hs <= g->d.H - g->d.row_hi && hn <= g->d.row_hi - g->d.row_lo &&
+                  hs <= g->d.row_hi - g->d.row_lo, GCM_ESHAPE);
+  return band_exchange_peer(g, c, s, hn, hs, (cudaStream_t)stream, phase);
+}
+
 // fill the halo rows of `s` (hn north, hs south) from the ring neighbours, on stream `q`
 static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, cudaStream_t q) {
   GcmProfScope ps(GCM_K_HALO, q);
@@ -181,9 +430,11 @@ static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int
     if ((st = gcm_halo_copy_rows(g, s, lo, s, hi, hs, q))) return st;
     return gcm_halo_copy_rows(g, s, hi - hn, s, lo - hn, hn, q);
   }
+  if (c->peer_mode) return band_exchange_peer(g, c, s, hn, hs, q);
 #ifdef GCM_EMU
   return GCM_EUNSUP;
 #else
+  GCM_REQUIRE(c->comm, GCM_ENULL);  // neither peer mailboxes nor an NCCL communicator
   const size_t ns = gcm_halo_buffer_doubles(g, hs), nn = gcm_halo_buffer_doubles(g, hn);
   if (c->buf_doubles < 2 * (ns + nn)) {
     if (c->buf) cudaFree(c->buf);

@@ -6,8 +6,8 @@
 // zero-filled by the hardware (the callers patch the periodic wrap afterwards, pe25_fast.cu).
 //
 // On the CPU emulator build (tests only) a "tensor map" is the plain description and a load is a synchronous copy with
-// the same zero fill; mbarrier operations are no-ops (every load is separated from its consumers by a __syncthreads
-// in the kernels that use them).
+// the same zero fill; the mbarrier is emulated with its real phase semantics (a waiting fiber yields until the phase
+// flips), so warp-specialised producer / consumer kernels run on the emulator too.
 #pragma once
 #include "gcm_common.h"
 
@@ -30,12 +30,27 @@ int gcm_tmap_get(GcmTmap* out, const double* base, int W, int H, int NZ, int bw,
 
 // ---- device side ------------------------------------------------------------------------------------------------
 #ifdef GCM_EMU
+// mbarrier on the emulator: bit 63 = phase, bits 32..62 = arrivals per phase, bits 0..31 = arrivals still pending.  A
+// block's fibers run on one OS thread and switch only when they yield, so plain read-modify-write is atomic; the bytes
+// of a bulk copy "land" at issue, so expect_tx is an arrival.  A waiter yields (stays runnable) until the phase flips.
 typedef unsigned long long GcmMbar;
-__device__ __forceinline__ void gcm_mbar_init(GcmMbar*, int) {}
+__device__ __forceinline__ void gcm_mbar_init(GcmMbar* b, int count) {
+  *b = ((unsigned long long)count << 32) | (unsigned long long)count;
+}
 __device__ __forceinline__ void gcm_mbar_fence_init() {}
 __device__ __forceinline__ void gcm_fence_proxy_async() {}
-__device__ __forceinline__ void gcm_mbar_expect_tx(GcmMbar*, unsigned) {}
-__device__ __forceinline__ void gcm_mbar_wait(GcmMbar*, unsigned) {}
+__device__ __forceinline__ void gcm_mbar_arrive(GcmMbar* b) {
+  unsigned long long v = *b;
+  const unsigned long long init = (v >> 32) & 0x7fffffffull;
+  unsigned long long pending = (v & 0xffffffffull) - 1;
+  unsigned long long phase = v >> 63;
+  if (pending == 0) { phase ^= 1; pending = init; }
+  *b = (phase << 63) | (init << 32) | pending;
+}
+__device__ __forceinline__ void gcm_mbar_expect_tx(GcmMbar* b, unsigned) { gcm_mbar_arrive(b); }
+__device__ __forceinline__ void gcm_mbar_wait(GcmMbar* b, unsigned parity) {
+  while ((unsigned)(*b >> 63) == (parity & 1u)) gcm_emu::yield_state(0);
+}
 __device__ __forceinline__ void gcm_tma_load3(double* dst, const GcmTmap* m, int x, int y, int z, GcmMbar*) {
   for (int r = 0; r < m->bh; ++r)
     for (int c = 0; c < m->bw; ++c) {
@@ -64,6 +79,9 @@ __device__ __forceinline__ void gcm_fence_proxy_async() {
 }
 __device__ __forceinline__ void gcm_mbar_expect_tx(GcmMbar* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gcm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gcm_mbar_arrive(GcmMbar* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gcm_smem_u32(bar)) : "memory");
 }
 // blocks until the phase with the given parity has completed (every expected byte has landed)
 __device__ __forceinline__ void gcm_mbar_wait(GcmMbar* bar, unsigned parity) {

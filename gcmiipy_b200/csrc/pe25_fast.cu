@@ -899,14 +899,20 @@ struct PfTmaMaps {
   GcmTmap cen[6];        // pgf, fv, u, v, t, q: box 32 x TJ x 1
 };
 
-template <int L, int PFT_TJ, bool SAME, int NS>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
+// Warp-specialised: warp PFT_TJ of the CTA is the PRODUCER (one lane issues the box loads of layer k into stage k % NS as
+// soon as the consumers have released it), warps 0 .. PFT_TJ-1 are the CONSUMERS (one tile row each).  Stages are handed
+// over through mbarriers only -- full[s]: the bytes of a layer have landed; empty[s]: every consumer warp is done with
+// it -- so the layer loop has no block-wide barrier and no thread of a compute warp ever issues a load.
+template <int L, int PFT_TJ, bool SAME, int NS, int MINB>
+__global__ void __launch_bounds__(PFT_TI * (PFT_TJ + 1), MINB)
 pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, PfConst base, PfConst star, PfMut out,
                         PfWork w, double dt, GcmRowSeg seg, size_t bstride2, size_t bstride3) {
   if (g.pdl_early) gcm_pdl_trigger();
   gcm_pdl_wait();
   GCM_DYN_SMEM(unsigned char, smraw);
-  GcmMbar* bars = reinterpret_cast<GcmMbar*>(smraw);  // NS barriers in the first 128 bytes
+  GcmMbar* full = reinterpret_cast<GcmMbar*>(smraw);  // barriers in the first 128 bytes: full[NS], empty[NS], patch
+  GcmMbar* empty = full + NS;
+  GcmMbar* patchbar = empty + NS;
   double* sm = reinterpret_cast<double*>(smraw + 128);
   constexpr int HBOX = (PFT_TJ + 2) * PFT_ROW;        // doubles a halo box delivers
   constexpr int HT = (HBOX + 15) / 16 * 16;           // halo tile pitch: box destinations are 128-byte aligned
@@ -914,17 +920,47 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
   constexpr int NCEN = SAME ? 2 : 6;
   constexpr int STAGE = PFT_NF * HT + NCEN * CT;
   constexpr unsigned STAGE_BYTES = (PFT_NF * HBOX + NCEN * CT) * sizeof(double);
+  constexpr int NCONS = PFT_TI * PFT_TJ;              // consumer threads
   const int H = g.H, W = g.W, plane = H * W, wrap = g.wrap_j;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PFT_TI + tx;
+  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile
+  const int x0 = blockIdx.x * PFT_TI - 2;      // first column of the halo box: the interior starts 16-byte aligned
+  const int zb = blockIdx.z * L;  // first layer of this member in the [members * L][H][W] view of the tensor maps
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      gcm_mbar_init(&full[s], 1);
+      gcm_mbar_init(&empty[s], PFT_TJ);
+    }
+    gcm_mbar_init(patchbar, NCONS);
+    gcm_mbar_fence_init();
+  }
+  __syncthreads();
+  if (ty == PFT_TJ) {  // ---- producer warp ----
+    if (tx == 0) {
+#pragma unroll 1
+      for (int k = 0; k < L; ++k) {
+        const int s = k % NS;
+        if (k >= NS) gcm_mbar_wait(&empty[s], ((k / NS) - 1) & 1);  // the consumers are done with layer k - NS
+        gcm_fence_proxy_async();
+        double* st = sm + s * STAGE;
+        gcm_mbar_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+        for (int f = 0; f < PFT_NF; ++f) gcm_tma_load3(st + f * HT, &maps.halo[f], x0, j0 - 1, zb + k, &full[s]);
+#pragma unroll
+        for (int f = 0; f < NCEN; ++f)
+          gcm_tma_load3(st + PFT_NF * HT + f * CT, &maps.cen[f], blockIdx.x * PFT_TI, j0, zb + k, &full[s]);
+      }
+    }
+    return;
+  }
+  // ---- consumer warps ----
   const int i = blockIdx.x * PFT_TI + tx;
   const int r = blockIdx.y * PFT_TJ + ty;
   const bool active = r < seg.n1;
-  const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile
-  const int x0 = blockIdx.x * PFT_TI - 2;      // first column of the halo box: the interior starts 16-byte aligned
   auto rowc = [&](int x) { return wrap ? ((x % H) + H) % H : (x < 0 ? 0 : (x >= H ? H - 1 : x)); };
   const int j = rowc(j0 + ty);
   const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
-  const int zb = blockIdx.z * L;  // first layer of this member in the [members * L][H][W] view of the tensor maps
   const double* __restrict__ p = base.p + o2;
   const double* __restrict__ sp = star.p + o2;
   const double* __restrict__ pn = w.pn + o2;
@@ -935,26 +971,10 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
   double* __restrict__ ot = out.t + o3;
   double* __restrict__ oq = out.q + o3;
 
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) gcm_mbar_init(&bars[s], 1);
-    gcm_mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int k, int s) {  // layer k -> stage s (one thread)
-    if (tid == 0) {
-      gcm_fence_proxy_async();
-      double* st = sm + s * STAGE;
-      gcm_mbar_expect_tx(&bars[s], STAGE_BYTES);
-#pragma unroll
-      for (int f = 0; f < PFT_NF; ++f) gcm_tma_load3(st + f * HT, &maps.halo[f], x0, j0 - 1, zb + k, &bars[s]);
-#pragma unroll
-      for (int f = 0; f < NCEN; ++f)
-        gcm_tma_load3(st + PFT_NF * HT + f * CT, &maps.cen[f], blockIdx.x * PFT_TI, j0, zb + k, &bars[s]);
-    }
-  };
   // CTAs whose halo box leaves the grid patch the zero-filled part with the periodic neighbour
   const bool edge_w = blockIdx.x == 0, edge_e = blockIdx.x + 1 == gridDim.x;
   const bool edge_j = wrap && (j0 - 1 < 0 || j0 + PFT_TJ + 1 > H);
+  const bool edge = edge_w || edge_e || edge_j;
   auto patch = [&](int k, double* st, int dr, int c) {  // tile element (dr, c) <- its periodic image
     int gj = j0 - 1 + dr, gi = x0 + c;
     if (gj < 0 || gj >= H) {
@@ -966,6 +986,8 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
 #pragma unroll
     for (int f = 0; f < PFT_NF; ++f) st[f * HT + rr] = fld[f][src];
   };
+  // patch stage s of layer k (its bytes have landed), then meet the other consumers: the patched elements are halo
+  // elements, which only the layer's own iteration reads
   auto fixup = [&](int k, int s) {
     double* st = sm + s * STAGE;
     if (edge_w || edge_e) {  // the halo column beyond the seam: tile column 1 (i = -1) / 34 (i = W)
@@ -981,9 +1003,9 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
         if (tid >= 1 && tid <= PFT_TI + 2) patch(k, st, dr, tid);
       }
     }
+    gcm_mbar_arrive(patchbar);
+    gcm_mbar_wait(patchbar, k & 1);
   };
-  issue(0, 0);
-  if (1 < L) issue(1, 1);
 
   const int jm = rowc(j0 + ty - 1), jp = rowc(j0 + ty + 1), jpp = rowc(j0 + ty + 2);
   const int ip = gcm_ip(i, W);
@@ -1014,8 +1036,7 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
   const double u_top = fld[0][(L - 1) * plane + e_c], v_top = fld[1][(L - 1) * plane + e_c],
                t_top = fld[2][(L - 1) * plane + e_c], q_top = fld[3][(L - 1) * plane + e_c];
 
-  gcm_mbar_wait(&bars[0], 0);
-  if (edge_w || edge_e || edge_j) fixup(0, 0);
+  gcm_mbar_wait(&full[0], 0);
   double u_k = 0.0, v_k = 0.0, t_k = 0.0, q_k = 0.0;
   double fu = 0.0, fv_ = 0.0, ft = 0.0, fq = 0.0, fu0 = 0.0, fv0 = 0.0, ft0 = 0.0, fq0 = 0.0;
   double sd_c = 0.0, sd_ip = 0.0, sd_jp = 0.0;  // level 0
@@ -1023,12 +1044,9 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
 
 #pragma unroll
   for (int k = 0; k < L; ++k) {
-    if (k + 1 < L) {  // the next layer's centre values feed the fluxes through the top of layer k
-      gcm_mbar_wait(&bars[(k + 1) % NS], ((k + 1) / NS) & 1);
-      if (edge_w || edge_e || edge_j) fixup(k + 1, (k + 1) % NS);
-    }
-    __syncthreads();  // stages of layers k and k + 1 are complete and patched; the stage of layer k - 1 is free
-    if (k + 2 < L) issue(k + 2, (k + 2) % NS);
+    if (edge) fixup(k, k % NS);
+    if (k + 1 < L)  // the next layer's centre values feed the fluxes through the top of layer k
+      gcm_mbar_wait(&full[(k + 1) % NS], ((k + 1) / NS) & 1);
     const double* sk = sm + (k % NS) * STAGE;
     const double* sn = sm + ((k + 1) % NS) * STAGE;
     if (k == 0) {
@@ -1106,6 +1124,10 @@ pe25f_update_tma_kernel(GcmGeomDev g, const GCM_GRID_CONSTANT PfTmaMaps maps, Pf
     }
     fu = fu_n; fv_ = fv_n; ft = ft_n; fq = fq_n;
     u_k = u_kp; v_k = v_kp; t_k = t_kp; q_k = q_kp;
+    if (k + NS < L) {  // this warp is done with the stage of layer k: hand it back to the producer
+      __syncwarp();
+      if (tx == 0) gcm_mbar_arrive(&empty[k % NS]);
+    }
   }
   if (active) out.p[o2 + e_c] = pn_c;
   gcm_flag_nonfinite(g.nonfinite, bad);
@@ -1128,7 +1150,8 @@ int g_gcm_knob[GCM_NKNOBS] = {0};
 //   9  programmatic dependent launch of the half-step kernels: 0 / 1 = on (a kernel's launch overlaps the drain of its
 //      predecessor in the stream: -3 ... -5 % per step, r03e), 2 = on + every kernel triggers its dependents at entry
 //      (waiting CTAs then hold SM slots the running kernel could use: slower on most grids), 3 = off
-//  10  TMA update kernel: layers in flight (2..4; 0 = 3)     11  TMA update kernel: tile rows (8; 0 = 4)
+//  10  TMA update kernel: layers in flight (4; 0 = 3)     11  TMA update kernel: tile rows (8; 0 = 4)
+//  13  TMA update kernel with 4-row tiles: 1 = 4 CTAs per SM (96 registers, spills) instead of 3 (128 registers)
 //  12  L2 promotion of the tensor maps: 0 = 128 B, 1 = none, 2 = 256 B
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < GCM_NKNOBS, GCM_ESHAPE);
@@ -1269,7 +1292,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   bool tma = tiled && g_gcm_knob[4] != 4 && (size_t)nbatch * L < 2147483647u;
   PfTmaMaps maps;
   const int tjt = g_gcm_knob[11] == 8 ? 8 : 4;                          // tile rows
-  const int nst = g_gcm_knob[10] >= 2 && g_gcm_knob[10] <= 4 ? g_gcm_knob[10] : 3;  // layers in flight
+  const int nst = (g_gcm_knob[10] == 4 && tjt == 4) ? 4 : 3;  // layers in flight
   if (tma && nrowsU > 0) {
     const double* hf[PFT_NF] = {star->u, star->v, star->t, star->q, w.spu};
     const double* cf[6] = {w.pgf, w.fv, base->u, base->v, base->t, base->q};
@@ -1285,29 +1308,31 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const size_t smt = 128 + (size_t)nst * (PFT_NF * HT + (same ? 2 : 6) * CT) * sizeof(double);
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
-      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tjt - 1) / tjt, nbatch), blockt(PFT_TI, tjt);
+      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tjt - 1) / tjt, nbatch), blockt(PFT_TI, tjt + 1);  // + producer warp
 #ifndef GCM_EMU
 #define PF_TMA_ATTR(K) \
   if (smt > 48 * 1024) GCM_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt))
 #else
 #define PF_TMA_ATTR(K)
 #endif
-#define PF_TMA_GO(TJ_, SAME_, NS_)                                                                                   \
-  do {                                                                                                               \
-    PF_TMA_ATTR((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_>));                                                      \
-    GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, \
-                   dt, parts[s2], b2, b3);                                                                           \
+#define PF_TMA_GO(TJ_, SAME_, NS_, MB_)                                                                                   \
+  do {                                                                                                                    \
+    PF_TMA_ATTR((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_, MB_>));                                                      \
+    GCM_LAUNCH_DEP((pe25f_update_tma_kernel<L, TJ_, SAME_, NS_, MB_>), gridt, blockt, smt, stream, d, maps, cb, cs, mo, w, \
+                   dt, parts[s2], b2, b3);                                                                                \
   } while (0)
-#define PF_TMA_NS(TJ_, SAME_)               \
-  do {                                      \
-    if (nst == 2) PF_TMA_GO(TJ_, SAME_, 2); \
-    else if (nst == 4) PF_TMA_GO(TJ_, SAME_, 4); \
-    else PF_TMA_GO(TJ_, SAME_, 3);          \
+#define PF_TMA_T4(SAME_)                                  \
+  do {                                                    \
+    if (nst == 4 && minb4) PF_TMA_GO(4, SAME_, 4, 4);     \
+    else if (nst == 4) PF_TMA_GO(4, SAME_, 4, 3);         \
+    else if (minb4) PF_TMA_GO(4, SAME_, 3, 4);            \
+    else PF_TMA_GO(4, SAME_, 3, 3);                       \
   } while (0)
+      const bool minb4 = g_gcm_knob[13] == 1;  // 4 CTAs per SM at 96 registers (spills) instead of 3 at 128
       if (tjt == 8) {
-        if (same) PF_TMA_NS(8, true); else PF_TMA_NS(8, false);
+        if (same) PF_TMA_GO(8, true, 3, 2); else PF_TMA_GO(8, false, 3, 2);
       } else {
-        if (same) PF_TMA_NS(4, true); else PF_TMA_NS(4, false);
+        if (same) PF_TMA_T4(true); else PF_TMA_T4(false);
       }
       GCM_CHECK_LAUNCH();
     }

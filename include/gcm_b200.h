@@ -221,9 +221,27 @@ int gcm_halo_copy_rows(const gcm_geom* g, const gcm_state* src, int src_row0, co
 typedef struct gcm_comm gcm_comm;
 /* rank 0 makes the 128-byte NCCL unique id; the caller ships it to the other ranks (e.g. torch.distributed) */
 int gcm_comm_unique_id(unsigned char* h_out128);
-/* collective over the ranks of the ring; nranks == 1 needs no NCCL and no id (the ring closes on the band itself) */
+/* collective over the ranks of the ring; nranks == 1 needs no NCCL and no id (the ring closes on the band itself);
+ * h_id128 == NULL with nranks > 1: no NCCL communicator, the ring then needs the peer mailboxes below */
 int gcm_comm_create(int nranks, int rank, const unsigned char* h_id128, gcm_comm** out);
 int gcm_comm_destroy(gcm_comm* c);
+
+/* Peer-memory halo exchange over NVLink / NVSwitch (replaces pack -> ncclSend/ncclRecv -> unpack: emulates the same
+ * np.roll over j, coordinates_3d.py:43-48).  Every rank owns a MAILBOX in device memory; a neighbour maps it (CUDA
+ * IPC) and its push kernel stores my halo rows straight into it over NVLink, then publishes a message number in it
+ * (system-scope fence + flag); my pull kernel waits for the number (bounded spin) and copies the rows into my halo
+ * rows.  Two slots alternate, so a rank may run one step ahead of its neighbours.  No host involvement per step.
+ *   gcm_comm_peer_setup   allocates the mailbox for the halo layout of band geometry g; h_handle64 = its IPC handle
+ *   gcm_comm_peer_connect maps the ring neighbours' mailboxes from their handles (same_process != 0: `north` /
+ *                         `south` are gcm_comm* of this process instead -- single-process tests of the protocol)
+ *   gcm_comm_peer_status  returns 0 = NCCL ring, 1 = IPC peers, 2 = same-process peers; *timeouts = pull kernels
+ *                         that gave up waiting for a neighbour (synchronises the device)
+ *   gcm_band_halo_peer    one exchange of hn / hs halo rows of `s`, or one half of it: phase 1 = push, 2 = pull
+ * Once connected, gcm_band_matsuno_step exchanges through the mailboxes. */
+int gcm_comm_peer_setup(gcm_comm* c, const gcm_geom* g, unsigned char* h_handle64);
+int gcm_comm_peer_connect(gcm_comm* c, const void* north, const void* south, int same_process);
+int gcm_comm_peer_status(gcm_comm* c, unsigned int* h_timeouts);
+int gcm_band_halo_peer(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, int phase, void* stream);
 /* dynamics.matsuno_timestep (dynamics.py:230-237) `nsteps` times on this rank's band (geometry with wrap_j = 0,
  * 1 halo row north and 2 south, or 2 + 4 for the one-exchange schedule, or 2 + 2 with opt-in terms on).  `cur` =
  * the band incl. halo rows (halo content is overwritten), `star` = scratch

@@ -262,3 +262,51 @@ def test_gloo_subgroup_bands(tmp_path):
                 assert np.array_equal(z[k], b), k
     finally:
         _lib._override_for_tests(None, None)
+
+
+@pytest.mark.parametrize("world,H,W", [(3, 24, 36), (2, 16, 32), (4, 32, 64)])
+def test_peer_mailbox_ring_same_process(backend, world, H, W):
+    """The peer-memory halo exchange of csrc/comm.cu (push kernel: my boundary rows -> the neighbours' mailboxes +
+    message flag; pull kernel: wait for both flags, mailbox -> halo rows; two alternating slots) with every rank of the
+    ring in THIS process, stepped phase by phase (all ranks push before any pulls, so no kernel waits for a later
+    launch).  Two exchanges per Matsuno step: both slots and the sequence numbers are exercised.  Bit-identical to the
+    whole grid; no pull may time out."""
+    import ctypes
+    from gcmiipy_b200 import _lib
+    from gcmiipy_b200.dynamics import _struct
+    geom, s = _case(H=H, W=W)
+    whole = dynamics.Stepper(geom, *s)
+    whole.step(450.0, 3)
+    lib = _lib.lib()
+    ranks = [bands.BandStepper(geom, *s, rank=r, world=world, native=False) for r in range(world)]
+    for b in ranks:
+        h = ctypes.c_void_p()
+        _lib.check(lib.gcm_comm_create(world, b.rank, None, ctypes.byref(h)), "gcm_comm_create")
+        b.comm = h
+        _lib.check(lib.gcm_comm_peer_setup(b.comm, b.dg.handle, (ctypes.c_ubyte * 64)()), "peer_setup")
+    for b in ranks:
+        _lib.check(lib.gcm_comm_peer_connect(b.comm, ranks[b.north].comm, ranks[b.south].comm, 1), "peer_connect")
+        assert lib.gcm_comm_peer_status(b.comm, None) == 2
+
+    def exchange(which):
+        for phase in (1, 2):
+            for b in ranks:
+                st = _struct(getattr(b, which))
+                _lib.check(lib.gcm_band_halo_peer(b.dg.handle, b.comm, ctypes.byref(st), b.xn, b.xs, phase, _lib.stream()),
+                           "gcm_band_halo_peer")
+
+    for _ in range(3):
+        exchange("cur")
+        for b in ranks:
+            b._half(b.cur, b.cur, b.star, 450.0)
+        exchange("star")
+        for b in ranks:
+            b._half(b.cur, b.star, b.nxt, 450.0)
+            b.cur, b.nxt = b.nxt, b.cur
+    full = [torch.cat([b.owned()[f] for b in ranks], dim=-2).cpu().numpy() for f in range(5)]
+    for a, ref in zip(full, whole.download()):
+        assert np.array_equal(a, ref)
+    for b in ranks:
+        assert b.peer_timeouts() == 0
+        comm, b.comm = b.comm, None          # this test owns the communicators
+        lib.gcm_comm_destroy(comm)

@@ -592,11 +592,12 @@ def test_nonfinite_watch_and_last_status(backend):
     assert watch.last_status(clear=True) == -2 and watch.last_status() == 0
 
 
-@pytest.mark.parametrize("knobs", [{}, {4: 4}, {10: 2}, {10: 4}, {11: 8}, {11: 8, 10: 2}, {12: 1}])
+@pytest.mark.parametrize("knobs", [{}, {4: 4}, {10: 4}, {13: 1}, {10: 4, 13: 1}, {11: 8}, {12: 1}])
 @pytest.mark.parametrize("H,W", [(10, 64), (3, 32)])
 def test_tma_update_variants_vs_oracle(backend, knobs, H, W):
-    """pe25f_update_tma_kernel (TMA box loads on mbarriers): default 3 layers in flight, 32 x 4 tiles; knob 10 = layers
-    in flight, knob 11 = 8 tile rows, knob 12 = L2 promotion of the tensor maps, knob 4 = 4 the LDGSTS kernel.  Two tile
+    """pe25f_update_tma_kernel (warp-specialised: TMA box loads by a producer warp, stages handed over on mbarriers):
+    default 3 layers in flight, 32 x 4 tiles, 3 CTAs per SM; knob 10 = 4 layers in flight, knob 13 = 4 CTAs per SM,
+    knob 11 = 8 tile rows, knob 12 = L2 promotion of the tensor maps, knob 4 = 4 the LDGSTS kernel.  Two tile
     columns / one (both seams in one CTA), partial tiles in j, the periodic wrap in i and j patched by the seam CTAs."""
     from gcmiipy_b200 import _lib
     geom = geometry.gen_geometry(H, W, 9, sig_func=geometry.manabe_sig)
