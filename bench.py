@@ -398,6 +398,9 @@ def run_native(args):
                    "l2_policy": "state %.0f MB > 126 MB L2: inputs larger than L2, no flush" % (total_cells * b_alg(L) / 2e6 / world)
                    if total_cells * b_alg(L) / 2 / world > 126e6 else "state fits L2 (latency/ALU-bound config); no flush"},
         "finite": finite,
+        "halo_transport": (("peer mailboxes (NVLink peer stores, CUDA IPC)" if getattr(stepper, "peer", False) else "NCCL send/recv")
+                           if world > 1 and members == 1 else None),
+        "peer_timeouts": stepper.peer_timeouts() if world > 1 and members == 1 and getattr(stepper, "comm", None) else None,
         "sim_days_per_day": (args.steps / (ms * 1e-3)) * dt,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
         "gpu_launches": int(round((launches_per_step or 0) * args.steps)),

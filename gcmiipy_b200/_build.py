@@ -29,6 +29,10 @@ SOURCES = {
     "host_step.cu": [],
     "pe25.cu": ["-fmad=false"],
     "pe25_fast.cu": [],
+    "pe25_fast_l3.cu": [],
+    "pe25_fast_l9.cu": [],
+    "pe25_fast_l17.cu": [],
+    "pe25_fast_l18.cu": [],
     "pe25_extras.cu": [],
     "sw2d.cu": ["-fmad=false"],
     "pe2d.cu": ["-fmad=false"],

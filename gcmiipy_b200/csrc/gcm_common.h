@@ -21,6 +21,7 @@
   type* name = reinterpret_cast<type*>(gcm_dyn_smem_)
 #endif
 
+extern int g_gcm_knob[GCM_NKNOBS];  // tuning knobs (pe25_fast.cu)
 #ifdef GCM_EMU
 #define GCM_LAUNCH_DEP GCM_LAUNCH
 #else
@@ -40,7 +41,6 @@ static inline void gcm_launch_dep(bool pdl, void (*kern)(KArgs...), dim3 grid, d
   cfg.numAttrs = pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
-extern int g_gcm_knob[GCM_NKNOBS];
 #define GCM_LAUNCH_DEP(kern, grid, block, smem, stream, ...) \
   gcm_launch_dep(g_gcm_knob[9] != 3, kern, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
@@ -70,7 +70,7 @@ int gcm_set_status(int st);
 #define GCM_G 9.8
 
 #define GCM_MAX_RADIX_PASSES 16
-#define GCM_MAXLC 16
+#define GCM_MAXLC 24
 
 // Stockham mixed-radix plan for one row of length n (see fft_rows.h)
 struct GcmFftPlan {

@@ -51,6 +51,7 @@ __device__ __forceinline__ void gcm_mbar_expect_tx(GcmMbar* b, unsigned) { gcm_m
 __device__ __forceinline__ void gcm_mbar_wait(GcmMbar* b, unsigned parity) {
   while ((unsigned)(*b >> 63) == (parity & 1u)) gcm_emu::yield_state(0);
 }
+__device__ __forceinline__ void gcm_mbar_wait_backoff(GcmMbar* b, unsigned parity) { gcm_mbar_wait(b, parity); }
 __device__ __forceinline__ void gcm_tma_load3(double* dst, const GcmTmap* m, int x, int y, int z, GcmMbar*) {
   for (int r = 0; r < m->bh; ++r)
     for (int c = 0; c < m->bw; ++c) {
@@ -95,6 +96,24 @@ __device__ __forceinline__ void gcm_mbar_wait(GcmMbar* bar, unsigned parity) {
       "DONE:\n\t"
       "}" ::"r"(gcm_smem_u32(bar)), "r"(parity)
       : "memory");
+}
+// the same for a thread that has nothing else to do (a producer waiting for its consumers): sleeps between probes
+// instead of competing with the compute warps for issue slots
+__device__ __forceinline__ void gcm_mbar_wait_backoff(GcmMbar* bar, unsigned parity) {
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(gcm_smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
 }
 // box of the tensor map at element coordinates (x, y, z) -> dst (128-byte aligned shared memory), completing on bar
 __device__ __forceinline__ void gcm_tma_load3(double* dst, const GcmTmap* m, int x, int y, int z, GcmMbar* bar) {

@@ -592,12 +592,12 @@ def test_nonfinite_watch_and_last_status(backend):
     assert watch.last_status(clear=True) == -2 and watch.last_status() == 0
 
 
-@pytest.mark.parametrize("knobs", [{}, {4: 4}, {10: 4}, {13: 1}, {10: 4, 13: 1}, {11: 8}, {12: 1}])
+@pytest.mark.parametrize("knobs", [{}, {4: 5}, {4: 5, 10: 3}, {4: 5, 13: 1}, {4: 5, 10: 3, 13: 1}, {4: 5, 11: 8}, {4: 5, 12: 1}])
 @pytest.mark.parametrize("H,W", [(10, 64), (3, 32)])
 def test_tma_update_variants_vs_oracle(backend, knobs, H, W):
     """pe25f_update_tma_kernel (warp-specialised: TMA box loads by a producer warp, stages handed over on mbarriers):
-    default 3 layers in flight, 32 x 4 tiles, 3 CTAs per SM; knob 10 = 4 layers in flight, knob 13 = 4 CTAs per SM,
-    knob 11 = 8 tile rows, knob 12 = L2 promotion of the tensor maps, knob 4 = 4 the LDGSTS kernel.  Two tile
+    knob 4 = 5 selects it (default: the LDGSTS tiled kernel); 4 layers in flight, 32 x 4 tiles, 3 CTAs per SM; knob 10 =
+    3 layers in flight, knob 13 = 4 CTAs per SM, knob 11 = 8 tile rows, knob 12 = L2 promotion of the tensor maps.  Two tile
     columns / one (both seams in one CTA), partial tiles in j, the periodic wrap in i and j patched by the seam CTAs."""
     from gcmiipy_b200 import _lib
     geom = geometry.gen_geometry(H, W, 9, sig_func=geometry.manabe_sig)
@@ -619,3 +619,24 @@ def test_tma_update_variants_vs_oracle(backend, knobs, H, W):
     for _ in range(3):
         ref = O.matsuno_timestep(*ref, 20.0, og)
     check_state(got, ref, TOL_RUN)
+
+
+@pytest.mark.parametrize("H,W,L", [(8, 32, 17), (6, 36, 18), (5, 64, 18), (6, 20, 17), (6, 24, 4)])
+def test_fused_path_layer_counts_vs_oracle(backend, H, W, L):
+    """The fused kernels are instantiated for 3, 9, 17 (test_geography.py:6-18 mountain strip) and 18 layers
+    (standard_atmosphere_isa.py:15-40); any other count (here 4) takes the general four-kernel path.  Tiled (W % 32 == 0),
+    direct-load and one-thread-per-cell update kernels, ptop != 0."""
+    from gcmiipy_b200 import _lib
+    from gcmiipy_b200.geometry import device_geom
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    geom.ptop = og.ptop = 1000.0 if W == 36 else 0.0
+    hm = 80.0 * np.random.default_rng(L).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    s = O.synthetic_state(og, seed=L * W)
+    st = dynamics.Stepper(geom, *s)
+    st.step(30.0, 2)
+    ref = s
+    for _ in range(2):
+        ref = O.matsuno_timestep(*ref, 30.0, og)
+    check_state(st.download(), ref, TOL_RUN)

@@ -39,25 +39,35 @@ def main():
     whole.step(dt, args.steps)
     ref = whole.download()
     ok = True
-    for native, overlap, wide in ((True, False, True), (True, True, False), (True, False, False), (False, False, False)):
+    variants = ((True, False, True, True), (True, False, True, False), (True, True, False, True), (True, True, False, False),
+                (True, False, False, True), (False, False, False, False))
+    for native, overlap, wide, peer in variants:
+        os.environ["GCM_BAND_PEER"] = "1" if peer else "0"      # peer mailboxes over NVLink, or the NCCL ring
         b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
         b.overlap = overlap
         b.step(dt, args.steps)
+        b.step(dt, 2)                                            # a second call: message numbers carry over
         got = b.gather()
+        whole2 = dynamics.Stepper(geom, *s0)
+        whole2.step(dt, args.steps + 2)
+        ref = whole2.download()
         same = all(np.array_equal(a, r) for a, r in zip(got, ref))
         finite = all(np.isfinite(a).all() for a in got)
-        flag = torch.tensor([int(same and finite)], device="cuda")
+        tmo = b.peer_timeouts() if b.comm is not None else 0
+        flag = torch.tensor([int(same and finite and tmo == 0)], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print("bitwise %s  native=%s overlap=%s one_exchange=%s  grid %dx%dx%d  ranks %d  steps %d" %
-                  ("OK" if flag.item() else "MISMATCH", native, overlap, wide, W, H, L, world, args.steps), flush=True)
+            print("bitwise %s  native=%s overlap=%s one_exchange=%s transport=%s timeouts=%d  grid %dx%dx%d  ranks %d  steps %d" %
+                  ("OK" if flag.item() else "MISMATCH", native, overlap, wide, "peer" if b.peer else "nccl", tmo, W, H, L,
+                   world, args.steps + 2), flush=True)
         ok = ok and bool(flag.item())
         del b
     if args.time:
         H, W, L, dt = 720, 1440, 9, 10.0
         geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
         s0 = synthetic.synthetic_state(geom, seed=1234)
-        for native, overlap, wide in ((True, False, True), (True, True, False), (True, False, False), (False, False, False)):
+        for native, overlap, wide, peer in variants:
+            os.environ["GCM_BAND_PEER"] = "1" if peer else "0"
             b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
             b.overlap = overlap
             b.step(dt, 5)
@@ -71,8 +81,9 @@ def main():
             t = torch.tensor([e0.elapsed_time(e1) / 30], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print("time native=%s overlap=%s one_exchange=%s: %.4f ms/step  (%.3e cell-updates/s on %d GPUs)" %
-                      (native, overlap, wide, t.item(), H * W * L / (t.item() * 1e-3), world), flush=True)
+                print("time native=%s overlap=%s one_exchange=%s transport=%s: %.4f ms/step  (%.3e cell-updates/s on %d GPUs)" %
+                      (native, overlap, wide, "peer" if b.peer else "nccl", t.item(), H * W * L / (t.item() * 1e-3), world),
+                      flush=True)
             del b
     dist.barrier()
     dist.destroy_process_group()
