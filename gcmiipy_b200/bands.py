@@ -26,12 +26,12 @@ HALO_N, HALO_S = 1, 2
 
 
 def _wide_ok(geom):
-    """The one-exchange schedule needs the row-segment kernels (fused path: 3 or 9 layers, W a product of 2, 3, 5)."""
+    """The one-exchange schedule needs the row-segment kernels (fused path: 3, 9, 17 or 18 layers, W a product of 2, 3, 5)."""
     W = geom.width
     for f in (2, 3, 5):
         while W % f == 0:
             W //= f
-    return geom.layers in (3, 9) and W == 1
+    return geom.layers in (3, 9, 17, 18) and W == 1
 
 
 class BandStepper:
