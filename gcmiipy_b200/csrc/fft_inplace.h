@@ -292,15 +292,21 @@ __host__ inline int gcm_fixed_plan_id(const GcmFftPlan& p) {
   return 0;
 }
 
-template <int NPJ, int PLAN, class IO>
+struct GcmNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `after_first()` runs once the first stage has consumed its inputs and the block has synchronised (the pipelined
+// filter kernel starts the bulk copy of its NEXT rows there: they land under the remaining stages)
+template <int NPJ, int PLAN, class IO, class Hook = GcmNoHook>
 __device__ __forceinline__ void gcm_filter_rows_io_fixed(double2* z, int nrows, const GcmFftPlan& plan,
                                                          const double2* __restrict__ tw,
                                                          const double* __restrict__ table, const GcmRowSeg seg, int pr0,
-                                                         IO& io, int tid, int nthr) {
+                                                         IO& io, int tid, int nthr, Hook after_first = Hook()) {
   using P = GcmFixedPlan<PLAN>;
   constexpr int last = P::n - 1;
   gcm_dif_stage_first<P::r0>(z, gcm_fft_stage(plan, 0), nrows, tw, io, tid, nthr);
   __syncthreads();
+  after_first();
   if constexpr (P::n == 3) {
     gcm_dif_stage<(P::r1 > 0 ? P::r1 : 2)>(z, gcm_fft_stage(plan, 1), nrows, tw, tid, nthr);
     __syncthreads();

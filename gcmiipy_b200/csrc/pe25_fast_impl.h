@@ -189,10 +189,130 @@ pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* i
     gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
 }
 
+// The same filter as a PERSISTENT, software-pipelined kernel (compile-time plans only): a CTA walks over units of NBAT
+// packed rows; while it transforms unit u, the raw rows of its next unit travel into a staging buffer as 1-D bulk copies
+// of whole rows (cp.async.bulk, the TMA unit's contiguous mode, SASS UBLKCP) completing on an mbarrier -- issued as soon as
+// the first stage has consumed the staging buffer, so they land under the remaining four stages.  The first stage then
+// reads shared memory instead of waiting for HBM: the non-pipelined kernel above exposes that latency once per CTA with
+// nothing to overlap it (DRAM 20 % busy, issue 44 %, ncu r03j).
+template <int L, int MODE>
+struct PfFilterStagedIO {
+  const double* __restrict__ sp;
+  const double* stage;  // [NBAT][2][W] raw rows of the unit
+  double* out;
+  GcmRowSeg seg;
+  int pr0, W, plane;
+  struct Ctx {
+    const double* s0;
+    const double* spr;
+    double* o;
+    bool two;
+  };
+  __device__ __forceinline__ Ctx begin(int row) const {
+    constexpr int NP = (L + 1) / 2;
+    const int pr = pr0 + row, r = pr / NP, k0 = 2 * (pr - r * NP);
+    const int j = gcm_seg_row(seg, r);
+    Ctx c;
+    c.s0 = stage + (size_t)row * 2 * W;
+    c.spr = sp + j * W;
+    c.o = out + k0 * plane + j * W;
+    c.two = k0 + 1 < L;
+    return c;
+  }
+  __device__ __forceinline__ double2 load(const Ctx& c, int i) const {
+    double x0 = c.s0[i], x1 = c.two ? c.s0[W + i] : 0.0;
+    if (MODE == 1) {  // su * iph(sp)  (dynamics.py:187)
+      const double ph = (c.spr[i] + c.spr[gcm_ip(i, W)]) * 0.5;
+      x0 *= ph;
+      x1 *= ph;
+    }
+    return make_double2(x0, x1);
+  }
+  __device__ __forceinline__ void store(const Ctx& c, int i, double2 v) const {
+    c.o[i] = v.x;
+    if (c.two) c.o[plane + i] = v.y;
+  }
+};
+
+template <int L, int MODE, int PLAN>
+__global__ void __launch_bounds__(256, 2)
+pe25f_filter_pipe_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
+                         size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
+  GCM_DYN_SMEM(unsigned char, smraw);
+  constexpr int NP = (L + 1) / 2;
+  const int W = g.W, plane = g.H * W;
+  GcmMbar* full = reinterpret_cast<GcmMbar*>(smraw);
+  double2* z = reinterpret_cast<double2*>(smraw + 128);               // [NBAT][W] complex work rows
+  double* stage = reinterpret_cast<double*>(z + (size_t)NBAT * W);   // [NBAT][2][W] raw rows of the next unit
+  const int npr_total = (seg.n1 + seg.n2) * NP;
+  const int nunits = (npr_total + NBAT - 1) / NBAT;
+  const double* inb = in + blockIdx.y * bstride3;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    gcm_mbar_init(full, 1);
+    gcm_mbar_fence_init();
+  }
+  __syncthreads();
+  auto prefetch = [&](int u) {  // one thread: the raw rows of unit u -> staging
+    const int pr0 = u * NBAT;
+    const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
+    unsigned bytes = 0;
+    for (int row = 0; row < nb; ++row) {
+      const int pr = pr0 + row, r = pr / NP, k0 = 2 * (pr - r * NP);
+      bytes += (k0 + 1 < L ? 2u : 1u) * (unsigned)W * 8u;
+    }
+    gcm_fence_proxy_async();
+    gcm_mbar_expect_tx(full, bytes);
+    for (int row = 0; row < nb; ++row) {
+      const int pr = pr0 + row, r = pr / NP, k0 = 2 * (pr - r * NP);
+      const int j = gcm_seg_row(seg, r);
+      const double* src = inb + (size_t)k0 * plane + (size_t)j * W;
+      gcm_bulk_load(stage + (size_t)row * 2 * W, src, (unsigned)W * 8u, full);
+      if (k0 + 1 < L) gcm_bulk_load(stage + (size_t)row * 2 * W + W, src + plane, (unsigned)W * 8u, full);
+    }
+  };
+  int u = blockIdx.x;
+  if (tid == 0 && u < nunits) prefetch(u);
+  unsigned phase = 0;
+  for (; u < nunits; u += gridDim.x) {
+    const int pr0 = u * NBAT;
+    const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
+    PfFilterStagedIO<L, MODE> io{sp + blockIdx.y * bstride2, stage, out + blockIdx.y * bstride3, seg, pr0, W, plane};
+    gcm_mbar_wait(full, phase);
+    phase ^= 1;
+    const int unext = u + gridDim.x;
+    auto hook = [&]() {
+      if (tid == 0 && unext < nunits) prefetch(unext);
+    };
+    gcm_filter_rows_io_fixed<NP, PLAN>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, tid, blockDim.x, hook);
+  }
+}
+
 // launch of the filter kernel whose image matches the plan
 template <int L, int MODE, int PLAN>
 static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream, const double* sp,
                                  const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3) {
+  if constexpr (PLAN > 0) {
+    // persistent pipelined kernel (knob 14 = 1: the one-unit-per-CTA kernel): work rows + staging rows + barrier
+    const size_t smp = 128 + 2 * smem;
+    const int per_sm = (int)((227 * 1024) / (smp + 1024)) < 4 ? (int)((227 * 1024) / (smp + 1024)) : 4;
+    if (g_gcm_knob[14] != 1 && per_sm >= 1 && (d.W % 2) == 0) {
+      int ncta = 148 * per_sm / (int)grid.y;
+      ncta = ncta < 1 ? 1 : ncta;
+      const dim3 gridp((unsigned)((int)grid.x < ncta ? (int)grid.x : ncta), grid.y);
+#ifndef GCM_EMU
+      if (smp > 48 * 1024)
+        GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_pipe_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smp));
+#endif
+      GCM_LAUNCH_DEP((pe25f_filter_pipe_kernel<L, MODE, PLAN>), gridp, dim3(threads), smp, stream, d, sp, in, out, seg, nbf,
+                     b2, b3);
+      GCM_CHECK_LAUNCH();
+      return GCM_OK;
+    }
+  }
 #ifndef GCM_EMU
   if (smem > 48 * 1024)
     GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
