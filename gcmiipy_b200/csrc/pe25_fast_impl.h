@@ -169,8 +169,9 @@ struct PfFilterIO {
 };
 
 // PLAN > 0: the radices of the plan are compile-time constants (GcmFixedPlan); 0: runtime switch, any plan
-template <int L, int MODE, int PLAN>
-__global__ void __launch_bounds__(256, 2)
+// MB: resident CTAs per SM the register allocation aims at (fixed plans launch 128 threads): 4 = 128 registers
+template <int L, int MODE, int PLAN, int MB = 4>
+__global__ void __launch_bounds__(PLAN > 0 ? 128 : 256, PLAN > 0 ? MB : 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
                     size_t bstride2, size_t bstride3) {
   if (g.pdl_early) gcm_pdl_trigger();
@@ -295,10 +296,11 @@ template <int L, int MODE, int PLAN>
 static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream, const double* sp,
                                  const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3) {
   if constexpr (PLAN > 0) {
-    // persistent pipelined kernel (knob 14 = 1: the one-unit-per-CTA kernel): work rows + staging rows + barrier
+    // persistent pipelined kernel (knob 14 = 2; measured slower than the one-unit-per-CTA kernel on every grid, r2f:
+    // the filter is bound by dependent-instruction latency at 16 warps per SM, not by its loads)
     const size_t smp = 128 + 2 * smem;
     const int per_sm = (int)((227 * 1024) / (smp + 1024)) < 4 ? (int)((227 * 1024) / (smp + 1024)) : 4;
-    if (g_gcm_knob[14] != 1 && per_sm >= 1 && (d.W % 2) == 0) {
+    if (g_gcm_knob[14] == 2 && per_sm >= 1 && (d.W % 2) == 0) {
       int ncta = 148 * per_sm / (int)grid.y;
       ncta = ncta < 1 ? 1 : ncta;
       const dim3 gridp((unsigned)((int)grid.x < ncta ? (int)grid.x : ncta), grid.y);
@@ -314,6 +316,23 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
     }
   }
 #ifndef GCM_EMU
+  if constexpr (PLAN == 1 && L == 9) {  // register-budget variants of the 1440-wide plan (knob 15, units digit)
+    const int mb = g_gcm_knob[15] % 10;
+    if (mb == 5 || mb == 6 || mb == 8) {
+      if (threads > 128) return gcm_set_status(GCM_EUNSUP);
+#define PF_FILTER_MB(MB_)                                                                                             \
+  do {                                                                                                                \
+    if (smem > 48 * 1024)                                                                                             \
+      GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                      \
+    GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN, MB_>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, \
+                   b2, b3);                                                                                           \
+  } while (0)
+      if (mb == 5) PF_FILTER_MB(5); else if (mb == 6) PF_FILTER_MB(6); else PF_FILTER_MB(8);
+      GCM_CHECK_LAUNCH();
+      return GCM_OK;
+    }
+  }
   if (smem > 48 * 1024)
     GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
@@ -381,8 +400,8 @@ pe25f_aflux_kernel(GcmGeomDev g, const double* __restrict__ p, const double* __r
 
 // Hydrostatic columns: one warp per (group of RG rows, chunk of 31 columns) marches south over the group's rows and
 // their south neighbour (pf_row_step): pgfu + phiu (unfiltered) -> pgf, fv = phiv + pgv.  Independent of spu.
-template <int L, bool PTOP0>
-__global__ void __launch_bounds__(128, 4)
+template <int L, bool PTOP0, int MB = 4>
+__global__ void __launch_bounds__(128, MB)
 pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, size_t bstride2, size_t bstride3) {
   if (g.pdl_early) gcm_pdl_trigger();
   gcm_pdl_wait();
@@ -800,8 +819,8 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 #define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
 #define PFT_NF 5  // staged fields: su, sv, st, sq, spu
 
-template <int L, int PFT_TJ>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, 512 / (PFT_TI * PFT_TJ))
+template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ)>
+__global__ void __launch_bounds__(PFT_TI * PFT_TJ, MB)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
   if (g.pdl_early) gcm_pdl_trigger();
@@ -1362,7 +1381,14 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     } else {
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
-      if (ptop0)
+      const int mbh = (g_gcm_knob[15] / 10) % 10;  // register-budget variants (knob 15, tens digit)
+      if (L == 9 && ptop0 && (mbh == 5 || mbh == 6 || mbh == 8)) {
+        if constexpr (L == 9) {
+          if (mbh == 5) GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true, 5>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+          else if (mbh == 6) GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true, 6>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+          else GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true, 8>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
+        }
+      } else if (ptop0)
         GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
       else
         GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, false>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
@@ -1450,7 +1476,14 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
       const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(PFT_TI, tj);
-      GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      const int mbu = (g_gcm_knob[15] / 100) % 10;  // register-budget variants (knob 15, hundreds digit)
+      if (L == 9 && (mbu == 5 || mbu == 6)) {
+        if constexpr (L == 9) {
+          if (mbu == 5) GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+          else GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 6>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        }
+      } else
+        GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       GCM_CHECK_LAUNCH();
     }
   } else if (nrowsU > 0) {
