@@ -33,7 +33,8 @@ int g_gcm_knob[GCM_NKNOBS] = {0};
 //  13  TMA update kernel with 4-row tiles: 1 = 4 CTAs per SM (96 registers, spills) instead of 3 (128 registers)
 //  12  L2 promotion of the tensor maps: 0 = 128 B, 1 = none, 2 = 256 B
 //  14  2 = the persistent pipelined filter kernel (bulk-copy prefetch of the next rows) instead of the one-unit-per-CTA one
-//  15  register budgets (L = 9): units digit = CTAs per SM the filter aims at (5, 6, 8), tens = hydro, hundreds = tiled update
+//  15  register budgets (L = 9): units digit = CTAs per SM the filter aims at (4, 6, 8; default 5), tens = hydro (5, 6, 8;
+//      default 4), hundreds = tiled update (5, 6; default 4)
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < GCM_NKNOBS, GCM_ESHAPE);
   g_gcm_knob[idx] = value;

@@ -169,8 +169,9 @@ struct PfFilterIO {
 };
 
 // PLAN > 0: the radices of the plan are compile-time constants (GcmFixedPlan); 0: runtime switch, any plan
-// MB: resident CTAs per SM the register allocation aims at (fixed plans launch 128 threads): 4 = 128 registers
-template <int L, int MODE, int PLAN, int MB = 4>
+// MB: resident CTAs per SM the register allocation aims at (fixed plans launch 128 threads): 5 = 96 registers, which
+// the filter fits without a spill (r2g: 5 CTAs per SM -4 % per launch on the 1440-wide rows; 6 and 8 spill and lose)
+template <int L, int MODE, int PLAN, int MB = 5>
 __global__ void __launch_bounds__(PLAN > 0 ? 128 : 256, PLAN > 0 ? MB : 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
                     size_t bstride2, size_t bstride3) {
@@ -295,6 +296,7 @@ pe25f_filter_pipe_kernel(GcmGeomDev g, const double* __restrict__ sp, const doub
 template <int L, int MODE, int PLAN>
 static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream, const double* sp,
                                  const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3) {
+  if (PLAN > 0 && threads > 128) threads = 128;  // the fixed-plan kernels are compiled for at most 128 threads
   if constexpr (PLAN > 0) {
     // persistent pipelined kernel (knob 14 = 2; measured slower than the one-unit-per-CTA kernel on every grid, r2f:
     // the filter is bound by dependent-instruction latency at 16 warps per SM, not by its loads)
@@ -318,7 +320,7 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
 #ifndef GCM_EMU
   if constexpr (PLAN == 1 && L == 9) {  // register-budget variants of the 1440-wide plan (knob 15, units digit)
     const int mb = g_gcm_knob[15] % 10;
-    if (mb == 5 || mb == 6 || mb == 8) {
+    if (mb == 4 || mb == 6 || mb == 8) {
       if (threads > 128) return gcm_set_status(GCM_EUNSUP);
 #define PF_FILTER_MB(MB_)                                                                                             \
   do {                                                                                                                \
@@ -328,7 +330,7 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
     GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN, MB_>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, \
                    b2, b3);                                                                                           \
   } while (0)
-      if (mb == 5) PF_FILTER_MB(5); else if (mb == 6) PF_FILTER_MB(6); else PF_FILTER_MB(8);
+      if (mb == 4) PF_FILTER_MB(4); else if (mb == 6) PF_FILTER_MB(6); else PF_FILTER_MB(8);
       GCM_CHECK_LAUNCH();
       return GCM_OK;
     }
