@@ -90,6 +90,10 @@ SIGNATURES = {
     "gcm_prof_kinds": (_i, []),
     "gcm_prof_kind_name": (C.c_char_p, [_i]),
     "gcm_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "gcm_grey_radiation": (_i, [_geom, c_dp, c_dp, c_dp, C.c_void_p, C.c_void_p, _d, c_dp, c_dp, c_dp, _d, c_dp, c_dp,
+                                c_stream]),
+    "gcm_solar_timestep": (_i, [_geom, c_dp, c_dp, c_dp, C.c_void_p, C.c_void_p, _d, c_dp, c_dp, c_dp, _d, _d, c_dp, c_dp,
+                                c_stream]),
     "gcm_temperature_convert": (_i, [_i, c_dp, c_dp, c_dp, _z, c_stream]),
 }
 

@@ -37,6 +37,7 @@ SOURCES = {
     "sw2d.cu": ["-fmad=false"],
     "pe2d.cu": ["-fmad=false"],
     "ops.cu": ["-fmad=false"],
+    "physics.cu": ["-fmad=false"],
 }
 
 

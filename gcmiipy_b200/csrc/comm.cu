@@ -509,7 +509,7 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
   GCM_REQUIRE(g && c && cur && star && nxt && ws, GCM_ENULL);
   GCM_REQUIRE(nsteps > 0, GCM_ESHAPE);
   GCM_REQUIRE(!g->d.wrap_j, GCM_EUNSUP);
-  const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi, lo = g->d.row_lo, n = g->d.row_hi - g->d.row_lo;
+  const int hn = g->d.row_lo, hs = g->d.H - g->d.row_hi, lo = g->d.row_lo, hi = g->d.row_hi, n = hi - lo;
   // opt-in terms (gcm_pe25_set_options): they reach j - 2 ... j + 2, so the band carries two halo rows on either side
   // and both states are exchanged, two rows each way, before a whole-band half step (no row-segment schedule)
   const bool ext = gcm_extras_on(g);
@@ -529,10 +529,61 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
       // ONE exchange per step: with 2 + 4 halo rows of the base state the band computes the predictor also on the
       // three rows its corrector reads across the band edges (the neighbours compute the same values from the same
       // inputs with the same kernels), so the star state needs no exchange.  Halves the latency-bound messages.
-      if ((st = band_exchange(g, c, a, hn, hs, main))) return st;
       const int rp[4] = {lo - 1, n + 4, 0, 0}, up[4] = {lo - 1, n + 3, 0, 0};
       const int rc[4] = {lo, n + 1, 0, 0}, uc[4] = {lo, n, 0, 0};
-      if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;  // dynamics.py:231
+      bool done = false;
+#ifndef GCM_EMU
+      const bool split = overlap && n >= 16;
+#else
+      const bool split = overlap && n >= 8;  // streams are program order here: the same calls, one after the other
+#endif
+      if (split) {
+        // Exchange OVERLAPPED with the interior of the predictor.  Rows whose stencil stays inside the owned rows need
+        // no halo: row phase of rows [lo+1, hi-2], update of rows [lo+1, hi-3].  They run on the caller's stream while
+        // the comm stream pushes / pulls the halo rows and then computes the rows next to them (two-segment launches:
+        // row phase of [lo-1, lo] and [hi-1, hi+2], update of [lo-1, lo] and [hi-2, hi+1]); the update of rows lo and
+        // hi-2 reads the row phase of rows lo+1 and hi-2, hence the event between the two.
+        const int none[4] = {0, 0, 0, 0};
+        const int ri[4] = {lo + 1, n - 2, 0, 0}, ui[4] = {lo + 1, n - 3, 0, 0};
+        const int rb[4] = {lo - 1, 2, hi - 1, 4}, ub[4] = {lo - 1, 2, hi - 2, 4};
+#ifndef GCM_EMU
+        GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // `a` is complete on the caller's stream
+        GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
+        cudaStream_t side = c->stream;
+#else
+        cudaStream_t side = main;
+#endif
+        if ((st = band_exchange(g, c, a, hn, hs, side))) return st;
+        st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, ri, none, main);
+        if (st == GCM_OK) {
+#ifndef GCM_EMU
+          GCM_CUDA(cudaEventRecord(c->ev_rint, main));  // row phase of the interior is done
+#endif
+          if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, none, ui, main))) return st;
+          if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rb, none, side))) return st;
+#ifndef GCM_EMU
+          GCM_CUDA(cudaStreamWaitEvent(side, c->ev_rint, 0));
+#endif
+          if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, none, ub, side))) return st;
+#ifndef GCM_EMU
+          GCM_CUDA(cudaEventRecord(c->ev_halo, side));
+          GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));
+#endif
+          done = true;
+        } else {
+          if (st != GCM_EUNSUP) return st;
+#ifndef GCM_EMU
+          GCM_CUDA(cudaEventRecord(c->ev_halo, side));
+          GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));  // no segmented kernels: the whole predictor after the exchange
+#endif
+          if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;
+          done = true;
+        }
+      }
+      if (!done) {
+        if ((st = band_exchange(g, c, a, hn, hs, main))) return st;
+        if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;  // dynamics.py:231
+      }
       if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, uc, main))) return st;  // dynamics.py:234
     } else {
       if ((st = band_half_step(g, c, a, a, star, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:231

@@ -71,9 +71,21 @@ def _minmax(t):
     return mn, mx, int(bad)
 
 
-def full_timestep(p, u, v, t, q, g, dt, utc, geom):
-    """no_limits_2_5d.py:79-94: dynamics step + the STATS diagnostics (the reference's print is dropped)."""
+def solar_timestep(t, p, g, dt, utc, geom):
+    """no_limits_2_5d.py:66-75: grey-radiation heating of the air columns and the ground over dt (t_lw = 0.1, t_sw =
+    0.9, albedo = 0.3) -> (theta_n, GroundVars_n).  One launch (grey_solar.solar_timestep, csrc/physics.cu)."""
+    from . import grey_solar
+    t_n, gt_n = grey_solar.solar_timestep(t, p, g, dt, utc, geom)
+    return t_n, GroundVars(gt_n, g.gw, g.snow, g.ice)
+
+
+def full_timestep(p, u, v, t, q, g, dt, utc, geom, physics=False):
+    """no_limits_2_5d.py:79-94: dynamics step + the STATS diagnostics (the reference's print is dropped).
+    physics=True also runs the column physics the reference keeps below its early `return` (:96-103): solar_timestep on
+    the new state."""
     p, u, v, t, q = matsuno_timestep(p, u, v, t, q, dt, geom)
+    if physics:
+        t, g = solar_timestep(t, p, g, dt, utc, geom)
     umin, umax, _ = _minmax(_host.dev(u))
     vmin, vmax, _ = _minmax(_host.dev(v))
     STATS["u_max"].append(umax)

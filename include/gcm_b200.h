@@ -320,6 +320,23 @@ int gcm_prof_kinds(void);
 const char* gcm_prof_kind_name(int kind);
 int gcm_prof_collect(double* h_ms, long long* h_launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Grey-radiation column physics: the step after the dynamics in no_limits_2_5d.full_timestep.
+ * One thread per column, layer recursions in the reference's order.
+ *   gcm_grey_radiation  grey_solar.basic_grey_radiation (grey_solar.py:358-563) with zenith_angle (:49-68, declination
+ *                       0): p surface pressure [H][W], tt true temperature [L][H][W], gt ground temperature [H][W] ->
+ *                       dTdt [L][H][W] (K/s), dt_ground [H][W] (K/s).
+ *   gcm_solar_timestep  no_limits_2_5d.solar_timestep (:66-75): potential temperature t -> t_n, gt -> gt_n over dt.
+ * h_lw / h_sw: HOST arrays [L] = t_lw ** dsig, t_sw ** dsig (basic_grey_transmittances, :323-333); sinlat / coslat
+ * [H], lon [W]: device tables in radians; hour_angle = utc / (-24 h) * 360 deg in radians (:51).  Needs L <= 24.
+ * ---------------------------------------------------------------------------------------------- */
+int gcm_grey_radiation(const gcm_geom* g, const double* p, const double* tt, const double* gt, const double* h_lw,
+                       const double* h_sw, double albedo, const double* sinlat, const double* coslat, const double* lon,
+                       double hour_angle, double* dTdt, double* dt_ground, void* stream);
+int gcm_solar_timestep(const gcm_geom* g, const double* p, const double* t, const double* gt, const double* h_lw,
+                       const double* h_sw, double albedo, const double* sinlat, const double* coslat, const double* lon,
+                       double hour_angle, double dt, double* t_n, double* gt_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -698,3 +698,71 @@ def synthetic_state(geom, seed=1234, amp_u=1.0, amp_p=50.0, amp_t=0.5):
     t = t + amp_t * smooth((L, H, W))
     v[:, -1, :] = 0
     return p, u, v, t, q
+
+
+# ---- grey-radiation column physics: grey_solar.py:40-68, :323-333, :358-563; no_limits_2_5d.py:66-75 ----
+sb_constant = 5.67e-8                 # W m-2 K-4    constants.py:71
+solar_constant = 1.3608 * 1000.0      # W m-2        constants.py:59 (1.3608 kW m-2)
+Cg = 1.13e6                           # J K-1 m-3    constants.py:25
+
+
+def solar_zenith_angle(latitude, hour_angle, declination):
+    """grey_solar.py:40-46: cosine of the solar zenith angle."""
+    return np.sin(latitude) * np.sin(declination) + np.cos(latitude) * np.cos(declination) * np.cos(hour_angle)
+
+
+def zenith_angle(longs, lats, utc_s, geom):
+    """grey_solar.py:49-68 (declination 0): max(cos zenith, 0) [H, W]; utc_s = model time in seconds."""
+    hour_angle = utc_s / (-24 * 3600.0) * 360 * (math.pi / 180.0)
+    t_longs = np.tile(longs, (geom.height, 1))
+    point_angle = t_longs + hour_angle
+    return np.maximum(solar_zenith_angle(lats, point_angle, 0.0), 0)
+
+
+def basic_grey_transmittances(t_lw, t_sw, geom):
+    """grey_solar.py:323-333 (AD 2.35): per-layer long-wave / short-wave transmittance, shape of geom.dsig."""
+    e_n = 1 - t_lw ** (geom.dsig)
+    e_n_sw = 1 - t_sw ** (geom.dsig)
+    return 1 - e_n, 1 - e_n_sw
+
+
+def basic_grey_radiation(p, tp, tt, gt, t_lw, t_sw, albedo, utc_s, geom):
+    """grey_solar.py:358-563 (the grey atmosphere of AD 2.7) -> (dT/dt [L, H, W] in K/s, d(ground T)/dt [H, W]).
+    p: surface pressure, tp: layer pressure (unused by the reference too), tt: true temperature, gt: ground temperature."""
+    L = geom.layers
+    lw, sw = basic_grey_transmittances(t_lw, t_sw, geom)
+    emission = (1 - lw) * sb_constant * tt ** 4
+    cum_sw_from_top = np.cumprod(sw[::-1], axis=0)[::-1]
+    cum_lw_from_bottom = np.cumprod(lw, axis=0)
+    clw_b_div = cum_lw_from_bottom / lw
+    B = np.sum(emission * clw_b_div, axis=0)                                   # 2.25
+    sza = zenith_angle(geom.long, geom.lat, utc_s, geom)
+    Sc = solar_constant * sza
+    S = (1 - albedo) * Sc * cum_sw_from_top[0]                                 # 2.26
+    U_s = 1 * sb_constant * gt ** 4                                            # 2.27
+    dt_ground = (B + S - U_s) / Cg / 0.1
+    shape = (L + 1, geom.height, geom.width)
+    upwelling, downwelling = np.zeros(shape), np.zeros(shape)
+    absorbed_dw = np.zeros(tt.shape)
+    for i in reversed(range(L)):                                               # long wave from above
+        absorbed_dw[i] = downwelling[i + 1] * (1 - lw[i])
+        downwelling[i] = downwelling[i + 1] * lw[i] + emission[i]
+    absorbed = np.zeros(tt.shape)
+    for i in range(L):                                                         # long wave from below (atmosphere only)
+        absorbed[i] = upwelling[i] * (1 - lw[i])
+        upwelling[i + 1] = upwelling[i] * lw[i] + emission[i]
+    U_n = clw_b_div * U_s * (1 - lw)                                           # 2.30
+    S_n = (1 - sw) * cum_sw_from_top / sw * Sc                                 # 2.31
+    B_n = emission                                                             # 2.32
+    dTdt = (U_n + S_n - 2 * B_n + absorbed_dw + absorbed) * (G / (Cp * p * geom.dsig))   # 2.34
+    return dTdt, dt_ground
+
+
+def solar_timestep(t, p, gt, dt, utc_s, geom):
+    """no_limits_2_5d.py:66-75 -> (theta_n, ground temperature_n); t_lw = 0.1, t_sw = 0.9, albedo = 0.3."""
+    tp = p * geom.sig + geom.ptop
+    tt = to_true_temp(t, tp)
+    dt_air, dt_ground = basic_grey_radiation(p, tp, tt, gt, 0.1, 0.9, 0.3, utc_s, geom)
+    gt_n = gt + dt_ground * dt
+    tt_n = tt + dt_air * dt
+    return to_potential_temp(tt_n, tp), gt_n
