@@ -41,6 +41,8 @@ WORKLOADS = {
 WORKLOADS_2D = {
     "c1": ("sw2d", 64, 64, 300.0, 300e3, "2-D shallow-water Matsuno C-grid 64x64, dx = 300 km, dt = 300 s (BASELINE configs[0]; the "
            "reference's dt = 700 s diverges after 8 steps, SURVEY 8d)"),
+    "c1dt700": ("sw2d", 64, 64, 700.0, 300e3, "2-D shallow-water Matsuno C-grid 64x64 at the reference's own dt = 700 s "
+                "(matsuno_c_grid.py:146-157): unstable, reported for 8 steps only (SURVEY 8d)"),
     "c1big": ("sw2d", 8192, 8192, 300.0, 300e3, "2-D shallow-water Matsuno C-grid 8192x8192 (HBM-resident: 1.6 GB of state)"),
     "p2d": ("pe2d", 4096, 4096, 100.0, 300e3, "2-D primitive equations (no_limits_2d) 4096x4096"),
 }
@@ -439,6 +441,8 @@ def run_2d(args):
     """c1 / c1big: matsuno_c_grid.matsumo_scheme (48 B per cell-update: u, v, h read + written once per step);
     p2d: no_limits_2d.matsuno_timestep (64 B: p, u, v, t; q untouched).  Single GPU."""
     kind, H, W, dt, dx, desc = WORKLOADS_2D[args.workload]
+    if args.workload == "c1dt700":
+        args.steps = min(args.steps, 8)          # the scheme diverges after 8 steps at this dt
     bpc = 48.0 if kind == "sw2d" else 64.0
     cells = H * W
     if args.impl == "reference":

@@ -89,7 +89,8 @@ class BandStepper:
         glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
         self._north_g, self._south_g = (glob(self.north), glob(self.south)) if world > 1 else (0, 0)
         self.nsteps_done = 0
-        self.overlap = True
+        import os
+        self.overlap = os.environ.get("GCM_BAND_OVERLAP", "1") != "0"     # exchange under the interior predictor rows
         self.comm = None
         self.peer = False
         if native:

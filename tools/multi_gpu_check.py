@@ -39,8 +39,8 @@ def main():
     whole.step(dt, args.steps)
     ref = whole.download()
     ok = True
-    variants = ((True, False, True, True), (True, False, True, False), (True, True, False, True), (True, True, False, False),
-                (True, False, False, True), (False, False, False, False))
+    variants = ((True, True, True, True), (True, False, True, True), (True, True, True, False), (True, True, False, True),
+                (True, True, False, False), (True, False, False, True), (False, False, False, False))
     for native, overlap, wide, peer in variants:
         os.environ["GCM_BAND_PEER"] = "1" if peer else "0"      # peer mailboxes over NVLink, or the NCCL ring
         b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
