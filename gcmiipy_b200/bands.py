@@ -90,7 +90,9 @@ class BandStepper:
         self._north_g, self._south_g = (glob(self.north), glob(self.south)) if world > 1 else (0, 0)
         self.nsteps_done = 0
         import os
-        self.overlap = os.environ.get("GCM_BAND_OVERLAP", "1") != "0"     # exchange under the interior predictor rows
+        # 1 = the halo exchange of the new state runs under the interior rows of the corrector's update (default);
+        # 2 = under the interior rows of the predictor; 0 = before the predictor, nothing overlapped (csrc/comm.cu)
+        self.overlap = int(os.environ.get("GCM_BAND_OVERLAP", "1"))
         self.comm = None
         self.peer = False
         if native:

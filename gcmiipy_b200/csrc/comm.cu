@@ -531,27 +531,36 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
       // inputs with the same kernels), so the star state needs no exchange.  Halves the latency-bound messages.
       const int rp[4] = {lo - 1, n + 4, 0, 0}, up[4] = {lo - 1, n + 3, 0, 0};
       const int rc[4] = {lo, n + 1, 0, 0}, uc[4] = {lo, n, 0, 0};
+      const int none[4] = {0, 0, 0, 0};
       bool done = false;
 #ifndef GCM_EMU
-      const bool split = overlap && n >= 16;
+      cudaStream_t side = c->stream;
 #else
-      const bool split = overlap && n >= 8;  // streams are program order here: the same calls, one after the other
+      cudaStream_t side = main;  // streams are program order on the emulator: the same calls, one after the other
 #endif
-      if (split) {
-        // Exchange OVERLAPPED with the interior of the predictor.  Rows whose stencil stays inside the owned rows need
-        // no halo: row phase of rows [lo+1, hi-2], update of rows [lo+1, hi-3].  They run on the caller's stream while
-        // the comm stream pushes / pulls the halo rows and then computes the rows next to them (two-segment launches:
-        // row phase of [lo-1, lo] and [hi-1, hi+2], update of [lo-1, lo] and [hi-2, hi+1]); the update of rows lo and
-        // hi-2 reads the row phase of rows lo+1 and hi-2, hence the event between the two.
-        const int none[4] = {0, 0, 0, 0};
+      // overlap = 1 (default): the exchange of the NEW state runs under the interior rows of the corrector's update.
+      // The update first writes the rows the neighbours are waiting for (the first 4 and the last 2 owned rows: one
+      // two-segment launch), then the comm stream pushes them / pulls the neighbours' while the caller's stream updates
+      // the other n - 6 rows -- the longest kernel of the step, with nothing else to do on the halo rows.  One extra
+      // small launch per step; the next predictor waits for the halos.  overlap = 2: the exchange runs under the
+      // interior rows of the PREDICTOR instead (ten extra small launches per step: measured slower on 8 GPUs, r2j).
+      const bool tail = overlap == 1 && n >= 12;
+      const bool split = overlap == 2 && n >= 16;
+      if (tail && s > 0) {
+#ifndef GCM_EMU
+        GCM_CUDA(cudaStreamWaitEvent(main, c->ev_halo, 0));  // halos of `a`: exchanged under the previous corrector
+#endif
+        if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;
+        done = true;
+      } else if (split) {
+        // Rows whose stencil stays inside the owned rows need no halo: row phase of rows [lo+1, hi-2], update of rows
+        // [lo+1, hi-3] on the caller's stream, while the comm stream exchanges and then computes the rows next to the
+        // halos (two-segment launches); the update of rows lo and hi-2 reads the row phase of rows lo+1 and hi-2.
         const int ri[4] = {lo + 1, n - 2, 0, 0}, ui[4] = {lo + 1, n - 3, 0, 0};
         const int rb[4] = {lo - 1, 2, hi - 1, 4}, ub[4] = {lo - 1, 2, hi - 2, 4};
 #ifndef GCM_EMU
         GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // `a` is complete on the caller's stream
-        GCM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
-        cudaStream_t side = c->stream;
-#else
-        cudaStream_t side = main;
+        GCM_CUDA(cudaStreamWaitEvent(side, c->ev_ready, 0));
 #endif
         if ((st = band_exchange(g, c, a, hn, hs, side))) return st;
         st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, ri, none, main);
@@ -584,7 +593,24 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
         if ((st = band_exchange(g, c, a, hn, hs, main))) return st;
         if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;  // dynamics.py:231
       }
-      if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, uc, main))) return st;  // dynamics.py:234
+      if (tail && s + 1 < nsteps) {
+        // corrector (dynamics.py:234): row phase of every row, update of the rows the neighbours need, exchange of the
+        // new state on the comm stream beside the update of the remaining rows
+        const int ub2[4] = {lo, hs, hi - hn, hn}, ui2[4] = {lo + hs, n - hs - hn, 0, 0};
+        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, none, main))) return st;
+        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, none, ub2, main))) return st;
+#ifndef GCM_EMU
+        GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // the boundary rows of `b` are written
+        GCM_CUDA(cudaStreamWaitEvent(side, c->ev_ready, 0));
+#endif
+        if ((st = band_exchange(g, c, b, hn, hs, side))) return st;
+#ifndef GCM_EMU
+        GCM_CUDA(cudaEventRecord(c->ev_halo, side));
+#endif
+        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, none, ui2, main))) return st;
+      } else {
+        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, uc, main))) return st;  // dynamics.py:234
+      }
     } else {
       if ((st = band_half_step(g, c, a, a, star, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:231
       if ((st = band_half_step(g, c, a, star, b, dt, overlap, ws, ws_bytes, main))) return st;     // dynamics.py:234

@@ -296,7 +296,13 @@ int gcm_geom_aux(const gcm_geom* cg, void** stream, void** ev_fork, void** ev_jo
   if (!g->aux_stream) {
     cudaStream_t q;
     cudaEvent_t a, b;
-    GCM_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    if (g_gcm_knob[3] == 2) {  // the side stream carries the longer chain (hydro -> filter): schedule its CTAs first
+      int lo = 0, hi = 0;
+      GCM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      GCM_CUDA(cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, hi));
+    } else {
+      GCM_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    }
     GCM_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     GCM_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     g->aux_stream = q;

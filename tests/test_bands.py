@@ -117,16 +117,14 @@ def test_native_band_loop_single_rank(backend, knob4, wide):
     whole = dynamics.Stepper(geom, *s)
     band = bands.BandStepper(geom, *s, rank=0, world=1, native=True, wide_halo=wide)
     assert band.comm is not None and (band.halo_n, band.halo_s) == ((2, 4) if wide else (1, 2))
-    for n in (3, 2):                                    # odd, then even: both buffer parities
-        whole.step(450.0, n)
-        band.step(450.0, n)
-        for a, b in zip(band.gather(), whole.download()):
-            assert np.array_equal(a, b)
-    band.overlap = False
-    whole.step(450.0, 1)
-    band.step(450.0, 1)
-    for a, b in zip(band.gather(), whole.download()):
-        assert np.array_equal(a, b)
+    assert band.overlap == 1          # default: the exchange of the new state under the corrector's interior update
+    for mode in (1, 2, 0):            # 2: exchange under the predictor's interior rows; 0: nothing overlapped
+        band.overlap = mode
+        for n in (3, 2, 1):                                 # odd, even, single: both buffer parities, first / last step
+            whole.step(450.0, n)
+            band.step(450.0, n)
+            for a, b in zip(band.gather(), whole.download()):
+                assert np.array_equal(a, b)
 
 
 def test_half_step_on_row_segments_equals_whole_band(backend):

@@ -39,8 +39,10 @@ def main():
     whole.step(dt, args.steps)
     ref = whole.download()
     ok = True
-    variants = ((True, True, True, True), (True, False, True, True), (True, True, True, False), (True, True, False, True),
-                (True, True, False, False), (True, False, False, True), (False, False, False, False))
+    # (native loop, overlap: 0 none / 1 exchange under the corrector's interior update / 2 under the predictor's interior,
+    #  one exchange per step, peer mailboxes)
+    variants = ((True, 1, True, True), (True, 2, True, True), (True, 0, True, True), (True, 1, True, False),
+                (True, 1, False, True), (True, 1, False, False), (True, 0, False, True), (False, 0, False, False))
     for native, overlap, wide, peer in variants:
         os.environ["GCM_BAND_PEER"] = "1" if peer else "0"      # peer mailboxes over NVLink, or the NCCL ring
         b = bands.BandStepper(geom, *s0, native=native, wide_halo=wide)
