@@ -35,6 +35,8 @@ WORKLOADS = {
     "c2": (46, 72, 9, 225.0, 1, "GISS 4x5deg 72x46x9 2.5-D Matsuno step (BASELINE configs[1])"),
     "c4": (24, 36, 9, 450.0, 1024, "ensemble of 1024 x 8x10deg 36x24x9 runs (BASELINE configs[3])"),
     # tuning aid: the per-rank share of configs[4] on 8 GPUs as a stand-alone periodic grid (not a BASELINE config)
+    # tuning aid: a quarter of configs[4]; on 2 GPUs every rank holds a 90-row band, as on 8 GPUs of the full grid
+    "c5q": (180, 1440, 9, 10.0, 1, "1440x180x9: a quarter of configs[4] (tuning aid: 2 ranks = the band size of 8 ranks on the full grid)"),
     "c5b8": (90, 1440, 9, 10.0, 1, "1440x90x9: one of 8 latitude bands of configs[4], stepped alone (tuning aid)"),
 }
 # 2-D schemes: name: (kind, H, W, dt, dx, description)

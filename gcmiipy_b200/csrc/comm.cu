@@ -538,11 +538,10 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
 #else
       cudaStream_t side = main;  // streams are program order on the emulator: the same calls, one after the other
 #endif
-      // overlap = 1 (default): the exchange of the NEW state runs under the interior rows of the corrector's update.
-      // The update first writes the rows the neighbours are waiting for (the first 4 and the last 2 owned rows: one
-      // two-segment launch), then the comm stream pushes them / pulls the neighbours' while the caller's stream updates
-      // the other n - 6 rows -- the longest kernel of the step, with nothing else to do on the halo rows.  One extra
-      // small launch per step; the next predictor waits for the halos.  overlap = 2: the exchange runs under the
+      // overlap = 1: the exchange of the NEW state runs under the interior rows of the corrector's update.  The comm
+      // stream updates the rows the neighbours are waiting for (the first 4 and the last 2 owned rows: one two-segment
+      // launch) and pushes them / pulls the neighbours' while the caller's stream updates the other n - 6 rows -- the
+      // longest kernel of the step.  One extra small launch per step; the next predictor waits for the halos.  overlap = 2: the exchange runs under the
       // interior rows of the PREDICTOR instead (ten extra small launches per step: measured slower on 8 GPUs, r2j).
       const bool tail = overlap == 1 && n >= 12;
       const bool split = overlap == 2 && n >= 16;
@@ -594,15 +593,16 @@ extern "C" int gcm_band_matsuno_step(const gcm_geom* g, gcm_comm* c, const gcm_s
         if ((st = gcm_pe25_half_step_rows(g, a, a, star, dt, 1, ws, ws_bytes, rp, up, main))) return st;  // dynamics.py:231
       }
       if (tail && s + 1 < nsteps) {
-        // corrector (dynamics.py:234): row phase of every row, update of the rows the neighbours need, exchange of the
-        // new state on the comm stream beside the update of the remaining rows
+        // corrector (dynamics.py:234): row phase of every row on the caller's stream; then, side by side, the update of
+        // the n - 6 interior rows there and, on the comm stream, the update of the rows the neighbours need followed by
+        // the exchange of the new state
         const int ub2[4] = {lo, hs, hi - hn, hn}, ui2[4] = {lo + hs, n - hs - hn, 0, 0};
         if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, rc, none, main))) return st;
-        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, none, ub2, main))) return st;
 #ifndef GCM_EMU
-        GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // the boundary rows of `b` are written
+        GCM_CUDA(cudaEventRecord(c->ev_ready, main));  // the row phase of the corrector is complete
         GCM_CUDA(cudaStreamWaitEvent(side, c->ev_ready, 0));
 #endif
+        if ((st = gcm_pe25_half_step_rows(g, a, star, b, dt, 1, ws, ws_bytes, none, ub2, side))) return st;
         if ((st = band_exchange(g, c, b, hn, hs, side))) return st;
 #ifndef GCM_EMU
         GCM_CUDA(cudaEventRecord(c->ev_halo, side));
