@@ -90,9 +90,10 @@ class BandStepper:
         self._north_g, self._south_g = (glob(self.north), glob(self.south)) if world > 1 else (0, 0)
         self.nsteps_done = 0
         import os
-        # 1 = the halo exchange of the new state runs under the interior rows of the corrector's update (default);
-        # 2 = under the interior rows of the predictor; 0 = before the predictor, nothing overlapped (csrc/comm.cu)
-        self.overlap = int(os.environ.get("GCM_BAND_OVERLAP", "1"))
+        # one-exchange schedule: 0 = exchange, then the step (default: fastest on 2 ... 8 B200s, profiles/round2 r2j-r2l);
+        # 1 = the exchange of the new state runs beside the interior rows of the corrector's update; 2 = beside the
+        # interior rows of the predictor.  Two-exchange schedule (wide_halo=False): non-zero = interior rows first.
+        self.overlap = int(os.environ.get("GCM_BAND_OVERLAP", "0"))
         self.comm = None
         self.peer = False
         if native:

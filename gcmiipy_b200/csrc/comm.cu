@@ -322,6 +322,7 @@ __device__ __forceinline__ void gcm_store_sys(unsigned long long* p, unsigned lo
 // publishes the message: system-wide fence, then the message number into both neighbours' flags.
 __global__ void band_push_kernel(gcm_state s, int H, int W, int L, GcmHaloJob to_n, GcmHaloJob to_s, size_t slot_doubles,
                                  GcmMboxHeader* mine, GcmMboxHeader* north, GcmMboxHeader* south) {
+  gcm_pdl_wait();  // launched as a programmatic dependent of the update kernel: the rows it sends are complete here
   __shared__ unsigned long long seq_s;
   __shared__ int last_s;
   if (threadIdx.x == 0) seq_s = mine->seq + 1;  // written only by the closing block of the previous push
@@ -352,6 +353,7 @@ __global__ void band_push_kernel(gcm_state s, int H, int W, int L, GcmHaloJob to
 // `timeouts` instead of hanging the GPU.
 __global__ void band_pull_kernel(gcm_state s, int H, int W, int L, GcmHaloJob from_s, GcmHaloJob from_n,
                                  size_t slot_doubles, GcmMboxHeader* mine) {
+  gcm_pdl_wait();  // the push of this rank (same stream) has bumped mine->seq
   __shared__ unsigned long long seq_s;
   if (threadIdx.x == 0) {
     const unsigned long long seq = mine->seq;
@@ -397,13 +399,13 @@ static int band_exchange_peer(const gcm_geom* g, gcm_comm* c, const gcm_state* s
   unsigned nblk = (unsigned)((total + 255) / 256);
   nblk = nblk < 1 ? 1 : (nblk > 148 * 2 ? 148 * 2 : nblk);
   if (phase & 1) {
-    GCM_LAUNCH(band_push_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{lo, hs, n_from_s},
-               GcmHaloJob{hi - hn, hn, s_from_n}, slot, mine, north, south);
+    GCM_LAUNCH_DEP(band_push_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{lo, hs, n_from_s},
+                   GcmHaloJob{hi - hn, hn, s_from_n}, slot, mine, north, south);
     GCM_CHECK_LAUNCH();
   }
   if (phase & 2) {
-    GCM_LAUNCH(band_pull_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{hi, hs, my_from_s},
-               GcmHaloJob{lo - hn, hn, my_from_n}, slot, mine);
+    GCM_LAUNCH_DEP(band_pull_kernel, dim3(nblk), dim3(256), 0, q, *s, H, W, L, GcmHaloJob{hi, hs, my_from_s},
+                   GcmHaloJob{lo - hn, hn, my_from_n}, slot, mine);
     GCM_CHECK_LAUNCH();
   }
   return GCM_OK;
