@@ -311,16 +311,22 @@ def run_native(args):
     host_in = [x.cpu().pin_memory() for x in stepper.tensors()]
     host_out = [torch.empty_like(x).pin_memory() for x in host_in]
     h2d = sum(x.numel() * 8 for x in host_in)
+    pipelined = world == 1 and members == 1 and not args.e2e_serial     # steps overlap across calls (host_step.cu)
+    kw = {"pipelined": True} if pipelined else {}
     for _ in range(2):
-        stepper.step_host(host_in, host_out, dt, 1)
+        stepper.step_host(host_in, host_out, dt, 1, **kw)
+    if pipelined:
+        stepper.host_join()
     barrier()
     e2e_ms = []
     for _ in range(3):
         barrier()
         e0.record()
         for _ in range(args.steps):
-            stepper.step_host(host_in, host_out, dt, 1)
+            stepper.step_host(host_in, host_out, dt, 1, **kw)
             host_in, host_out = host_out, host_in
+        if pipelined:
+            stepper.host_join()          # the last copy-outs are inside the timed region
         e1.record()
         barrier()
         tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -406,7 +412,9 @@ def run_native(args):
                            if world > 1 and members == 1 else None),
         "peer_timeouts": stepper.peer_timeouts() if world > 1 and members == 1 and getattr(stepper, "comm", None) else None,
         "sim_days_per_day": (args.steps / (ms * 1e-3)) * dt,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+                "call": "Stepper.step_host(pinned host state in, pinned host state out) every step"
+                        + (", pipelined across steps, joined inside the timed region" if pipelined else "")},
         "gpu_launches": int(round((launches_per_step or 0) * args.steps)),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
@@ -543,6 +551,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS) + sorted(WORKLOADS_2D))
     ap.add_argument("--repeats", type=int, default=5, help="timed calls of --steps steps (median reported; at least 200 ms)")
     ap.add_argument("--no-hash", action="store_true", help="skip the SHA-256 of the final state")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e through the joining host step (no overlap across steps)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 = fused kernels (default), 1 = general 4-kernel path")

@@ -41,6 +41,8 @@ SIGNATURES = {
     "gcm_pe25_half_step_rows": (_i, [_geom, _st, _st, _st, _d, _i, c_dp, _z, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      c_stream]),
     "gcm_pe25_matsuno_step_host": (_i, [_geom, _st, _st, _st, _st, _st, _d, _i, c_dp, _z, c_stream]),
+    "gcm_pe25_matsuno_step_host_pipelined": (_i, [_geom, _st, _st, _st, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
+    "gcm_host_pipe_join": (_i, [c_stream]),
     "gcm_comm_unique_id": (_i, [C.c_void_p]),
     "gcm_comm_create": (_i, [_i, _i, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gcm_comm_destroy": (_i, [C.c_void_p]),

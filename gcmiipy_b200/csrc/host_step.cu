@@ -26,6 +26,9 @@ extern int g_gcm_knob[GCM_NKNOBS];  // pe25_fast.cu; knob 6 = latitude blocks of
 struct GcmHostPipe {
   cudaStream_t q_in, q_out;
   cudaEvent_t ev_start, ev_in[GCM_HOST_MAX_BLOCKS + 1], ev_done[GCM_HOST_MAX_BLOCKS], ev_out;
+  cudaEvent_t ev_outb[GCM_HOST_MAX_BLOCKS];  // block b of the newest pipelined call has reached the host
+  int outb_valid;                            // ev_outb[] have been recorded at least once
+  int pending;                               // a pipelined call has not been joined yet
 };
 
 #ifndef GCM_EMU
@@ -46,6 +49,7 @@ static int host_pipe(GcmHostPipe** out) {
     GCM_CUDA(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
     for (int b = 0; b <= GCM_HOST_MAX_BLOCKS; ++b) GCM_CUDA(cudaEventCreateWithFlags(&p->ev_in[b], cudaEventDisableTiming));
     for (int b = 0; b < GCM_HOST_MAX_BLOCKS; ++b) GCM_CUDA(cudaEventCreateWithFlags(&p->ev_done[b], cudaEventDisableTiming));
+    for (int b = 0; b < GCM_HOST_MAX_BLOCKS; ++b) GCM_CUDA(cudaEventCreateWithFlags(&p->ev_outb[b], cudaEventDisableTiming));
     g_pipe = p;
   }
   *out = g_pipe;
@@ -98,6 +102,11 @@ extern "C" int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_
   if (nblocks > 1 && gcm_pe25_fast_supported(g)) {
     GcmHostPipe* pp;
     if ((st = host_pipe(&pp))) return st;
+    if (pp->pending) {  // an unjoined pipelined call: its copy-outs come first
+      GCM_CUDA(cudaStreamWaitEvent(main, pp->ev_out, 0));
+      pp->pending = 0;
+    }
+    pp->outb_valid = 0;
     GCM_CUDA(cudaEventRecord(pp->ev_start, main));  // everything the caller queued before is done first
     GCM_CUDA(cudaStreamWaitEvent(pp->q_in, pp->ev_start, 0));
     GCM_CUDA(cudaStreamWaitEvent(pp->q_out, pp->ev_start, 0));
@@ -137,4 +146,93 @@ extern "C" int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_
   if ((st = gcm_pe25_matsuno_step(g, d_cur, d_nxt, dt, 1, 1, ws, ws_bytes, main))) return st;
   (void)d_star;
   return copy_rows(g, h_out, d_nxt, 0, H, 1, main);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same step for a caller that steps again and again through host buffers (a time loop whose state lives in host
+// memory between steps): consecutive calls are PIPELINED ACROSS STEPS.  gcm_pe25_matsuno_step_host joins the copy-out
+// stream into the caller's stream before it returns, so the copy-in of the next call cannot start before the last
+// block of this one has reached the host, and each direction of the PCIe link idles while the other fills / drains.
+// Here
+//   * the call does NOT join: h_out is complete only after gcm_host_pipe_join(stream) (or a later non-pipelined call);
+//   * the blocks are visited in the rotated order start_block, start_block + 1, ... (mod nblocks); a caller that passes
+//     start_block = call number makes block k of call n + 1 depend only on blocks k - 1 .. k + 1 of call n (the
+//     periodic grid is a ring of blocks), which call n finished two positions earlier;
+//   * the copy-in of block b waits for the copy-out of block b of the previous pipelined call (the caller may be feeding
+//     the previous output back in: bench.py and a host-resident time loop do), nothing else;
+//   * d_in / d_out must ALTERNATE between two pairs of device states from call to call (the copy-in of call n + 1
+//     overlaps the compute and copy-out of call n); d_star and the workspace are shared (compute is in stream order).
+// Same kernels, same row segments per block: bit-identical to gcm_pe25_matsuno_step.  nblocks >= 3.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gcm_pe25_matsuno_step_host_pipelined(const gcm_geom* g, const gcm_state* h_in, const gcm_state* h_out,
+                                                    const gcm_state* d_in, const gcm_state* d_star, const gcm_state* d_out,
+                                                    double dt, int nblocks, int start_block, void* ws, size_t ws_bytes,
+                                                    void* stream) {
+  GCM_REQUIRE(g && h_in && h_out && d_in && d_star && d_out && ws, GCM_ENULL);
+  GCM_REQUIRE(g->d.wrap_j && !gcm_extras_on(g) && gcm_pe25_fast_supported(g), GCM_EUNSUP);
+#ifdef GCM_EMU
+  (void)dt; (void)nblocks; (void)start_block; (void)ws_bytes; (void)stream;
+  return GCM_EUNSUP;
+#else
+  const int H = g->d.H;
+  cudaStream_t main = (cudaStream_t)stream;
+  if (nblocks <= 0) nblocks = g_gcm_knob[6] > 0 ? g_gcm_knob[6] : 8;
+  if (nblocks > GCM_HOST_MAX_BLOCKS) nblocks = GCM_HOST_MAX_BLOCKS;
+  while (nblocks > 3 && H / nblocks < 8) --nblocks;
+  GCM_REQUIRE(nblocks >= 3 && H / nblocks >= 8, GCM_ESHAPE);
+  GcmHostPipe* pp;
+  int st;
+  if ((st = host_pipe(&pp))) return st;
+  auto lo = [&](int b) { return (int)((long long)b * H / nblocks); };  // balanced blocks: sizes differ by at most one
+  auto wrapb = [&](int b) { return ((b % nblocks) + nblocks) % nblocks; };
+  const int s0 = wrapb(start_block);
+  GCM_CUDA(cudaEventRecord(pp->ev_start, main));  // everything the caller queued before (incl. the previous compute)
+  GCM_CUDA(cudaStreamWaitEvent(pp->q_in, pp->ev_start, 0));
+  // copy-in, blocks s0 - 1, s0, s0 + 1, ... : block x waits for the previous call's copy-out of block x
+  for (int k = 0; k < nblocks; ++k) {
+    const int x = wrapb(s0 - 1 + k);
+    if (pp->outb_valid) GCM_CUDA(cudaStreamWaitEvent(pp->q_in, pp->ev_outb[x], 0));
+    if ((st = copy_rows(g, d_in, h_in, lo(x), lo(x + 1), 0, pp->q_in))) return st;
+    GCM_CUDA(cudaEventRecord(pp->ev_in[x], pp->q_in));
+  }
+  for (int k = 0; k < nblocks; ++k) {
+    const int b = wrapb(s0 + k);
+    const int r0 = lo(b), r1 = lo(b + 1);
+    // rows [r0 - 2, r1 + 4) of the ring: the block itself and its two neighbours
+    GCM_CUDA(cudaStreamWaitEvent(main, pp->ev_in[wrapb(b - 1)], 0));
+    GCM_CUDA(cudaStreamWaitEvent(main, pp->ev_in[b], 0));
+    GCM_CUDA(cudaStreamWaitEvent(main, pp->ev_in[wrapb(b + 1)], 0));
+    int sr[4], su[4];
+    wrap_seg(r0 - 1, r1 + 3, H, sr);  // predictor: star rows [r0-1, r1+2) need the row phase of [r0-1, r1+3)
+    wrap_seg(r0 - 1, r1 + 2, H, su);
+    if ((st = gcm_pe25_half_step_rows(g, d_in, d_in, d_star, dt, 1, ws, ws_bytes, sr, su, main))) return st;
+    wrap_seg(r0, r1 + 1, H, sr);      // corrector: rows [r0, r1)
+    wrap_seg(r0, r1, H, su);
+    if ((st = gcm_pe25_half_step_rows(g, d_in, d_star, d_out, dt, 1, ws, ws_bytes, sr, su, main))) return st;
+    GCM_CUDA(cudaEventRecord(pp->ev_done[b], main));
+    GCM_CUDA(cudaStreamWaitEvent(pp->q_out, pp->ev_done[b], 0));
+    if ((st = copy_rows(g, h_out, d_out, r0, r1, 1, pp->q_out))) return st;
+    GCM_CUDA(cudaEventRecord(pp->ev_outb[b], pp->q_out));
+  }
+  GCM_CUDA(cudaEventRecord(pp->ev_out, pp->q_out));
+  pp->outb_valid = 1;
+  pp->pending = 1;
+  return GCM_OK;
+#endif
+}
+
+// makes `stream` wait for the copy-outs of every pipelined call issued so far on this device
+extern "C" int gcm_host_pipe_join(void* stream) {
+#ifndef GCM_EMU
+  GcmHostPipe* pp;
+  int st;
+  if ((st = host_pipe(&pp))) return st;
+  if (pp->pending) {
+    GCM_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, pp->ev_out, 0));
+    pp->pending = 0;
+  }
+#else
+  (void)stream;
+#endif
+  return GCM_OK;
 }

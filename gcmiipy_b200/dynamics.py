@@ -116,11 +116,36 @@ class Stepper:
         self.cur, self.nxt = self.nxt, self.cur
         self.nsteps_done += int(nsteps)
 
-    def step_host(self, host_in, host_out, dt, nsteps=1):
+    def step_host(self, host_in, host_out, dt, nsteps=1, pipelined=False):
         """Host-resident caller: copy the five (pinned) host tensors `host_in` to the device, advance, copy the
         new state into the five (pinned) host tensors `host_out`.  All asynchronous on the current stream.
         One step of one member goes through `gcm_pe25_matsuno_step_host`: latitude blocks copied in, stepped and
-        copied out on three streams, so the PCIe link runs in both directions at once."""
+        copied out on three streams, so the PCIe link runs in both directions at once.
+
+        pipelined=True (a time loop whose state lives in host memory between steps): consecutive calls overlap -- the
+        copy-in of the next step starts while the last blocks of this one are still on their way out
+        (`gcm_pe25_matsuno_step_host_pipelined`).  `host_out` is then complete only after `host_join()`."""
+        ok_host = all(not x.is_cuda and x.is_contiguous() and x.dtype == torch.float64 for x in list(host_in) + list(host_out))
+        if pipelined and int(nsteps) == 1 and self.nbatch == 1 and self.cur[0].dim() == 2 and not self.dg.options_on and ok_host:
+            if getattr(self, "_pipe", None) is None:
+                mk = lambda: [torch.empty_like(x) for x in self.cur]
+                self._pipe = {"x": (mk(), mk()), "y": (self.cur, self.nxt), "star": mk(), "n": 0}
+            pp = self._pipe
+            n = pp["n"]
+            ws, need = _workspace(self.dg, 1, self)
+            hi, ho = _struct(host_in), _struct(host_out)
+            sx, ss, sy = _struct(pp["x"][n % 2]), _struct(pp["star"]), _struct(pp["y"][n % 2])
+            st = _lib.lib().gcm_pe25_matsuno_step_host_pipelined(self.dg.handle, ctypes.byref(hi), ctypes.byref(ho),
+                                                                 ctypes.byref(sx), ctypes.byref(ss), ctypes.byref(sy),
+                                                                 _host.scalar(dt), 0, n, _host.ptr(ws), need, _lib.stream())
+            if st == 0:
+                pp["n"] = n + 1
+                self.cur = pp["y"][n % 2]          # the newest state on the device
+                self.nxt = pp["y"][(n + 1) % 2]
+                self.nsteps_done += 1
+                return
+            if st != -4:                           # GCM_EUNSUP: no row-segment kernels for this geometry -> plain path
+                _lib.check(st, "gcm_pe25_matsuno_step_host_pipelined")
         if int(nsteps) == 1 and self.nbatch == 1 and self.cur[0].dim() == 2 and not self.dg.options_on and all(
                 not x.is_cuda and x.is_contiguous() and x.dtype == torch.float64 for x in list(host_in) + list(host_out)):
             if getattr(self, "_star", None) is None:
@@ -140,6 +165,10 @@ class Stepper:
         self.step(dt, nsteps)
         for dst, src in zip(host_out, self.cur):
             dst.copy_(src, non_blocking=True)
+
+    def host_join(self):
+        """Make the current stream wait for the copy-outs of every `step_host(..., pipelined=True)` issued so far."""
+        _lib.check(_lib.lib().gcm_host_pipe_join(_lib.stream()), "gcm_host_pipe_join")
 
     def tensors(self):
         """The current state as device tensors (p, u, v, t, q); valid until the next step()."""

@@ -135,6 +135,19 @@ int gcm_pe25_matsuno_step_host(const gcm_geom* g, const gcm_state* h_in, const g
                                const gcm_state* d_star, const gcm_state* d_nxt, double dt, int nblocks,
                                void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same step pipelined ACROSS consecutive calls, for a time loop whose state lives in host memory between steps
+ * (the reference's own situation: numpy arrays in, numpy arrays out, dynamics.py:230-237).  The call does not join its
+ * copy-out stream into `stream`: h_out is complete after gcm_host_pipe_join(stream).  Blocks are visited in the
+ * rotated order start_block, start_block + 1, ... (pass the call number); the copy-in of a block waits only for the
+ * previous call's copy-out of the same block, so both directions of the PCIe link stay busy from step to step.
+ * d_in / d_out must alternate between two pairs of device states from call to call.  Bit-identical to
+ * gcm_pe25_matsuno_step.  GCM_EUNSUP without the fused row-segment kernels. */
+int gcm_pe25_matsuno_step_host_pipelined(const gcm_geom* g, const gcm_state* h_in, const gcm_state* h_out,
+                                         const gcm_state* d_in, const gcm_state* d_star, const gcm_state* d_out,
+                                         double dt, int nblocks, int start_block, void* d_workspace,
+                                         size_t workspace_bytes, void* stream);
+int gcm_host_pipe_join(void* stream);
+
 /* Kernel path of the half step: 0 (default) = the fused kernels of pe25_fast.cu whenever the geometry allows
  * (L in {3, 9}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
  * comparisons, widths with other prime factors). */
