@@ -19,7 +19,8 @@ int g_gcm_knob[GCM_NKNOBS] = {0};
 // tuning knobs (bench.py --knob i=v; 0 = automatic):
 //   0  threads of the filter kernel                 1  packed rows (layer pairs) per CTA of the filter kernel
 //   2  rows per warp task of the hydro kernel (RG)  3  1 = the two chains one after the other on the caller's stream; 2 = side stream at the highest priority
-//   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update;
+//   4  1 = update kernel with direct global loads even when W % 32 == 0; 2 = never the one-thread-per-cell update (and
+//      no 36-wide tiles: the column march); 6 = no 36-wide tiles;
 //      3 = the one-thread-per-cell update for every member count; 5 = the warp-specialised TMA update (pe25f_update_tma_kernel)
 //      instead of the LDGSTS tiled update
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)

@@ -821,18 +821,20 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 #define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
 #define PFT_NF 5  // staged fields: su, sv, st, sq, spu
 
-template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ)>
-__global__ void __launch_bounds__(PFT_TI * PFT_TJ, MB)
+// TI: tile width = 32, or 36 (the 36-wide ensemble members: one tile spans the row, both seams in the same tile)
+template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ), int TI = PFT_TI>
+__global__ void __launch_bounds__(TI * PFT_TJ, MB)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
+  constexpr int TROW = TI + 4;  // [pad, west halo, TI columns, east halo, pad]: the interior starts 16-byte aligned
   if (g.pdl_early) gcm_pdl_trigger();
   gcm_pdl_wait();
   constexpr int pfd = 2;  // L1 prefetch distance (layers) of the once-read fields: 1..3 measured alike, off costs 14 %
   GCM_DYN_SMEM(double, sm);
-  constexpr int PFT_TILE = (PFT_TJ + 2) * PFT_ROW, PFT_STAGE = PFT_NF * PFT_TILE;  // doubles per field tile / stage
+  constexpr int TILE = (PFT_TJ + 2) * TROW, PFT_STAGE = PFT_NF * TILE;  // doubles per field tile / stage
   const int H = g.H, W = g.W, plane = H * W, wrap = g.wrap_j;
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PFT_TI + tx;
-  const int i = blockIdx.x * PFT_TI + tx;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TI + tx;
+  const int i = blockIdx.x * TI + tx;
   const int r = blockIdx.y * PFT_TJ + ty;
   const bool active = r < seg.n1;
   const int j0 = seg.a + blockIdx.y * PFT_TJ;  // first row of the tile
@@ -859,34 +861,34 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   const int e_c = j * W + i;
   // halo ring of the tile: north row, south row, west column, east column -> (tile row, tile column, global offset)
   int hr = 0, hc = 0, e_h = 0;
-  constexpr int RING_ROW = PFT_TI + 2;  // a ring row spans columns -1 .. TI
+  constexpr int RING_ROW = TI + 2;  // a ring row spans columns -1 .. TI
   const bool has_halo = tid < 2 * RING_ROW + 2 * PFT_TJ;
   if (has_halo) {
     int rr, cc;  // tile coordinates, -1 .. TJ and -1 .. TI
     if (tid < RING_ROW) { rr = -1; cc = tid - 1; }
     else if (tid < 2 * RING_ROW) { rr = PFT_TJ; cc = tid - RING_ROW - 1; }
     else if (tid < 2 * RING_ROW + PFT_TJ) { rr = tid - 2 * RING_ROW; cc = -1; }
-    else { rr = tid - 2 * RING_ROW - PFT_TJ; cc = PFT_TI; }
+    else { rr = tid - 2 * RING_ROW - PFT_TJ; cc = TI; }
     const int gj = rowc(j0 + rr);
-    int gi = blockIdx.x * PFT_TI + cc;
+    int gi = blockIdx.x * TI + cc;
     gi = gi < 0 ? gi + W : (gi >= W ? gi - W : gi);
     hr = rr + 1;
     hc = cc + 2;
     e_h = gj * W + gi;
   }
-  const int t_c = (ty + 1) * PFT_ROW + (tx + 2);  // own position in a tile
-  const int t_h = hr * PFT_ROW + hc;
+  const int t_c = (ty + 1) * TROW + (tx + 2);  // own position in a tile
+  const int t_h = hr * TROW + hc;
 
   auto issue = [&](int k, int s) {  // stage layer k into stage s
     double* st = sm + s * PFT_STAGE;
     const int off = k * plane;
     if ((tx & 1) == 0) {  // two columns per copy: even columns are 16-byte aligned in the tile and in the field
 #pragma unroll
-      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async16(st + f * PFT_TILE + t_c, fld[f] + off + e_c);
+      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async16(st + f * TILE + t_c, fld[f] + off + e_c);
     }
     if (has_halo) {
 #pragma unroll
-      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * PFT_TILE + t_h, fld[f] + off + e_h);
+      for (int f = 0; f < PFT_NF; ++f) gcm_cp_async8(st + f * TILE + t_h, fld[f] + off + e_h);
     }
     gcm_cp_async_commit();
   };
@@ -928,8 +930,8 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   __syncthreads();
   if (PFT_NS - 1 < L) issue(PFT_NS - 1, PFT_NS - 1);
   const double* s0 = sm;
-  double u_k = s0[0 * PFT_TILE + t_c], v_k = s0[1 * PFT_TILE + t_c], t_k = s0[2 * PFT_TILE + t_c],
-         q_k = s0[3 * PFT_TILE + t_c];
+  double u_k = s0[0 * TILE + t_c], v_k = s0[1 * TILE + t_c], t_k = s0[2 * TILE + t_c],
+         q_k = s0[3 * TILE + t_c];
   double sd_c = 0.0, sd_ip = 0.0, sd_jp = 0.0;  // level 0
   double fu = (u_k + u_top) * 0.5 * ((sd_c + sd_ip) * 0.5);
   double fv_ = (v_k + v_top) * 0.5 * ((sd_c + sd_jp) * 0.5);
@@ -958,14 +960,14 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     const double own_pgf = fld[6][e], own_fv = fld[7][e], own_u = fld[8][e], own_v = fld[9][e], own_t = fld[10][e],
                  own_q = fld[11][e];
     // horizontal neighbours from the tile
-    const double* su_ = sk + 0 * PFT_TILE + t_c;
-    const double* sv_ = sk + 1 * PFT_TILE + t_c;
-    const double* st_ = sk + 2 * PFT_TILE + t_c;
-    const double* sq_ = sk + 3 * PFT_TILE + t_c;
-    const double* pu_ = sk + 4 * PFT_TILE + t_c;
-    const double u_im = su_[-1], u_ip = su_[1], u_jp = su_[PFT_ROW], u_jm = su_[-PFT_ROW];
-    const double v_im = sv_[-1], v_ip = sv_[1], v_jp = sv_[PFT_ROW], v_jm = sv_[-PFT_ROW], v_jm_ip = sv_[1 - PFT_ROW];
-    const double pu_c = pu_[0], pu_im = pu_[-1], pu_ip = pu_[1], pu_jp = pu_[PFT_ROW], pu_jp_im = pu_[PFT_ROW - 1];
+    const double* su_ = sk + 0 * TILE + t_c;
+    const double* sv_ = sk + 1 * TILE + t_c;
+    const double* st_ = sk + 2 * TILE + t_c;
+    const double* sq_ = sk + 3 * TILE + t_c;
+    const double* pu_ = sk + 4 * TILE + t_c;
+    const double u_im = su_[-1], u_ip = su_[1], u_jp = su_[TROW], u_jm = su_[-TROW];
+    const double v_im = sv_[-1], v_ip = sv_[1], v_jp = sv_[TROW], v_jm = sv_[-TROW], v_jm_ip = sv_[1 - TROW];
+    const double pu_c = pu_[0], pu_im = pu_[-1], pu_ip = pu_[1], pu_jp = pu_[TROW], pu_jp_im = pu_[TROW - 1];
     const double pv_c = v_k * a_c, pv_ip = v_ip * a_ip, pv_jm = v_jm * a_jm, pv_jm_ip = v_jm_ip * a_jm_ip,
                  pv_jp = v_jp * a_jp;
 
@@ -980,8 +982,8 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
       sd_c = (pit_c - pre_c) - pit_c * sb;
       sd_ip = (pit_ip - pre_ip) - pit_ip * sb;
       sd_jp = (pit_jp - pre_jp) - pit_jp * sb;
-      u_kp = sn[0 * PFT_TILE + t_c]; v_kp = sn[1 * PFT_TILE + t_c]; t_kp = sn[2 * PFT_TILE + t_c];
-      q_kp = sn[3 * PFT_TILE + t_c];
+      u_kp = sn[0 * TILE + t_c]; v_kp = sn[1 * TILE + t_c]; t_kp = sn[2 * TILE + t_c];
+      q_kp = sn[3 * TILE + t_c];
       fu_n = (u_kp + u_k) * 0.5 * ((sd_c + sd_ip) * 0.5);
       fv_n = (v_kp + v_k) * 0.5 * ((sd_c + sd_jp) * 0.5);
       ft_n = (t_kp + t_k) * 0.5 * sd_c;
@@ -1005,9 +1007,9 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     if (zero_v) v_n *= 0.0;  // dynamics.py:222
     // tracers: advec_t (dynamics.py:174-181) + advec_sig, flux form (dynamics.py:214, :219)
     const double adv_t = ((pu_c * (t_k + st_[1]) - pu_im * (st_[-1] + t_k)) * rdxj +
-                          (pv_c * (t_k + st_[PFT_ROW]) - pv_jm * (st_[-PFT_ROW] + t_k)) * rdy) * 0.5;
+                          (pv_c * (t_k + st_[TROW]) - pv_jm * (st_[-TROW] + t_k)) * rdy) * 0.5;
     const double adv_q = ((pu_c * (q_k + sq_[1]) - pu_im * (sq_[-1] + q_k)) * rdxj +
-                          (pv_c * (q_k + sq_[PFT_ROW]) - pv_jm * (sq_[-PFT_ROW] + q_k)) * rdy) * 0.5;
+                          (pv_c * (q_k + sq_[TROW]) - pv_jm * (sq_[-TROW] + q_k)) * rdy) * 0.5;
     if (active) {
       const double u_n = pu_n * r_pnu;
       const double t_n = (own_t * p_c - (adv_t + ads_t) * dt) * r_pn;
@@ -1318,7 +1320,10 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   // takes the same kernel as the whole grid (bit-identical decomposition).
   const bool cells = ((size_t)W * nbatch <= 128 || g_gcm_knob[4] == 3) && (size_t)(segU.n1 + segU.n2) * W < (1u << 22) &&
                      g_gcm_knob[4] != 2;
-  const bool tiled = !cells && W % PFT_TI == 0 && g_gcm_knob[4] != 1;  // update on staged shared-memory tiles
+  // update on staged shared-memory tiles: 32-wide tiles, or 36-wide ones when only those divide the row (the 36 x 24
+  // ensemble members: knob 4 = 6 or 2 keeps them on the direct-load kernel)
+  const bool tile36 = W % PFT_TI != 0 && W % 36 == 0 && g_gcm_knob[4] != 6 && g_gcm_knob[4] != 2;
+  const bool tiled = !cells && (W % PFT_TI == 0 || tile36) && g_gcm_knob[4] != 1;
   if (nrowsR > 0) {
     // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run
     // side by side (caller's stream + the geometry's side stream).
@@ -1421,7 +1426,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   }
   // TMA update (knob 4 = 5; the LDGSTS kernel stays the default while it measures faster, profiles/round2): tensor
   // maps of the 11 fields (cached per pointer); a driver without cuTensorMapEncodeTiled falls back to LDGSTS
-  bool tma = tiled && g_gcm_knob[4] == 5 && (size_t)nbatch * L < 2147483647u;
+  bool tma = tiled && !tile36 && g_gcm_knob[4] == 5 && (size_t)nbatch * L < 2147483647u;
   PfTmaMaps maps;
   const int tjt = g_gcm_knob[11] == 8 ? 8 : 4;                          // tile rows
   const int nst = (g_gcm_knob[10] != 3 && tjt == 4) ? 4 : 3;  // layers in flight (knob 10 = 3: three)
@@ -1474,12 +1479,18 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     // row, so a band stays bit-identical to the whole grid)
     const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
     constexpr int tj = 4;  // tile height (8 measured slower on B200: r02a)
-    const size_t smt = (size_t)PFT_NS * PFT_NF * (tj + 2) * PFT_ROW * sizeof(double);
+    const int ti = tile36 ? 36 : PFT_TI;
+    const size_t smt = (size_t)PFT_NS * PFT_NF * (tj + 2) * (ti + 4) * sizeof(double);
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
-      const dim3 gridt(W / PFT_TI, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(PFT_TI, tj);
+      const dim3 gridt(W / ti, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(ti, tj);
       const int mbu = (g_gcm_knob[15] / 100) % 10;  // register-budget variants (knob 15, hundreds digit)
-      if (L == 9 && (mbu == 5 || mbu == 6)) {
+      if (tile36) {
+        if (mbu == 4)  // 4 CTAs of 144 threads per SM at 112 registers instead of 3 at 128
+          GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 4, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        else
+          GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      } else if (L == 9 && (mbu == 5 || mbu == 6)) {
         if constexpr (L == 9) {
           if (mbu == 5) GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
           else GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 6>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);

@@ -343,6 +343,41 @@ def test_ensemble_members_are_independent(backend):
         check_state(tuple(a[m] for a in out), ref, TOL_RUN)
 
 
+@pytest.mark.parametrize("H,W,nm", [(24, 36, 5), (6, 72, 2), (5, 36, 4)])
+def test_ensemble_on_36_wide_tiles_vs_oracle(backend, H, W, nm):
+    """Ensembles of 36-wide members (BASELINE configs[3]: 1024 x 36 x 24 x 9; more than 128 / W members) take the
+    shared-memory-tiled update with 36-wide tiles (`pe25f_update_tiled_kernel<L, 4, 3, 36>`: a tile spans the member's
+    row, both periodic seams inside it; partial tiles in j); knob 4 = 6 keeps the direct-load column march.  Every
+    member against the oracle, and both kernels against each other."""
+    from gcmiipy_b200 import _lib
+    geom = geometry.gen_geometry(H, W, 9, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, 9, sig_func=O.manabe_sig)
+    hm = 60.0 * np.random.default_rng(W + H).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    members = []
+    for m in range(nm):
+        sm = list(O.synthetic_state(og, seed=900 + m))
+        sm[2] = sm[2] + 0.2 * np.random.default_rng(m).standard_normal(sm[2].shape)    # v != 0 on the wall row too
+        members.append(sm)
+    batched = tuple(np.stack([m[f] for m in members]) for f in range(5))
+    res = {}
+    try:
+        for mode in (0, 6):
+            assert _lib.lib().gcm_tuning_knob(4, mode) == 0
+            st = dynamics.Stepper(geom, *batched)
+            st.step(200.0, 3)
+            res[mode] = st.download()
+    finally:
+        _lib.lib().gcm_tuning_knob(4, 0)
+    for a, b in zip(res[0], res[6]):
+        assert rel(a, b) <= 1e-13
+    for m, s in enumerate(members):
+        ref = tuple(s)
+        for _ in range(3):
+            ref = O.matsuno_timestep(*ref, 200.0, og)
+        check_state(tuple(a[m] for a in res[0]), ref, TOL_RUN)
+
+
 def test_nonfinite_input_propagates_like_numpy(backend):
     """The reference has no error path: NaNs propagate and the caller polls (matsuno_c_grid.py:184-187)."""
     geom = geometry.gen_geometry(8, 8, 3, sig_func=geometry.manabe_sig)
