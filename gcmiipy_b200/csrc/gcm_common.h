@@ -5,7 +5,7 @@
 
 #include "gcm_b200.h"
 
-#define GCM_NKNOBS 16  // tuning knobs (gcm_tuning_knob)
+#define GCM_NKNOBS 24  // tuning knobs (gcm_tuning_knob)
 
 #ifdef GCM_EMU
 #include "cuda_emu.h"  // tests/emu: CPU execution of these sources for the no-GPU test-suite only

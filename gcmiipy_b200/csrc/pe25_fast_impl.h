@@ -136,10 +136,12 @@ struct PfFilterIO {
   double* out;
   GcmRowSeg seg;
   int pr0, W, plane;
+  double2* zkeep;  // MODE 2: the filtered packed rows stay in the transform's work rows (read back by the aflux pass)
   struct Ctx {
     const double* s0;
     const double* spr;
     double* o;
+    double2* zr;
     bool two;
   };
   __device__ __forceinline__ Ctx begin(int row) const {
@@ -150,12 +152,13 @@ struct PfFilterIO {
     c.s0 = in + k0 * plane + j * W;
     c.spr = sp + j * W;
     c.o = out + k0 * plane + j * W;
+    c.zr = MODE == 2 ? zkeep + (size_t)row * W : nullptr;
     c.two = k0 + 1 < L;
     return c;
   }
   __device__ __forceinline__ double2 load(const Ctx& c, int i) const {
     double x0 = c.s0[i], x1 = c.two ? c.s0[plane + i] : 0.0;
-    if (MODE == 1) {  // su * iph(sp)  (dynamics.py:187)
+    if (MODE >= 1) {  // su * iph(sp)  (dynamics.py:187)
       const double ph = (c.spr[i] + c.spr[gcm_ip(i, W)]) * 0.5;
       x0 *= ph;
       x1 *= ph;
@@ -165,6 +168,9 @@ struct PfFilterIO {
   __device__ __forceinline__ void store(const Ctx& c, int i, double2 v) const {
     c.o[i] = v.x;
     if (c.two) c.o[plane + i] = v.y;
+    // in place: the last inverse stage has read every input of this butterfly before it stores, and no other thread
+    // touches these positions
+    if (MODE == 2) c.zr[i] = v;
   }
 };
 
@@ -174,7 +180,7 @@ struct PfFilterIO {
 template <int L, int MODE, int PLAN, int MB = 5>
 __global__ void __launch_bounds__(PLAN > 0 ? 128 : 256, PLAN > 0 ? MB : 2)
 pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* in, double* out, GcmRowSeg seg, int NBAT,
-                    size_t bstride2, size_t bstride3) {
+                    size_t bstride2, size_t bstride3, const double* __restrict__ aux_sv, double* __restrict__ aux_part) {
   if (g.pdl_early) gcm_pdl_trigger();
   gcm_pdl_wait();
   GCM_DYN_SMEM(double2, z);
@@ -184,11 +190,42 @@ pe25f_filter_kernel(GcmGeomDev g, const double* __restrict__ sp, const double* i
   const int pr0 = blockIdx.x * NBAT;
   const int nb = npr_total - pr0 < NBAT ? npr_total - pr0 : NBAT;
   PfFilterIO<L, MODE> io{sp + blockIdx.y * bstride2, in + blockIdx.y * bstride3, out + blockIdx.y * bstride3, seg, pr0, W,
-                         g.H * W};
+                         g.H * W, z};
   if constexpr (PLAN > 0)
     gcm_filter_rows_io_fixed<NP, PLAN>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
   else
     gcm_filter_rows_io<NP>(z, nb, g.plan, g.tws, g.smmzp, seg, pr0, io, threadIdx.x, blockDim.x);
+  if constexpr (MODE == 2) {
+    // aflux (dynamics.py:35-46) fused: the two layers of a packed row contribute conv[k0] + conv[k0+1] to pit; the sum
+    // over the NP layer pairs of a latitude is taken by the update kernel in a fixed order (pair 0 first), so the band
+    // decomposition stays bit-invariant.  part[pair][j][i] lives in the (otherwise unused) sd work field.
+    const int H = g.H, plane = H * W;
+    const double* __restrict__ spb = sp + blockIdx.y * bstride2;
+    const double* __restrict__ svb = aux_sv + blockIdx.y * bstride3;
+    double* __restrict__ part = aux_part + blockIdx.y * bstride3;
+    const double rdy = g.rdy;
+    for (int row = 0; row < nb; ++row) {
+      const int pr = pr0 + row, r = pr / NP, pair = pr - r * NP, k0 = 2 * pair;
+      const int j = gcm_seg_row(seg, r);
+      const int jm = gcm_row(j, -1, H, g.wrap_j), jp = gcm_row(j, 1, H, g.wrap_j);
+      const double rdxj = g.rdx_j[j];
+      const bool two = k0 + 1 < L;
+      const double ds0 = g.c_dsig[k0], ds1 = two ? g.c_dsig[k0 + 1] : 0.0;
+      const double2* zr = z + (size_t)row * W;
+      for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        const double2 pu_c = zr[i], pu_im = zr[gcm_im(i, W)];
+        const double sp_c = spb[j * W + i];
+        const double pjh = (sp_c + spb[jp * W + i]) * 0.5, pjh_m = (spb[jm * W + i] + sp_c) * 0.5;
+        const double pv_c0 = svb[k0 * plane + j * W + i] * pjh, pv_jm0 = svb[k0 * plane + jm * W + i] * pjh_m;
+        double conv = ((pu_c.x - pu_im.x) * rdxj + (pv_c0 - pv_jm0) * rdy) * ds0;
+        if (two) {
+          const double pv_c1 = svb[(k0 + 1) * plane + j * W + i] * pjh, pv_jm1 = svb[(k0 + 1) * plane + jm * W + i] * pjh_m;
+          conv += ((pu_c.y - pu_im.y) * rdxj + (pv_c1 - pv_jm1) * rdy) * ds1;
+        }
+        part[pair * plane + j * W + i] = conv;
+      }
+    }
+  }
 }
 
 // The same filter as a PERSISTENT, software-pipelined kernel (compile-time plans only): a CTA walks over units of NBAT
@@ -295,26 +332,31 @@ pe25f_filter_pipe_kernel(GcmGeomDev g, const double* __restrict__ sp, const doub
 // launch of the filter kernel whose image matches the plan
 template <int L, int MODE, int PLAN>
 static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream, const double* sp,
-                                 const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3) {
+                                 const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2, size_t b3,
+                                 const double* aux_sv = nullptr, double* aux_part = nullptr) {
   if (PLAN > 0 && threads > 128) threads = 128;  // the fixed-plan kernels are compiled for at most 128 threads
   if constexpr (PLAN > 0) {
     // persistent pipelined kernel (knob 14 = 2; measured slower than the one-unit-per-CTA kernel on every grid, r2f:
     // the filter is bound by dependent-instruction latency at 16 warps per SM, not by its loads)
     const size_t smp = 128 + 2 * smem;
     const int per_sm = (int)((227 * 1024) / (smp + 1024)) < 4 ? (int)((227 * 1024) / (smp + 1024)) : 4;
-    if (g_gcm_knob[14] == 2 && per_sm >= 1 && (d.W % 2) == 0) {
+    if (MODE != 2 && g_gcm_knob[14] == 2 && per_sm >= 1 && (d.W % 2) == 0) {
       int ncta = 148 * per_sm / (int)grid.y;
       ncta = ncta < 1 ? 1 : ncta;
       const dim3 gridp((unsigned)((int)grid.x < ncta ? (int)grid.x : ncta), grid.y);
 #ifndef GCM_EMU
-      if (smp > 48 * 1024)
-        GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_pipe_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smp));
+      if constexpr (MODE != 2) {
+        if (smp > 48 * 1024)
+          GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_pipe_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smp));
+      }
 #endif
-      GCM_LAUNCH_DEP((pe25f_filter_pipe_kernel<L, MODE, PLAN>), gridp, dim3(threads), smp, stream, d, sp, in, out, seg, nbf,
-                     b2, b3);
-      GCM_CHECK_LAUNCH();
-      return GCM_OK;
+      if constexpr (MODE != 2) {
+        GCM_LAUNCH_DEP((pe25f_filter_pipe_kernel<L, MODE, PLAN>), gridp, dim3(threads), smp, stream, d, sp, in, out, seg,
+                       nbf, b2, b3);
+        GCM_CHECK_LAUNCH();
+        return GCM_OK;
+      }
     }
   }
 #ifndef GCM_EMU
@@ -328,7 +370,7 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
       GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)smem));                                                                      \
     GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN, MB_>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, \
-                   b2, b3);                                                                                           \
+                   b2, b3, aux_sv, aux_part);                                                                         \
   } while (0)
       if (mb == 4) PF_FILTER_MB(4); else if (mb == 6) PF_FILTER_MB(6); else PF_FILTER_MB(8);
       GCM_CHECK_LAUNCH();
@@ -339,20 +381,21 @@ static int pf_filter_launch_plan(const GcmGeomDev& d, dim3 grid, int threads, si
     GCM_CUDA(cudaFuncSetAttribute(pe25f_filter_kernel<L, MODE, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
 #endif
-  GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, b2, b3);
+  GCM_LAUNCH_DEP((pe25f_filter_kernel<L, MODE, PLAN>), grid, dim3(threads), smem, stream, d, sp, in, out, seg, nbf, b2, b3,
+                 aux_sv, aux_part);
   GCM_CHECK_LAUNCH();
   return GCM_OK;
 }
 template <int L, int MODE>
 static int pf_filter_launch(int plan_id, const GcmGeomDev& d, dim3 grid, int threads, size_t smem, void* stream,
                             const double* sp, const double* in, double* out, GcmRowSeg seg, int nbf, size_t b2,
-                            size_t b3) {
+                            size_t b3, const double* aux_sv = nullptr, double* aux_part = nullptr) {
   switch (plan_id) {
-    case 1: return pf_filter_launch_plan<L, MODE, 1>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
-    case 2: return pf_filter_launch_plan<L, MODE, 2>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
-    case 3: return pf_filter_launch_plan<L, MODE, 3>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
-    case 4: return pf_filter_launch_plan<L, MODE, 4>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
-    default: return pf_filter_launch_plan<L, MODE, 0>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3);
+    case 1: return pf_filter_launch_plan<L, MODE, 1>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3, aux_sv, aux_part);
+    case 2: return pf_filter_launch_plan<L, MODE, 2>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3, aux_sv, aux_part);
+    case 3: return pf_filter_launch_plan<L, MODE, 3>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3, aux_sv, aux_part);
+    case 4: return pf_filter_launch_plan<L, MODE, 4>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3, aux_sv, aux_part);
+    default: return pf_filter_launch_plan<L, MODE, 0>(d, grid, threads, smem, stream, sp, in, out, seg, nbf, b2, b3, aux_sv, aux_part);
   }
 }
 
@@ -822,7 +865,9 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 #define PFT_NF 5  // staged fields: su, sv, st, sq, spu
 
 // TI: tile width = 32, or 36 (the 36-wide ensemble members: one tile spans the row, both seams in the same tile)
-template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ), int TI = PFT_TI>
+// PARTS: pit comes as NP partial sums of conv, one per layer pair (the aflux pass fused into the filter kernel, MODE 2),
+// in the sd work field; pit = their sum in pair order, p_n = p - pit dt (dynamics.py:39-40, :193-194) are formed here
+template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ), int TI = PFT_TI, bool PARTS = false>
 __global__ void __launch_bounds__(TI * PFT_TJ, MB)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
@@ -904,7 +949,22 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   // per-column (2-D) factors while the first layers are on their way
   const double rdxj = g.rdx_j[j], rdxh = g.rdx_h[j], rdy = g.rdy;
   const double p_c = p[e_c], p_ip = p[j * W + ip], p_jp = p[jp * W + i];
-  const double pn_c = pn[e_c], pn_ip = pn[j * W + ip], pn_jp = pn[jp * W + i];
+  double pit_c, pit_ip, pit_jp, pn_c, pn_ip, pn_jp;
+  if constexpr (PARTS) {
+    constexpr int NP = (L + 1) / 2;
+    const double* __restrict__ part = w.sd + o3;
+    pit_c = part[e_c]; pit_ip = part[j * W + ip]; pit_jp = part[jp * W + i];
+#pragma unroll
+    for (int pr = 1; pr < NP; ++pr) {
+      pit_c += part[pr * plane + e_c];
+      pit_ip += part[pr * plane + j * W + ip];
+      pit_jp += part[pr * plane + jp * W + i];
+    }
+    pn_c = p_c - pit_c * dt; pn_ip = p_ip - pit_ip * dt; pn_jp = p_jp - pit_jp * dt;
+  } else {
+    pit_c = pit[e_c]; pit_ip = pit[j * W + ip]; pit_jp = pit[jp * W + i];
+    pn_c = pn[e_c]; pn_ip = pn[j * W + ip]; pn_jp = pn[jp * W + i];
+  }
   const double pu_fac = (p_c + p_ip) * 0.5, pv_fac = (p_c + p_jp) * 0.5;                    // calc_pu / calc_pv
   const double r_pnu = 1.0 / ((pn_c + pn_ip) * 0.5), r_pnv = 1.0 / ((pn_c + pn_jp) * 0.5);  // un_pu / un_pv
   const double r_pn = 1.0 / pn_c;
@@ -918,7 +978,7 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
   // sd (dynamics.py:42-44) of the three columns the vertical fluxes need -- (j, i), (j, i+1), (j+1, i) -- is rebuilt
   // from pit and the running sums of conv, whose operands the horizontal advection loads anyway:
   //   sd[k] = sum_{l >= k} conv[l] - pit sigb[k] = (pit - sum_{l < k} conv[l]) - pit sigb[k],   sd[0] = 0
-  const double pit_c = pit[e_c], pit_ip = pit[j * W + ip], pit_jp = pit[jp * W + i];
+
   const double rdxj_jp = g.rdx_j[jp];
   double pre_c = 0.0, pre_ip = 0.0, pre_jp = 0.0;
   // layer L-1 pairs with layer 0 through the bottom of layer 0 (np.roll), times sd[0] = 0
@@ -1324,6 +1384,12 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   // ensemble members: knob 4 = 6 or 2 keeps them on the direct-load kernel)
   const bool tile36 = W % PFT_TI != 0 && W % 36 == 0 && g_gcm_knob[4] != 6 && g_gcm_knob[4] != 2;
   const bool tiled = !cells && (W % PFT_TI == 0 || tile36) && g_gcm_knob[4] != 1;
+  // aflux fused into the filter of the mass flux (filter MODE 2 writes the per-pair partial sums of conv, the tiled
+  // update forms pit and p_n from them): one launch and one pass over spu less per half step.  Needs the tiled update
+  // (the other update kernels read sd), a compile-time FFT plan, no opt-in terms (pe25_extras reads p_n); knob 16 = 1:
+  // the separate aflux kernel
+  const bool fuse_aflux = tiled && g_gcm_knob[4] != 5 && g_gcm_knob[16] != 1 && !gcm_extras_on(g) &&
+                          g_gcm_knob[8] != 1 && gcm_fixed_plan_id(d.plan) > 0;
   if (nrowsR > 0) {
     // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run
     // side by side (caller's stream + the geometry's side stream).
@@ -1362,7 +1428,10 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const int ntasks = nchunk * ((nrowsR + rg - 1) / rg);
     {
       GcmProfScope ps(GCM_K_FILTER_A, qa);
-      int stf = pf_filter_launch<L, 1>(plan_id, d, gridf, tf, smf, qa, star->p, star->u, w.spu, segR, nbf, b2, b3);
+      int stf = fuse_aflux ? pf_filter_launch<L, 2>(plan_id, d, gridf, tf, smf, qa, star->p, star->u, w.spu, segR, nbf, b2,
+                                                    b3, star->v, w.sd)
+                           : pf_filter_launch<L, 1>(plan_id, d, gridf, tf, smf, qa, star->p, star->u, w.spu, segR, nbf, b2,
+                                                    b3);
       if (stf) return stf;
     }
     if (W < 62 && g_gcm_knob[7] != 1) {  // narrow rows: whole row groups per CTA, east neighbour through shared memory
@@ -1401,7 +1470,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
         GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, false>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);
     }
     GCM_CHECK_LAUNCH();
-    {
+    if (!fuse_aflux) {
       GcmProfScope ps(GCM_K_AFLUX_F, qa);
       const dim3 grida((nrowsR * W + 127) / 128, nbatch);
       if (tiled)  // the tiled update rebuilds sd: pit and p_n only
@@ -1486,10 +1555,14 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       const dim3 gridt(W / ti, (parts[s2].n1 + tj - 1) / tj, nbatch), blockt(ti, tj);
       const int mbu = (g_gcm_knob[15] / 100) % 10;  // register-budget variants (knob 15, hundreds digit)
       if (tile36) {
-        if (mbu == 4)  // 4 CTAs of 144 threads per SM at 112 registers instead of 3 at 128
+        if (fuse_aflux)
+          GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36, true>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+        else if (mbu == 4)  // 4 CTAs of 144 threads per SM at 112 registers instead of 3 at 128
           GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 4, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
         else
           GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
+      } else if (fuse_aflux) {
+        GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 4, PFT_TI, true>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       } else if (L == 9 && (mbu == 5 || mbu == 6)) {
         if constexpr (L == 9) {
           if (mbu == 5) GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);

@@ -103,7 +103,9 @@ size_t gcm_pe25_workspace_bytes(const gcm_geom* g, int nbatch);
 
 /* element offset (doubles, member 0) of a work field a half step leaves in the workspace: 0 = spu, the filtered mass
  * flux arakawa_1977(su * iph(sp)) (dynamics.py:187-189); 1 = the filtered pgfu + phiu (:202); 2 = pit (:39-40);
- * 3 = p_n (:193-194).  (size_t)-1 for an unknown field.  Diagnostic / test access only. */
+ * 3 = p_n (:193-194; 2 and 3 are produced only when aflux runs as its own kernel: wide grids with a compile-time FFT
+ * plan fuse it into the filter and form pit / p_n inside the update kernel).  (size_t)-1 for an unknown field.
+ * Diagnostic / test access only. */
 size_t gcm_pe25_workspace_field(const gcm_geom* g, int nbatch, int which);
 
 /* dynamics.half_timestep (dynamics.py:183-227): out = base + dt * F(star).  Rows of `star` within

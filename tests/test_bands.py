@@ -97,9 +97,11 @@ def test_band_diagnostics_single_rank(backend):
                  "v_min": np.min(full[2]), "nonfinite": 0}
 
 
-def test_band_with_tiled_update_is_bit_identical(backend, knob4):
-    """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too."""
-    geom, s = _case(H=16, W=32)
+@pytest.mark.parametrize("W", [32, 288])
+def test_band_with_tiled_update_is_bit_identical(backend, knob4, W):
+    """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too.  W = 288: a
+    compile-time FFT plan, so aflux is fused into the filter (per-pair partial sums of conv, summed by the update)."""
+    geom, s = _case(H=16, W=W)
     whole = dynamics.Stepper(geom, *s)
     whole.step(450.0, 2)
     band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
@@ -262,7 +264,7 @@ def test_gloo_subgroup_bands(tmp_path):
         _lib._override_for_tests(None, None)
 
 
-@pytest.mark.parametrize("world,H,W", [(3, 24, 36), (2, 16, 32), (4, 32, 64)])
+@pytest.mark.parametrize("world,H,W", [(3, 24, 36), (2, 16, 32), (4, 32, 64), (2, 24, 288)])
 def test_peer_mailbox_ring_same_process(backend, world, H, W):
     """The peer-memory halo exchange of csrc/comm.cu (push kernel: my boundary rows -> the neighbours' mailboxes +
     message flag; pull kernel: wait for both flags, mailbox -> halo rows; two alternating slots) with every rank of the
