@@ -859,6 +859,8 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 // registers and resident warps; the six values a cell reads once (pgf, fv, u, v, t, q) come straight from global
 // memory.  Needs W % 32 == 0; one launch per row segment.
 // ---------------------------------------------------------------------------------------------------
+// value of knob 16 that fuses aflux into the filter: 1 = opt-in (the separate aflux kernel is the default), 0 = default on
+#define GCM_FUSE_AFLUX_ON 1
 #define PFT_TI 32
 #define PFT_NS 3  // layers in flight
 #define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
@@ -1386,9 +1388,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
   const bool tiled = !cells && (W % PFT_TI == 0 || tile36) && g_gcm_knob[4] != 1;
   // aflux fused into the filter of the mass flux (filter MODE 2 writes the per-pair partial sums of conv, the tiled
   // update forms pit and p_n from them): one launch and one pass over spu less per half step.  Needs the tiled update
-  // (the other update kernels read sd), a compile-time FFT plan, no opt-in terms (pe25_extras reads p_n); knob 16 = 1:
-  // the separate aflux kernel
-  const bool fuse_aflux = tiled && g_gcm_knob[4] != 5 && g_gcm_knob[16] != 1 && !gcm_extras_on(g) &&
+  // (the other update kernels read sd), a compile-time FFT plan, no opt-in terms (pe25_extras reads p_n).  Knob 16
+  // selects it (GCM_FUSE_AFLUX_ON below)
+  const bool fuse_aflux = tiled && g_gcm_knob[4] != 5 && g_gcm_knob[16] == GCM_FUSE_AFLUX_ON && !gcm_extras_on(g) &&
                           g_gcm_knob[8] != 1 && gcm_fixed_plan_id(d.plan) > 0;
   if (nrowsR > 0) {
     // Two independent chains:  F(su iph(sp)) -> aflux   and   hydro -> F(pgfu + phiu).  On a whole grid / band they run

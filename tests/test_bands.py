@@ -101,13 +101,19 @@ def test_band_diagnostics_single_rank(backend):
 def test_band_with_tiled_update_is_bit_identical(backend, knob4, W):
     """W = 32: the band's interior rows run the shared-memory-tiled update kernel, the whole grid too.  W = 288: a
     compile-time FFT plan, so aflux is fused into the filter (per-pair partial sums of conv, summed by the update)."""
+    from gcmiipy_b200 import _lib
     geom, s = _case(H=16, W=W)
-    whole = dynamics.Stepper(geom, *s)
-    whole.step(450.0, 2)
-    band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
-    band.step(450.0, 2)
-    for a, b in zip(band.gather(), whole.download()):
-        assert np.array_equal(a, b)
+    try:
+        for fused in ((0, 1) if W == 288 else (0,)):
+            _lib.lib().gcm_tuning_knob(16, fused)
+            whole = dynamics.Stepper(geom, *s)
+            whole.step(450.0, 2)
+            band = bands.BandStepper(geom, *s, rank=0, world=1, native=True)
+            band.step(450.0, 2)
+            for a, b in zip(band.gather(), whole.download()):
+                assert np.array_equal(a, b)
+    finally:
+        _lib.lib().gcm_tuning_knob(16, 0)
 
 
 @pytest.mark.parametrize("wide", [True, False])

@@ -711,3 +711,32 @@ def test_fused_path_layer_counts_vs_oracle(backend, H, W, L):
     for _ in range(2):
         ref = O.matsuno_timestep(*ref, 30.0, og)
     check_state(st.download(), ref, TOL_RUN)
+
+
+@pytest.mark.parametrize("H,W,nm", [(12, 288, 1), (8, 1440, 1), (24, 36, 5), (10, 72, 3)])
+def test_aflux_fused_into_filter_vs_oracle(backend, H, W, nm):
+    """Knob 16 = 1: aflux (dynamics.py:35-46) fused into the filter of the mass flux -- filter MODE 2 keeps the filtered
+    packed row in shared memory and writes conv[k0] + conv[k0+1] per layer pair; the tiled update sums the pairs in a
+    fixed order into pit and forms p_n = p - pit dt.  Against the oracle and against the separate aflux kernel."""
+    from gcmiipy_b200 import _lib
+    geom = geometry.gen_geometry(H, W, 9, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, 9, sig_func=O.manabe_sig)
+    members = [O.synthetic_state(og, seed=40 + m) for m in range(nm)]
+    batched = tuple(np.stack([m[f] for m in members]) for f in range(5)) if nm > 1 else members[0]
+    res = {}
+    try:
+        for mode in (0, 1):
+            assert _lib.lib().gcm_tuning_knob(16, mode) == 0
+            st = dynamics.Stepper(geom, *batched)
+            st.step(20.0, 3)
+            res[mode] = st.download()
+    finally:
+        _lib.lib().gcm_tuning_knob(16, 0)
+    for a, b in zip(res[0], res[1]):
+        assert rel(a, b) <= 1e-13
+    for m, s in enumerate(members):
+        ref = tuple(s)
+        for _ in range(3):
+            ref = O.matsuno_timestep(*ref, 20.0, og)
+        got = tuple(a[m] for a in res[1]) if nm > 1 else res[1]
+        check_state(got, ref, TOL_RUN)

@@ -1,12 +1,12 @@
 #!/bin/bash
-# r2t: aflux fused into the filter (default) vs the separate aflux kernel (knob 16=1)
+# r2t: aflux fused into the filter (default) vs the separate aflux kernel (knob 16=1 = fused)
 TAG=${1:-r2t}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -k "parity or bands or extras" > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -4 gpurun_out/${TAG}_pytest.log
 i=0
 for wl in c5 c3 c4 c5b8; do
-  for k in 0 1; do
+  for k in 1 0; do
     timeout 300 python bench.py --workload $wl --knob 16=$k --steps 20 --warmup 5 --no-cpu-baseline --no-hash > gpurun_out/${TAG}_v${i}.json 2> gpurun_out/${TAG}_v${i}.err
     python - <<PY
 import json
