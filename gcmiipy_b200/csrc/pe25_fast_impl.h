@@ -490,6 +490,83 @@ pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, 
   }
 }
 
+// Hydrostatic columns, tile form (knob 7 = 2): a CTA owns RT rows x 31 columns (lane 31 of every warp is the east halo
+// column, warp RT the south halo row).  Every thread evaluates ONE column -- nine times the threads of the marching
+// kernel above and a ninth of its dependent chain (RT + 1 evaluations per RT rows, the same redundancy) --, the east
+// neighbour comes by shuffle, the south neighbour through shared memory.  Same expressions, operand for operand, as
+// pf_row_step.  One launch per contiguous row segment.
+#define PFH_RT 8
+template <int L, bool PTOP0, int MB = 2>
+__global__ void __launch_bounds__(32 * (PFH_RT + 1), MB)
+pe25f_hydro_tile_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, size_t bstride2, size_t bstride3) {
+  if (g.pdl_early) gcm_pdl_trigger();
+  gcm_pdl_wait();
+  GCM_DYN_SMEM(double, xs);  // [PFH_RT + 1 rows][2 L + 1 values][32 lanes]
+  const int H = g.H, W = g.W, plane = H * W;
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int nrows = seg.n1;
+  const int r0 = blockIdx.y * PFH_RT;                              // first row of the tile within the segment
+  const int rt = nrows - r0 < PFH_RT ? nrows - r0 : PFH_RT;        // rows of this tile; row rt is only the south neighbour
+  const size_t o2 = blockIdx.z * bstride2, o3 = blockIdx.z * bstride3;
+  const double* __restrict__ sp = star.p + o2;
+  const double* __restrict__ st = star.t + o3;
+  double* pgf = w.pgf + o3;
+  double* __restrict__ fv = w.fv + o3;
+  int i = blockIdx.x * 31 + lane;
+  const bool own = lane < 31 && i < W;
+  i = i % W;
+  // stored row of tile row ty: consecutive rows from seg.a (periodic on a whole grid, halo rows on a band)
+  int j = seg.a + r0 + ty;
+  if (g.wrap_j) j = j >= H ? j - H : j;
+  const bool row_ok = ty <= rt && j < H;
+  const int c2 = j * W + i;
+  double phi[L], rho[L];
+  double sp_c = 1.0;
+  double* xr = xs + (size_t)ty * (2 * L + 1) * 32;
+  if (row_ok) {
+    sp_c = sp[c2];
+    pf_column<L, PTOP0>(g, sp_c, g.hmap[c2], st + c2, plane, phi, rho);
+    xr[lane] = sp_c;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      xr[(1 + k) * 32 + lane] = phi[k];
+      xr[(1 + L + k) * 32 + lane] = rho[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < L; ++k) { phi[k] = 0.0; rho[k] = 1.0; }
+  }
+  // pgfu + phiu of row j (dynamics.py:159, :162-165): every lane of the warp takes part in the shuffles
+  {
+    const double sp_e = __shfl_down_sync(0xffffffffu, sp_c, 1);
+    const double rdxj = row_ok ? g.rdx_j[j] : 0.0;
+    const double psum = sp_c + sp_e, gradp = (sp_e - sp_c) * rdxj;
+    const double a_u = psum * gradp;       // (p_c + p_e) dp/dx
+    const double b_u = psum * 0.5 * rdxj;  // iph(p) / dx
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const double phi_e = __shfl_down_sync(0xffffffffu, phi[k], 1);
+      const double rho_e = __shfl_down_sync(0xffffffffu, rho[k], 1);
+      const double x = g.c_sig[k] * a_u * gcm_rcp(rho[k] + rho_e) + b_u * (phi_e - phi[k]);
+      if (own && row_ok && ty < rt) pgf[k * plane + c2] = x;
+    }
+  }
+  __syncthreads();
+  if (own && row_ok && ty < rt) {  // fv = phiv + pgv of this row against its south neighbour (dynamics.py:160, :167-169)
+    const double* xsn = xs + (size_t)(ty + 1) * (2 * L + 1) * 32;
+    const double sp_s = xsn[lane];
+    const double rdy = g.rdy;
+    const double psum = sp_c + sp_s;
+    const double a_v = psum * ((sp_s - sp_c) * rdy);  // (p_c + p_jp) dp/dy
+    const double b_v = psum * 0.5 * rdy;              // jph(p) / dy
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const double phi_s = xsn[(1 + k) * 32 + lane], rho_s = xsn[(1 + L + k) * 32 + lane];
+      fv[k * plane + c2] = g.c_sig[k] * a_v * gcm_rcp(rho[k] + rho_s) + b_v * (phi_s - phi[k]);
+    }
+  }
+}
+
 // Hydrostatic columns on narrow grids (W < 62, the ensemble members): a 31-column warp chunk would leave most lanes
 // idle, so a CTA takes G whole row groups (G * W threads, one column each) and the east neighbour comes through
 // shared memory instead of a shuffle.  Same arithmetic as pe25f_hydro_kernel.
@@ -861,6 +938,8 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 // ---------------------------------------------------------------------------------------------------
 // value of knob 16 that fuses aflux into the filter: 1 = opt-in (the separate aflux kernel is the default), 0 = default on
 #define GCM_FUSE_AFLUX_ON 1
+// value of knob 7 that selects the tile form of the hydro kernel (2 = opt-in, 0 = default on)
+#define GCM_HYDRO_TILE_ON 2
 #define PFT_TI 32
 #define PFT_NS 3  // layers in flight
 #define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
@@ -1460,6 +1539,25 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
       const int mbh = (g_gcm_knob[15] / 10) % 10;  // register-budget variants (knob 15, tens digit)
+      if (g_gcm_knob[7] == GCM_HYDRO_TILE_ON) {  // tile form: one launch per contiguous row segment
+        const GcmRowSeg hp[2] = {{segR.a, segR.n1, 0, 0}, {segR.c, segR.n2, 0, 0}};
+        const size_t smh = (size_t)(PFH_RT + 1) * (2 * L + 1) * 32 * sizeof(double);
+        for (int s2 = 0; s2 < 2; ++s2) {
+          if (hp[s2].n1 <= 0) continue;
+          const dim3 gridh(nchunk, (hp[s2].n1 + PFH_RT - 1) / PFH_RT, nbatch), blockh(32, PFH_RT + 1);
+#ifndef GCM_EMU
+          if (smh > 48 * 1024) {
+            GCM_CUDA(cudaFuncSetAttribute(pe25f_hydro_tile_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
+            GCM_CUDA(cudaFuncSetAttribute(pe25f_hydro_tile_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
+          }
+#endif
+          if (ptop0 && mbh == 3 && smh <= 48 * 1024)  // 3 CTAs per SM at 72 registers
+            GCM_LAUNCH_DEP((pe25f_hydro_tile_kernel<L, true, 3>), gridh, blockh, smh, qb, d, cs, w, hp[s2], b2, b3);
+          else if (ptop0) GCM_LAUNCH_DEP((pe25f_hydro_tile_kernel<L, true>), gridh, blockh, smh, qb, d, cs, w, hp[s2], b2, b3);
+          else GCM_LAUNCH_DEP((pe25f_hydro_tile_kernel<L, false>), gridh, blockh, smh, qb, d, cs, w, hp[s2], b2, b3);
+          GCM_CHECK_LAUNCH();
+        }
+      } else
       if (L == 9 && ptop0 && (mbh == 5 || mbh == 6 || mbh == 8)) {
         if constexpr (L == 9) {
           if (mbh == 5) GCM_LAUNCH_DEP((pe25f_hydro_kernel<L, true, 5>), gridc, dim3(128), 0, qb, d, cs, w, segR, rg, b2, b3);

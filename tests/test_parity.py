@@ -740,3 +740,36 @@ def test_aflux_fused_into_filter_vs_oracle(backend, H, W, nm):
             ref = O.matsuno_timestep(*ref, 20.0, og)
         got = tuple(a[m] for a in res[1]) if nm > 1 else res[1]
         check_state(got, ref, TOL_RUN)
+
+
+@pytest.mark.parametrize("H,W,L", [(20, 64, 9), (9, 96, 9), (3, 62, 3), (17, 288, 9), (5, 70, 18)])
+def test_hydro_tile_kernel_matches_marching_kernel(backend, H, W, L):
+    """Knob 7 = 2: pe25f_hydro_tile_kernel (one column per thread, RT + 1 = 9 warps per CTA, south neighbour through shared
+    memory) against the marching warp kernel: the same expressions operand for operand -- bit for bit on the emulator
+    build, to the last bits on the GPU (FMA contraction is chosen per kernel) -- and against the oracle.  Partial tiles
+    in j (H = 20, 9, 3, 17, 5), the periodic wrap of the south neighbour, ptop != 0, 18 layers (85 KB of shared memory)."""
+    from gcmiipy_b200 import _lib
+    geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
+    og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
+    geom.ptop = og.ptop = 500.0 if W == 96 else 0.0
+    hm = 40.0 * np.random.default_rng(H + W).random((H, W))
+    geom.heightmap = hm; og.heightmap = hm
+    s = O.synthetic_state(og, seed=H * 7 + W)
+    res = {}
+    try:
+        for mode in (0, 2):
+            assert _lib.lib().gcm_tuning_knob(7, mode) == 0
+            st = dynamics.Stepper(geom, *s)
+            st.step(15.0, 2)
+            res[mode] = st.download()
+    finally:
+        _lib.lib().gcm_tuning_knob(7, 0)
+    for a, b in zip(res[0], res[2]):
+        if backend == "emu":
+            exact(a, b)
+        else:
+            assert rel(a, b) <= 1e-13
+    ref = s
+    for _ in range(2):
+        ref = O.matsuno_timestep(*ref, 15.0, og)
+    check_state(res[2], ref, TOL_RUN)
