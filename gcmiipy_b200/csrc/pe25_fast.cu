@@ -25,8 +25,8 @@ int g_gcm_knob[GCM_NKNOBS] = {0};
 //      instead of the LDGSTS tiled update
 //   5  direct-load update kernel: L1 prefetch distance in layers + 1 (1 = off)
 //   6  latitude blocks of the host-resident step (host_step.cu)
-//   7  1 = warp-chunk hydro kernel also on narrow grids (default: W < 62 takes pe25f_hydro_narrow_kernel); 2 = the tile
-//      form of the hydro kernel (one column per thread, pe25f_hydro_tile_kernel) on wide grids
+//   7  hydro kernel: 0 = W < 62 pe25f_hydro_narrow_kernel, else the tile form pe25f_hydro_tile_kernel (one column per
+//      thread); 1 = the marching warp-chunk kernel everywhere; 3 = the marching kernel on wide grids only
 //   8  1 = filter kernel with the runtime radix switch even when the plan has a compile-time twin (GcmFixedPlan)
 //   9  programmatic dependent launch of the half-step kernels: 0 / 1 = on (a kernel's launch overlaps the drain of its
 //      predecessor in the stream: -3 ... -5 % per step, r03e), 2 = on + every kernel triggers its dependents at entry

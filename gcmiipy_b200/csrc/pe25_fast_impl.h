@@ -490,7 +490,8 @@ pe25f_hydro_kernel(GcmGeomDev g, PfConst star, PfWork w, GcmRowSeg seg, int RG, 
   }
 }
 
-// Hydrostatic columns, tile form (knob 7 = 2): a CTA owns RT rows x 31 columns (lane 31 of every warp is the east halo
+// Hydrostatic columns, tile form (the default on wide grids; knob 7 = 3 keeps the marching kernel above): a CTA owns RT
+// rows x 31 columns (lane 31 of every warp is the east halo
 // column, warp RT the south halo row).  Every thread evaluates ONE column -- nine times the threads of the marching
 // kernel above and a ninth of its dependent chain (RT + 1 evaluations per RT rows, the same redundancy) --, the east
 // neighbour comes by shuffle, the south neighbour through shared memory.  Same expressions, operand for operand, as
@@ -938,8 +939,6 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 // ---------------------------------------------------------------------------------------------------
 // value of knob 16 that fuses aflux into the filter: 1 = opt-in (the separate aflux kernel is the default), 0 = default on
 #define GCM_FUSE_AFLUX_ON 1
-// value of knob 7 that selects the tile form of the hydro kernel (2 = opt-in, 0 = default on)
-#define GCM_HYDRO_TILE_ON 2
 #define PFT_TI 32
 #define PFT_NS 3  // layers in flight
 #define PFT_ROW (PFT_TI + 4)  // [pad, west halo, 32 columns, east halo, pad]: the interior starts 16-byte aligned
@@ -1539,7 +1538,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
       const int mbh = (g_gcm_knob[15] / 10) % 10;  // register-budget variants (knob 15, tens digit)
-      if (g_gcm_knob[7] == GCM_HYDRO_TILE_ON) {  // tile form: one launch per contiguous row segment
+      if (g_gcm_knob[7] == 0) {  // tile form (default on wide grids): one launch per contiguous row segment
         const GcmRowSeg hp[2] = {{segR.a, segR.n1, 0, 0}, {segR.c, segR.n2, 0, 0}};
         const size_t smh = (size_t)(PFH_RT + 1) * (2 * L + 1) * 32 * sizeof(double);
         for (int s2 = 0; s2 < 2; ++s2) {
