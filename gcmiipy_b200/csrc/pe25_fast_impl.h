@@ -1538,7 +1538,9 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GcmProfScope ps(GCM_K_COLUMN_F, qb);
       const dim3 gridc((ntasks + 3) / 4, nbatch);
       const int mbh = (g_gcm_knob[15] / 10) % 10;  // register-budget variants (knob 15, tens digit)
-      if (g_gcm_knob[7] == 0) {  // tile form (default on wide grids): one launch per contiguous row segment
+      // tile form: the default from 256 columns up (a 72-wide grid is 18 CTAs of it and loses to the marching kernel,
+      // r2u); the choice depends on the width only, never on the rows of a launch.  One launch per contiguous segment.
+      if (g_gcm_knob[7] == 0 && W >= 256) {
         const GcmRowSeg hp[2] = {{segR.a, segR.n1, 0, 0}, {segR.c, segR.n2, 0, 0}};
         const size_t smh = (size_t)(PFH_RT + 1) * (2 * L + 1) * 32 * sizeof(double);
         for (int s2 = 0; s2 < 2; ++s2) {

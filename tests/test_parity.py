@@ -742,16 +742,16 @@ def test_aflux_fused_into_filter_vs_oracle(backend, H, W, nm):
         check_state(got, ref, TOL_RUN)
 
 
-@pytest.mark.parametrize("H,W,L", [(20, 64, 9), (9, 96, 9), (3, 62, 3), (17, 288, 9), (5, 70, 18)])
+@pytest.mark.parametrize("H,W,L", [(20, 256, 9), (9, 320, 9), (3, 256, 3), (17, 288, 9), (5, 270, 18)])
 def test_hydro_tile_kernel_matches_marching_kernel(backend, H, W, L):
-    """pe25f_hydro_tile_kernel (the default on wide grids: one column per thread, RT + 1 = 9 warps per CTA, south neighbour
+    """pe25f_hydro_tile_kernel (the default from 256 columns up: one column per thread, RT + 1 = 9 warps per CTA, south neighbour
     through shared memory) against the marching warp kernel (knob 7 = 3): the same expressions operand for operand -- bit for bit on the emulator
     build, to the last bits on the GPU (FMA contraction is chosen per kernel) -- and against the oracle.  Partial tiles
     in j (H = 20, 9, 3, 17, 5), the periodic wrap of the south neighbour, ptop != 0, 18 layers (85 KB of shared memory)."""
     from gcmiipy_b200 import _lib
     geom = geometry.gen_geometry(H, W, L, sig_func=geometry.manabe_sig)
     og = O.gen_geometry(H, W, L, sig_func=O.manabe_sig)
-    geom.ptop = og.ptop = 500.0 if W == 96 else 0.0
+    geom.ptop = og.ptop = 500.0 if W == 320 else 0.0
     hm = 40.0 * np.random.default_rng(H + W).random((H, W))
     geom.heightmap = hm; og.heightmap = hm
     s = O.synthetic_state(og, seed=H * 7 + W)
