@@ -50,6 +50,8 @@ SIGNATURES = {
     "gcm_comm_peer_connect": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, _i]),
     "gcm_comm_peer_status": (_i, [C.c_void_p, C.POINTER(C.c_uint)]),
     "gcm_band_halo_peer": (_i, [_geom, C.c_void_p, _st, _i, _i, _i, c_stream]),
+    "gcm_halo_exchange_begin": (_i, [_geom, C.c_void_p, _st, _i, _i, c_stream]),
+    "gcm_halo_exchange_end": (_i, [_geom, C.c_void_p, _st, _i, _i, c_stream]),
     "gcm_band_matsuno_step": (_i, [_geom, C.c_void_p, _st, _st, _st, _d, _i, _i, c_dp, _z, c_stream]),
     "gcm_pe25_set_options": (_i, [_geom, C.POINTER(Pe25Options)]),
     "gcm_pe25_select_path": (_i, [_i]),

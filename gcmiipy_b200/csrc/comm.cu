@@ -463,6 +463,16 @@ static int band_exchange(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int
 #endif
 }
 
+// SURVEY 8(b) names the two halves of an exchange gcm_halo_exchange_begin / _end: begin = push my boundary rows to the
+// neighbours' mailboxes (returns at once: the caller may queue interior work behind it on another stream), end = wait
+// for theirs and fill my halo rows.  Peer mailboxes only (an NCCL exchange is one grouped call: gcm_band_matsuno_step).
+extern "C" int gcm_halo_exchange_begin(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, void* stream) {
+  return gcm_band_halo_peer(g, c, s, hn, hs, 1, stream);
+}
+extern "C" int gcm_halo_exchange_end(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, void* stream) {
+  return gcm_band_halo_peer(g, c, s, hn, hs, 2, stream);
+}
+
 // out = base + dt F(star) on the band, halos of `star` exchanged first; interior rows overlap the exchange
 static int band_half_step(const gcm_geom* g, gcm_comm* c, const gcm_state* base, const gcm_state* star,
                           const gcm_state* out, double dt, int overlap, void* ws, size_t ws_bytes, cudaStream_t main) {

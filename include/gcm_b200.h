@@ -257,6 +257,9 @@ int gcm_comm_peer_setup(gcm_comm* c, const gcm_geom* g, unsigned char* h_handle6
 int gcm_comm_peer_connect(gcm_comm* c, const void* north, const void* south, int same_process);
 int gcm_comm_peer_status(gcm_comm* c, unsigned int* h_timeouts);
 int gcm_band_halo_peer(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, int phase, void* stream);
+/* the two halves under the names SURVEY 8(b) gives them: begin = push (phase 1), end = wait + fill my halo rows (2) */
+int gcm_halo_exchange_begin(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, void* stream);
+int gcm_halo_exchange_end(const gcm_geom* g, gcm_comm* c, const gcm_state* s, int hn, int hs, void* stream);
 /* dynamics.matsuno_timestep (dynamics.py:230-237) `nsteps` times on this rank's band (geometry with wrap_j = 0,
  * 1 halo row north and 2 south, or 2 + 4 for the one-exchange schedule, or 2 + 2 with opt-in terms on).  `cur` =
  * the band incl. halo rows (halo content is overwritten), `star` = scratch

@@ -295,11 +295,10 @@ def test_peer_mailbox_ring_same_process(backend, world, H, W):
         assert lib.gcm_comm_peer_status(b.comm, None) == 2
 
     def exchange(which):
-        for phase in (1, 2):
+        for fn in (lib.gcm_halo_exchange_begin, lib.gcm_halo_exchange_end):     # = gcm_band_halo_peer phases 1, 2
             for b in ranks:
                 st = _struct(getattr(b, which))
-                _lib.check(lib.gcm_band_halo_peer(b.dg.handle, b.comm, ctypes.byref(st), b.xn, b.xs, phase, _lib.stream()),
-                           "gcm_band_halo_peer")
+                _lib.check(fn(b.dg.handle, b.comm, ctypes.byref(st), b.xn, b.xs, _lib.stream()), "gcm_halo_exchange")
 
     for _ in range(3):
         exchange("cur")
