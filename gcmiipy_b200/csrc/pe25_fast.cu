@@ -37,7 +37,6 @@ int g_gcm_knob[GCM_NKNOBS] = {0};
 //  14  2 = the persistent pipelined filter kernel (bulk-copy prefetch of the next rows) instead of the one-unit-per-CTA one
 //  15  register budgets (L = 9): units digit = CTAs per SM the filter aims at (4, 6, 8; default 5), tens = hydro (5, 6, 8;
 //      default 4), hundreds = tiled update (5, 6; default 4)
-//  17  L2 persistence window on a work field (experiment): 1 = pgf on the side stream, 2 = spu on the caller's, 3 = both
 //  16  1 = aflux fused into the filter of the mass flux (per-pair partial sums of conv) instead of its own kernel
 extern "C" int gcm_tuning_knob(int idx, int value) {
   GCM_REQUIRE(idx >= 0 && idx < GCM_NKNOBS, GCM_ESHAPE);

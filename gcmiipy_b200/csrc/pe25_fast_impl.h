@@ -1487,37 +1487,6 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
       GCM_CUDA(cudaEventRecord(ev_fork, qa));
       GCM_CUDA(cudaStreamWaitEvent(qb, ev_fork, 0));
     }
-    // Experiment (knob 17): keep a work field that is written by one kernel of the half step and read by the next ones
-    // in the persisting part of L2 (an access-policy window on the launching stream): 1 = pgf (hydro -> filter ->
-    // update) on the side stream, 2 = spu (filter -> aflux -> update) on the caller's stream, 3 = both at half the
-    // hit ratio.  Set once per (stream, buffer); 0 leaves the streams alone.
-    if (g_gcm_knob[17] > 0 && nbatch == 1) {
-      static int s_limit_set = 0;
-      static size_t s_persist = 0;
-      if (!s_limit_set) {
-        int dev = 0, maxp = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        s_persist = (size_t)maxp;
-        if (s_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, s_persist);
-        s_limit_set = 1;
-      }
-      const size_t bytes = (size_t)L * H * W * sizeof(double);
-      const int mode = g_gcm_knob[17];
-      auto window = [&](cudaStream_t q, void* ptr, double share) {
-        cudaStreamAttrValue av = {};
-        av.accessPolicyWindow.base_ptr = ptr;
-        av.accessPolicyWindow.num_bytes = bytes;
-        double hr = s_persist ? share * (double)s_persist / (double)bytes : 0.0;
-        av.accessPolicyWindow.hitRatio = (float)(hr > 1.0 ? 1.0 : hr);
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(q, cudaStreamAttributeAccessPolicyWindow, &av);
-      };
-      if (mode == 1 || mode == 3) window(qb, w.pgf, mode == 3 ? 0.5 : 1.0);
-      if (mode == 2 || mode == 3) window(qa, w.spu, mode == 3 ? 0.5 : 1.0);
-      cudaGetLastError();
-    }
 #endif
     // filter launches: NBAT packed rows per CTA, about 1440 elements, but at least four CTAs per SM when possible
     const int npr_total = nrowsR * NP;
