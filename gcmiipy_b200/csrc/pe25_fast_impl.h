@@ -6,9 +6,14 @@
 //
 //   F1  pe25f_filter_kernel<1>   spu = arakawa_1977(su * iph(sp))                          (dynamics.py:187-189)
 //   A   pe25f_aflux_kernel       pit = sum_k conv, p_n = p - pit dt  (+ sd on the direct-load update path)  (:35-46, :194)
-//   H   pe25f_hydro_kernel       hydrostatic phi, rho by column in registers -> pgfu + phiu, fv = phiv + pgv (:111-171)
+//   H   pe25f_hydro_tile_kernel (W >= 256) / pe25f_hydro_kernel / pe25f_hydro_narrow_kernel (W < 62)
+//                                hydrostatic phi, rho by column in registers -> pgfu + phiu, fv = phiv + pgv (:111-171)
 //   F0  pe25f_filter_kernel<0>   pgf = arakawa_1977(pgfu + phiu), in place                 (:202)
-//   U   pe25f_update_tiled_kernel / pe25f_update_kernel   momentum and tracer update       (:197-222)
+//   U   pe25f_update_tiled_kernel (32- or 36-wide tiles, LDGSTS) / pe25f_update_kernel / pe25f_update_cell_kernel
+//                                momentum and tracer update                                (:197-222)
+// Measured alternatives kept behind tuning knobs: pe25f_update_tma_kernel (TMA box loads on
+// mbarriers, warp-specialised), pe25f_filter_pipe_kernel (persistent, bulk-copy prefetch), filter MODE 2 (aflux fused).
+// Instantiated per layer count in pe25_fast_l{3,9,17,18}.cu.
 //
 // Work fields in HBM between the launches: spu, pgf, fv (3-D), pit, p_n (2-D).  phi and rho never leave the SM; sd is
 // rebuilt inside U.

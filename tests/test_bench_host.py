@@ -50,3 +50,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "cell_updates_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_two_d_workloads_and_states():
+    """c1 / c1dt700 / c1big / p2d: BASELINE configs[0] and the 2-D primitive-equation scheme; seeded states."""
+    import numpy as np
+    assert bench.WORKLOADS_2D["c1"][:3] == ("sw2d", 64, 64) and bench.WORKLOADS_2D["c1dt700"][3] == 700.0
+    assert "configs[0]" in bench.WORKLOADS_2D["c1"][5]
+    u, v, h = bench._state_2d("sw2d", 8, 8)
+    assert h.shape == (8, 8) and np.all(h == 8000.0) and abs(u[4, 4]) > 0.5
+    s = bench._state_2d("pe2d", 6, 10)
+    assert len(s) == 5 and all(a.shape == (6, 10) for a in s)
+    t, out = bench._cpu_2d("sw2d", 8, 8, 300.0, 300e3, 2)
+    assert t > 0 and all(np.isfinite(a).all() for a in out)
