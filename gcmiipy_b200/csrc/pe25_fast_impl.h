@@ -952,8 +952,7 @@ pe25f_update_cell_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, Pf
 // TI: tile width = 32, or 36 (the 36-wide ensemble members: one tile spans the row, both seams in the same tile)
 // PARTS: pit comes as NP partial sums of conv, one per layer pair (the aflux pass fused into the filter kernel, MODE 2),
 // in the sd work field; pit = their sum in pair order, p_n = p - pit dt (dynamics.py:39-40, :193-194) are formed here
-// SAME: base == star (the predictor): the cell's own u, v, t, q are the staged centre values, no second read
-template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ), int TI = PFT_TI, bool PARTS = false, bool SAME = false>
+template <int L, int PFT_TJ, int MB = 512 / (PFT_TI * PFT_TJ), int TI = PFT_TI, bool PARTS = false>
 __global__ void __launch_bounds__(TI * PFT_TJ, MB)
 pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, PfWork w, double dt, GcmRowSeg seg,
                           size_t bstride2, size_t bstride3) {
@@ -1023,11 +1022,9 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     }
     gcm_cp_async_commit();
   };
-  constexpr bool same = SAME;
   for (int k = 0; k < pfd && k < L; ++k) {
 #pragma unroll
-    for (int f = 6; f < 12; ++f)
-      if (f < 8 || !same) gcm_prefetch_l1(fld[f] + k * plane + e_c);
+    for (int f = 6; f < 12; ++f) gcm_prefetch_l1(fld[f] + k * plane + e_c);
   }
   // layers 0 .. NS-2 are issued up front; iteration k then issues layer k + NS - 1 into the stage layer k - 1 left
 #pragma unroll
@@ -1101,20 +1098,12 @@ pe25f_update_tiled_kernel(GcmGeomDev g, PfConst base, PfConst star, PfMut out, P
     // this cell's pgf, fv, u, v, t, q: read once, straight from global memory, consumed at the end of the layer;
     // their lines are asked into L1 two layers ahead (no register, no scoreboard)
     const int e = k * plane + e_c;
-    // (predictor: base == star, the cell's own u, v, t, q are the staged centre values -- no second read)
     if (k + pfd < L) {
-      gcm_prefetch_l1(fld[6] + e + pfd * plane);
-      gcm_prefetch_l1(fld[7] + e + pfd * plane);
-      if (!same) {
 #pragma unroll
-        for (int f = 8; f < 12; ++f) gcm_prefetch_l1(fld[f] + e + pfd * plane);
-      }
+      for (int f = 6; f < 12; ++f) gcm_prefetch_l1(fld[f] + e + pfd * plane);
     }
-    const double own_pgf = fld[6][e], own_fv = fld[7][e];
-    double own_u = u_k, own_v = v_k, own_t = t_k, own_q = q_k;
-    if (!same) {
-      own_u = fld[8][e]; own_v = fld[9][e]; own_t = fld[10][e]; own_q = fld[11][e];
-    }
+    const double own_pgf = fld[6][e], own_fv = fld[7][e], own_u = fld[8][e], own_v = fld[9][e], own_t = fld[10][e],
+                 own_q = fld[11][e];
     // horizontal neighbours from the tile
     const double* su_ = sk + 0 * TILE + t_c;
     const double* sv_ = sk + 1 * TILE + t_c;
@@ -1666,9 +1655,6 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
     const GcmRowSeg parts[2] = {{segU.a, segU.n1, 0, 0}, {segU.c, segU.n2, 0, 0}};
     constexpr int tj = 4;  // tile height (8 measured slower on B200: r02a)
     const int ti = tile36 ? 36 : PFT_TI;
-    // predictor (base == star): the variant that takes the cell's own values from the staged tile (knob 5 = 9: off)
-    const bool same_state = base->u == star->u && base->v == star->v && base->t == star->t && base->q == star->q &&
-                            g_gcm_knob[5] != 9;
     const size_t smt = (size_t)PFT_NS * PFT_NF * (tj + 2) * (ti + 4) * sizeof(double);
     for (int s2 = 0; s2 < 2; ++s2) {
       if (parts[s2].n1 <= 0) continue;
@@ -1679,8 +1665,6 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
           GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36, true>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
         else if (mbu == 4)  // 4 CTAs of 144 threads per SM at 112 registers instead of 3 at 128
           GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 4, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
-        else if (same_state)
-          GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36, false, true>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
         else
           GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 3, 36>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       } else if (fuse_aflux) {
@@ -1690,9 +1674,7 @@ static int pf_half_step(const gcm_geom* g, const gcm_state* base, const gcm_stat
           if (mbu == 5) GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 5>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
           else GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 6>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
         }
-      } else if (same_state)
-        GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj, 4, PFT_TI, false, true>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
-      else
+      } else
         GCM_LAUNCH_DEP((pe25f_update_tiled_kernel<L, tj>), gridt, blockt, smt, stream, d, cb, cs, mo, w, dt, parts[s2], b2, b3);
       GCM_CHECK_LAUNCH();
     }
