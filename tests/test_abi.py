@@ -102,3 +102,19 @@ def test_band_entry_points_reject_bad_geometry(backend):
     rc = lib.gcm_pe25_matsuno_step_host(band.dg.handle, ctypes.byref(hs), ctypes.byref(hs), ctypes.byref(bc),
                                         ctypes.byref(bc), ctypes.byref(bn), 1.0, 0, _host.ptr(wsb), needb, _lib.stream())
     assert rc == -4                                                      # band geometry: not a whole grid
+
+
+def test_sass_shows_tma_and_mbarrier_instructions():
+    """The built sm_100a library carries the Blackwell-native load path: cp.async.bulk.tensor -> UTMALDG (update kernel on
+    TMA box loads), cp.async.bulk -> UBLKCP (pipelined filter), mbarrier -> SYNCS.*, and the LDGSTS (cp.async) path of the
+    default update kernel.  Needs cuobjdump (CUDA toolkit) and the built library; no GPU."""
+    import shutil
+    import subprocess
+    from gcmiipy_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not here")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper() or "sm_100" in sass
+    for mnemonic in ("UTMALDG.3D", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "LDGSTS"):
+        assert mnemonic in sass, mnemonic
