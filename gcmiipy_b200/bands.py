@@ -237,6 +237,16 @@ class BandStepper:
         lo, hi = self.dg.row_lo, self.dg.row_hi
         return tuple(x.narrow(x.dim() - 2, lo, hi - lo) for x in self.cur)
 
+    def solar_timestep(self, gt, dt, utc):
+        """The column physics of no_limits_2_5d.solar_timestep (no_limits_2_5d.py:66-75) on this rank's band: the columns
+        are independent, so every rank runs `gcm_solar_timestep` on its stored rows and no communication is needed
+        (halo rows are recomputed from the neighbours' rows by the next exchange).  gt: ground temperature of the stored
+        rows [rows, W] (device tensor or array); theta of the band is replaced, the new ground temperature returned."""
+        from . import grey_solar
+        t_n, gt_n = grey_solar.solar_timestep(self.cur[3], self.cur[0], _host.dev(gt), dt, utc, self.geom, dg=self.dg)
+        self.cur[3].copy_(_host.dev(t_n))
+        return gt_n
+
     def diagnostics(self):
         """The STATS diagnostics of no_limits_2_5d.full_timestep (no_limits_2_5d.py:85-88) over the whole grid:
         {"u_max", "u_min", "v_max", "v_min", "nonfinite"} -- `gcm_diag_minmax` on the rows this rank owns, then one

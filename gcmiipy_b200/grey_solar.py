@@ -50,10 +50,18 @@ def _tables(geom, dg):
     if tabs is None:
         lat = np.asarray(_host.magnitude(geom.lat), dtype=np.float64).reshape(-1)
         lon = np.asarray(_host.magnitude(geom.long), dtype=np.float64).reshape(-1)
+        if getattr(dg, "rows", None) is not None:      # a latitude band: the stored rows' latitudes (halo rows included)
+            lat = lat[np.asarray(dg.rows)]
         mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(_lib.device())
         tabs = (mk(np.sin(lat)), mk(np.cos(lat)), mk(lon))
         dg._solar_tabs = tabs
     return tabs
+
+
+def _ground_temperature(g):
+    """g: GroundVars (no_limits_2_5d.py:143: gt, gw, snow, ice) or the ground temperature array / tensor itself (a torch
+    tensor has a `.gt` METHOD, so the namedtuple is recognised by its fields)."""
+    return g.gt if "gt" in getattr(g, "_fields", ()) else g
 
 
 def _layer_arrays(t_lw, t_sw, geom):
@@ -65,7 +73,7 @@ def basic_grey_radiation(p, tp, tt, g, t_lw, t_sw, albedo, utc, geom):
     """grey_solar.py:358-563: the basic grey atmosphere of AD 2.7 -> (dT/dt [L, H, W] in K/s, d(ground T)/dt [H, W]).
     p: surface pressure, tp: layer pressures (unused, as in the reference), tt: true temperature, g: GroundVars (or the
     ground temperature itself)."""
-    gt = g.gt if hasattr(g, "gt") else g
+    gt = _ground_temperature(g)
     fam = _host.Family(p, tt, gt)
     dg = device_geom(geom)
     dp, dtt, dgt = (_host.dev(x).contiguous() for x in (p, tt, gt))
@@ -81,12 +89,14 @@ def basic_grey_radiation(p, tp, tt, g, t_lw, t_sw, albedo, utc, geom):
     return fam.out(dTdt, "kelvin / second"), fam.out(dtg, "kelvin / second")
 
 
-def solar_timestep(t, p, g, dt, utc, geom, t_lw=0.1, t_sw=0.9, albedo=0.3):
+def solar_timestep(t, p, g, dt, utc, geom, t_lw=0.1, t_sw=0.9, albedo=0.3, dg=None):
     """no_limits_2_5d.solar_timestep (no_limits_2_5d.py:66-75) in one launch: theta -> T, radiation, explicit update
-    of the air and ground temperatures over dt, T -> theta.  Returns (theta_n, ground temperature_n)."""
-    gt = g.gt if hasattr(g, "gt") else g
+    of the air and ground temperatures over dt, T -> theta.  Returns (theta_n, ground temperature_n).
+    dg: the device geometry of a latitude band (bands.BandStepper.dg) -- the columns are independent, so a band runs
+    the same kernel on its stored rows (arrays shaped like the band)."""
+    gt = _ground_temperature(g)
     fam = _host.Family(t, p, gt)
-    dg = device_geom(geom)
+    dg = dg if dg is not None else device_geom(geom)
     dt_, dp, dgt = (_host.dev(x).contiguous() for x in (t, p, gt))
     L, H, W = dg.L, dg.H, dg.W
     assert tuple(dt_.shape) == (L, H, W) and tuple(dp.shape) == (H, W) and tuple(dgt.shape) == (H, W)

@@ -133,3 +133,25 @@ def test_run_over_hansen_topography_golden(backend):
     for name, a, b in zip("puvtq", st.download(), ref):
         scale = suv if name in "uv" else np.max(np.abs(b))
         assert np.max(np.abs(a - b)) / scale <= 1e-11, name
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_band_solar_timestep_matches_whole_grid(backend, world):
+    """f4 under the latitude-band layout ("trivially shardable"): every band runs the column physics on its
+    stored rows with its own latitudes; owned rows equal the whole-grid result bit for bit."""
+    import torch
+    from gcmiipy_b200 import bands
+    H, W, L = 24, 36, 9
+    geom = geometry.gen_geometry(H, W, L)
+    s = O.synthetic_state(O.gen_geometry(H, W, L), seed=21)
+    gt = 280.0 + 12.0 * np.random.default_rng(2).random((H, W))
+    utc = 9.25 * HOURS
+    t_ref, gt_ref = grey_solar.solar_timestep(s[3], s[0], gt, 600.0, utc, geom)
+    for rank in range(world):
+        b = bands.BandStepper(geom, *s, rank=rank, world=world, native=False)
+        rows = np.asarray(b.dg.rows)
+        gt_n = b.solar_timestep(torch.from_numpy(np.ascontiguousarray(gt[rows])), 600.0, utc)
+        lo, hi = b.dg.row_lo, b.dg.row_hi
+        assert np.array_equal(b.cur[3].cpu().numpy()[:, lo:hi, :], t_ref[:, b.j0:b.j1, :])
+        gt_n = gt_n.cpu().numpy() if hasattr(gt_n, "cpu") else gt_n
+        assert np.array_equal(gt_n[lo:hi], gt_ref[b.j0:b.j1])
