@@ -150,11 +150,13 @@ int gcm_pe25_matsuno_step_host_pipelined(const gcm_geom* g, const gcm_state* h_i
                                          size_t workspace_bytes, void* stream);
 int gcm_host_pipe_join(void* stream);
 
-/* Kernel path of the half step: 0 (default) = the fused kernels of pe25_fast.cu whenever the geometry allows
- * (L in {3, 9}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
+/* Kernel path of the half step: 0 (default) = the fused kernels of pe25_fast_impl.h whenever the geometry allows
+ * (L in {3, 9, 17, 18}, W a product of 2, 3, 5), else the general 4-kernel path; 1 = always the general path (A/B
  * comparisons, widths with other prime factors). */
 int gcm_pe25_select_path(int path);
-/* launch-shape tuning knobs of the fused kernels (idx 0..9, see pe25_fast.cu); 0 = automatic */
+/* launch-shape / kernel-choice tuning knobs of the fused kernels (idx 0..23, listed in pe25_fast.cu); 0 = automatic.
+ * They select between measured alternatives (e.g. 4 = 5: the TMA update kernel, 14 = 2: the pipelined filter, 7 = 3: the
+ * marching hydro kernel) and never change results beyond the last bits; GCM_ESHAPE for an unknown index. */
 int gcm_tuning_knob(int idx, int value);
 
 /* Opt-in terms of the 2.5-D half step.  All OFF by default: the step is then the
