@@ -28,6 +28,7 @@ struct GcmHostPipe {
   cudaEvent_t ev_start, ev_in[GCM_HOST_MAX_BLOCKS + 1], ev_done[GCM_HOST_MAX_BLOCKS], ev_out;
   cudaEvent_t ev_outb[GCM_HOST_MAX_BLOCKS];  // block b of the newest pipelined call has reached the host
   int outb_valid;                            // ev_outb[] have been recorded at least once
+  int outb_blocks, outb_rows;                // block partition (nblocks, H) the recorded ev_outb[] belong to
   int pending;                               // a pipelined call has not been joined yet
 };
 
@@ -188,6 +189,12 @@ extern "C" int gcm_pe25_matsuno_step_host_pipelined(const gcm_geom* g, const gcm
   const int s0 = wrapb(start_block);
   GCM_CUDA(cudaEventRecord(pp->ev_start, main));  // everything the caller queued before (incl. the previous compute)
   GCM_CUDA(cudaStreamWaitEvent(pp->q_in, pp->ev_start, 0));
+  if (pp->outb_valid && (pp->outb_blocks != nblocks || pp->outb_rows != H)) {
+    // the previous pipelined call cut another grid or other blocks: its per-block events do not describe these rows;
+    // wait for all of its copy-outs instead
+    GCM_CUDA(cudaStreamWaitEvent(pp->q_in, pp->ev_out, 0));
+    pp->outb_valid = 0;
+  }
   // copy-in, blocks s0 - 1, s0, s0 + 1, ... : block x waits for the previous call's copy-out of block x
   for (int k = 0; k < nblocks; ++k) {
     const int x = wrapb(s0 - 1 + k);
@@ -216,6 +223,8 @@ extern "C" int gcm_pe25_matsuno_step_host_pipelined(const gcm_geom* g, const gcm
   }
   GCM_CUDA(cudaEventRecord(pp->ev_out, pp->q_out));
   pp->outb_valid = 1;
+  pp->outb_blocks = nblocks;
+  pp->outb_rows = H;
   pp->pending = 1;
   return GCM_OK;
 #endif
