@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "gcm_common.h"
@@ -29,8 +30,10 @@ unsigned int* gcm_nonfinite_word() {
   return &word;
 #else
   static unsigned int* words[64] = {nullptr};
+  static std::mutex mu;  // two threads may create their first geometry at the same time
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   if (!words[dev]) {
     unsigned int* w = nullptr;
     if (cudaMalloc((void**)&w, 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -108,6 +108,8 @@ class Stepper:
             dst.copy_(_host.dev(src), non_blocking=True)
 
     def step(self, dt, nsteps=1):
+        if getattr(self, "_pipe", None) is not None:
+            self.host_join()        # pending copy-outs of pipelined host steps read the buffers this step writes
         ws, need = _workspace(self.dg, self.nbatch, self)
         sin, sout = _struct(self.cur), _struct(self.nxt)
         _lib.check(_lib.lib().gcm_pe25_matsuno_step(self.dg.handle, ctypes.byref(sin), ctypes.byref(sout),
